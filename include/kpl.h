@@ -1,0 +1,164 @@
+/*
+ * kpl.h -- C ABI of the B200-native Keypoint-Learning detection path (libkpl_b200.so).
+ *
+ * This is the drop-in boundary.  Every entry point replaces one piece of the reference's
+ * pcl::keypoints::KeypointLearningDetector / TestDetector path; the citations (file:line) are
+ * into the reference tree (CVLAB-Unibo/Keypoint-Learning).  Plain C, POD only, no torch / PCL /
+ * OpenCV types.  All functions return KPL_OK (0) or a KPL_E_* code; the message of the last
+ * failure on a context is available through kpl_last_error().  There is no CPU fallback: every
+ * compute entry point fails with KPL_E_CUDA when no sm_100 device is usable.
+ *
+ * Threading: one context per host thread / per GPU; calls on one context must be serialised by
+ * the caller (the reference detector is equally non-reentrant, include/KeypointLearning.h:180-204).
+ * Ownership: input pointers are borrowed for the duration of the call; outputs are caller
+ * allocated; the context owns all device memory and releases it in kpl_destroy().
+ */
+#ifndef KPL_B200_H_
+#define KPL_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define KPL_API
+#else
+#define KPL_API __attribute__((visibility("default")))
+#endif
+
+typedef struct kpl_ctx kpl_ctx;
+
+enum kpl_status {
+    KPL_OK = 0,
+    KPL_E_INVALID = 1,        /* bad argument / parameter combination                                   */
+    KPL_E_FOREST = 2,         /* forest missing, unreadable or empty  (loadForest -> false, hpp:165-174)  */
+    KPL_E_SIZE_MISMATCH = 3,  /* normals/points size mismatch         (initCompute -> false, hpp:149-153) */
+    KPL_E_NONFINITE = 4,      /* non-finite point or query normal: the reference mis-aligns its response
+                                 cloud in that case (hpp:277-290 vs :203-253); we refuse instead          */
+    KPL_E_VARCOUNT = 5,       /* annuli*bins != forest var_count                                          */
+    KPL_E_CUDA = 6,           /* CUDA runtime failure or no usable device                                 */
+    KPL_E_GRID = 7,           /* uniform grid would exceed 2^31-2 cells / point outside a forced grid     */
+    KPL_E_NOMEM = 8,
+    KPL_E_IO = 9,
+    KPL_E_UNSUPPORTED = 10
+};
+
+enum kpl_normals_mode {
+    KPL_NORMALS_GIVEN = 0,   /* setNormals() was called                      (KeypointLearning.h:108-109)       */
+    KPL_NORMALS_KNN = 1,     /* pcl::NormalEstimation::setKSearch(k)         (main_test_detector.cpp:162-169)    */
+    KPL_NORMALS_RADIUS = 2   /* NormalEstimation::setRadiusSearch(r_feat)    (impl/KeypointLearning.hpp:130-137) */
+};
+
+/* Per-point roles for slab-sharded clouds (no counterpart in the reference, which is single process). */
+enum kpl_role { KPL_ROLE_HALO = 0, KPL_ROLE_SCORE = 1, KPL_ROLE_OWNED = 3 };
+
+/* Mirrors the detector's setters (include/KeypointLearning.h:81-90,102-155) and the TestDetector
+ * command line (src/main_test_detector.cpp:53-91,105-106). */
+typedef struct kpl_params {
+    float radius_features;    /* setRadiusSearch          default 20   (main_test_detector.cpp:65)   */
+    float radius_nms;         /* setNonMaxRadius          default 4    (:66)                         */
+    double threshold;         /* setPredictionThreshold   default (double)0.85f (:67)                */
+    int32_t n_annulus;        /* setNAnnulus              default 5    (:105)                        */
+    int32_t n_bins;           /* setNBins                 default 10   (:106)                        */
+    int32_t non_maxima;       /* setNonMaxima             default 1                                  */
+    int32_t draws_remove;     /* setNonMaximaDrawsRemove  default 0 in TestDetector (:128)           */
+    float draws_threshold;    /* setNonMaximaDrawsThreshold (uninitialised in the reference; 0 here) */
+    int32_t normals_mode;     /* enum kpl_normals_mode, used when no normals are passed              */
+    int32_t k_normals;        /* 10 (main_test_detector.cpp:167)                                     */
+    float viewpoint[3];       /* PCD VIEWPOINT / sensor_origin_, (0,0,0)                             */
+    int32_t flip_normals;     /* --flipNormals (:173-179), applied to normals computed here          */
+    int32_t cells_per_radius; /* grid resolution: cell = r_feat*(1+2^-20)/cells_per_radius, default 4 */
+    int32_t grid_forced;      /* 1: use grid_origin/grid_dims below (slab of a larger cloud)         */
+    double grid_origin[3];
+    int32_t grid_dims[3];
+} kpl_params;
+
+/* Device-time breakdown of the last detect call (CUDA events on the context stream), ms. */
+typedef struct kpl_timings {
+    float grid_ms, normals_ms, features_ms, forest_ms, nms_ms, total_ms;
+} kpl_timings;
+
+/* Exact work counters of the last detect call (used for the roofline byte model). */
+typedef struct kpl_stats {
+    int64_t n_points;         /* points in the call                                   */
+    int64_t n_scored;         /* points that received a score                         */
+    int64_t feature_pairs;    /* sum over scored points of voting neighbours (self excluded) */
+    int64_t candidate_pairs;  /* distance tests executed by the feature kernel        */
+    int64_t n_above_threshold;
+    int64_t n_keypoints;
+    int64_t grid_cells;
+    int32_t grid_dims[3];
+    int32_t kernel_launches;  /* kernels launched by the last call                    */
+    double grid_origin[3];
+    double grid_cell;
+} kpl_stats;
+
+/* ---- lifetime ------------------------------------------------------------------------------- */
+KPL_API int kpl_create(int device, kpl_ctx** out);            /* new KeypointLearningDetector (main_test_detector.cpp:123) */
+KPL_API void kpl_destroy(kpl_ctx* ctx);                       /* ~KeypointLearningDetector   (KeypointLearning.h:93-97)    */
+KPL_API const char* kpl_last_error(const kpl_ctx* ctx);
+KPL_API const char* kpl_version(void);
+KPL_API int kpl_set_stream(kpl_ctx* ctx, void* cuda_stream);  /* run on a caller-owned cudaStream_t (NULL: context stream)  */
+
+/* ---- parameters ----------------------------------------------------------------------------- */
+KPL_API int kpl_params_default(kpl_params* p);                /* ctor defaults + TestDetector values                        */
+KPL_API int kpl_set_params(kpl_ctx* ctx, const kpl_params* p);
+KPL_API int kpl_get_params(const kpl_ctx* ctx, kpl_params* p);
+
+/* ---- forest --------------------------------------------------------------------------------- */
+/* loadForest(path): opencv_ml_rtrees YAML or YAML.gz -> flat device arrays (impl/KeypointLearning.hpp:159-176). */
+KPL_API int kpl_load_forest(kpl_ctx* ctx, const char* path);
+/* Same from already-flattened host arrays: node i is a leaf iff var[i] < 0; go left iff x[var] <= thr. */
+KPL_API int kpl_set_forest(kpl_ctx* ctx, int32_t ntrees, int32_t nnodes, const int32_t* roots, const int32_t* var,
+                           const float* thr, const int32_t* left, const int32_t* right, const float* value,
+                           int32_t var_count);
+KPL_API int kpl_forest_info(const kpl_ctx* ctx, int32_t* ntrees, int32_t* nnodes, int32_t* var_count, int32_t* max_depth);
+
+/* ---- the hot path, host buffers (what detector->compute() binds to) --------------------------- */
+/* xyz: n points, 3 floats each at xyz_stride bytes (16 = pcl::PointXYZ, 12 = packed).
+ * normals: NULL (estimate per params.normals_mode) or n normals, 3 floats each at normals_stride bytes
+ *          (32 = pcl::Normal).  role: NULL or n bytes of enum kpl_role.
+ * scores_out: NULL or n floats (forest response, impl/KeypointLearning.hpp:287; NaN for unscored roles).
+ * kp_idx_out: capacity n int32, ascending indices of the keypoints (keypoints_indices_, hpp:252-253).  */
+KPL_API int kpl_detect(kpl_ctx* ctx, const float* xyz, int32_t xyz_stride, const float* normals, int32_t normals_stride,
+                       const uint8_t* role, int64_t n, float* scores_out, int32_t* kp_idx_out, int64_t* n_kp_out);
+
+/* pcl::NormalEstimation::compute as TestDetector uses it (main_test_detector.cpp:162-169):
+ * normals_out = n x (nx, ny, nz, curvature). Mode / k / viewpoint / flip come from the params. */
+KPL_API int kpl_normals(kpl_ctx* ctx, const float* xyz, int32_t xyz_stride, int64_t n, float* normals_out);
+
+/* computePointsForTrainingFeatures (impl/KeypointLearning.hpp:299-318): rows of A*B floats for the
+ * m given point indices (NULL: all points, m == n). */
+KPL_API int kpl_features(kpl_ctx* ctx, const float* xyz, int32_t xyz_stride, const float* normals, int32_t normals_stride,
+                         int64_t n, const int32_t* indices, int64_t m, float* features_out);
+
+/* searchForNeighbors / tree_->radiusSearch semantics (hpp:213,334): per point the number of
+ * neighbours with d2 < (float)(r*r) (self included) and the wrapping 64-bit sum of
+ * (index+1)*0x9E3779B97F4A7C15 over them; either output may be NULL. */
+KPL_API int kpl_radius_stats(kpl_ctx* ctx, const float* xyz, int32_t xyz_stride, int64_t n, double radius,
+                             int32_t* counts_out, uint64_t* hash_out);
+/* Explicit neighbour lists (ascending index) of m query points; two-call protocol:
+ * indices_out == NULL fills offsets_out[m+1] only. */
+KPL_API int kpl_radius_neighbors(kpl_ctx* ctx, const float* xyz, int32_t xyz_stride, int64_t n, double radius,
+                                 const int32_t* queries, int64_t m, int64_t* offsets_out, int32_t* indices_out);
+
+/* ---- the hot path, device-resident buffers (inputs already in HBM; outputs stay there) -------- */
+/* d_xyz4: n float4 (x,y,z,*).  d_normals4: NULL or n float4 (nx,ny,nz,*).  d_role: NULL or n bytes.
+ * d_scores: NULL or n floats.  d_kp_idx: n int32.  The call enqueues on the context stream and
+ * synchronises once at the end to return n_kp. */
+KPL_API int kpl_detect_device(kpl_ctx* ctx, const void* d_xyz4, const void* d_normals4, const void* d_role, int64_t n,
+                              void* d_scores, void* d_kp_idx, int64_t* n_kp_out);
+
+/* ---- introspection --------------------------------------------------------------------------- */
+KPL_API int kpl_get_timings(const kpl_ctx* ctx, kpl_timings* t);
+KPL_API int kpl_get_stats(const kpl_ctx* ctx, kpl_stats* s);
+/* Device copies of intermediate results of the last call, for parity tests: what = "normals"
+ * (n x 4 floats, original order) or "features" (n x A*B floats, original order). */
+KPL_API int kpl_fetch(kpl_ctx* ctx, const char* what, float* out, int64_t capacity_floats);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KPL_B200_H_ */

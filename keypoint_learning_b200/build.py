@@ -1,0 +1,96 @@
+"""In-tree build of libkpl_b200.so (CUDA kernels + C ABI) and the C++ host tools, sm_100a only.
+
+nvcc cross-compiles without a GPU.  -fmad=false is part of the arithmetic contract of the hot path
+(see csrc/kpl_math.cuh), not an optimisation switch.
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+CSRC = os.path.join(HERE, "csrc")
+HOST = os.path.join(HERE, "host")
+LIB = os.path.join(HERE, "libkpl_b200.so")
+TEST_DETECTOR = os.path.join(HERE, "TestDetector")
+
+CU_SOURCES = ["capi.cu", "grid.cu", "normals.cu", "features.cu", "forest.cu", "nms.cu", "forest_yaml.cpp"]
+NVCC_FLAGS = [
+    "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-fmad=false",
+    "-Xcompiler", "-fPIC,-fvisibility=hidden,-O2", "--expt-relaxed-constexpr", "-cudart", "static",
+]
+
+
+def _nvcc() -> str:
+    for cand in (shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found")
+
+
+def _host_cxx() -> str:
+    # the image exports CXX=/opt/gcc/bin/g++ (a wrapper); the distro compiler is the reliable one
+    return "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else (shutil.which("g++") or "g++")
+
+
+def _stale(target: str, deps: list[str]) -> bool:
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
+
+
+def build_lib(force: bool = False, verbose: bool = False) -> str:
+    srcs = [os.path.join(CSRC, s) for s in CU_SOURCES]
+    deps = srcs + [os.path.join(CSRC, h) for h in ("kpl_internal.h", "kpl_math.cuh")] + [os.path.join(ROOT, "include", "kpl.h"), __file__]
+    if not force and not _stale(LIB, deps):
+        return LIB
+    objdir = os.path.join(HERE, "build")
+    os.makedirs(objdir, exist_ok=True)
+    objs = []
+    procs = []
+    for s in srcs:
+        o = os.path.join(objdir, os.path.basename(s) + ".o")
+        objs.append(o)
+        cmd = [_nvcc(), *NVCC_FLAGS, "-ccbin", _host_cxx(), "-x", "cu", "-c", s, "-o", o]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+        procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    for cmd, p in procs:
+        out, _ = p.communicate()
+        if verbose or p.returncode:
+            sys.stderr.write(out)
+        if p.returncode:
+            raise RuntimeError("nvcc failed: " + " ".join(cmd))
+    link = [_nvcc(), "-shared", "-o", LIB, *objs, "-ccbin", _host_cxx(), "-gencode", "arch=compute_100a,code=sm_100a",
+            "-cudart", "static", "-lz", "-Xlinker", "--no-undefined"]
+    subprocess.check_call(link)
+    return LIB
+
+
+def build_host(force: bool = False) -> str:
+    """C++ facade + TestDetector CLI (links against libkpl_b200.so with an $ORIGIN rpath)."""
+    main = os.path.join(HOST, "main_test_detector.cpp")
+    if not os.path.exists(main):
+        return ""
+    deps = [os.path.join(HOST, f) for f in os.listdir(HOST)] + [LIB]
+    if not force and not _stale(TEST_DETECTOR, deps):
+        return TEST_DETECTOR
+    srcs = [os.path.join(HOST, f) for f in sorted(os.listdir(HOST)) if f.endswith(".cpp")]
+    cmd = [_host_cxx(), "-O2", "-std=c++17", "-Wall", "-Wextra", "-I", os.path.join(ROOT, "include"), "-I", HOST, *srcs,
+           "-o", TEST_DETECTOR, "-L", HERE, "-lkpl_b200", "-Wl,-rpath,$ORIGIN"]
+    subprocess.check_call(cmd)
+    return TEST_DETECTOR
+
+
+def build_all(force: bool = False, verbose: bool = False) -> None:
+    build_lib(force, verbose)
+    build_host(force)
+
+
+if __name__ == "__main__":
+    build_all(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    print(LIB)

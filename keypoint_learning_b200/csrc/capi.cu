@@ -1,0 +1,527 @@
+// capi.cu -- the extern "C" surface declared in include/kpl.h and the stage orchestration.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+#include "kpl_internal.h"
+
+namespace kpl {
+int pack_forest(const HostForestArrays& in, std::vector<PackedNode>& nodes, std::vector<int32_t>& roots, int& max_depth, std::string& err);
+cudaError_t launch_all_flags(kpl_ctx* c, int64_t n);
+}
+using namespace kpl;
+
+#define KPL_CUDA(call)                                                                              \
+    do {                                                                                            \
+        cudaError_t e__ = (call);                                                                   \
+        if (e__ != cudaSuccess) {                                                                   \
+            char b__[512];                                                                          \
+            snprintf(b__, sizeof b__, "%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+            ctx->err = b__;                                                                         \
+            return e__ == cudaErrorMemoryAllocation ? KPL_E_NOMEM : KPL_E_CUDA;                     \
+        }                                                                                           \
+    } while (0)
+
+static int fail(kpl_ctx* ctx, int code, const std::string& msg)
+{
+    ctx->err = msg;
+    return code;
+}
+
+static float dec_float(uint32_t u)
+{
+    uint32_t b = (u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u;
+    float f;
+    memcpy(&f, &b, 4);
+    return f;
+}
+
+template <typename T>
+static void release(DevBuf<T>& b) { if (b.p) cudaFree(b.p); b.p = nullptr; b.cap = 0; }
+
+extern "C" {
+
+const char* kpl_version(void) { return "kpl-b200 0.1 (sm_100a)"; }
+
+int kpl_params_default(kpl_params* p)
+{
+    if (!p) return KPL_E_INVALID;
+    memset(p, 0, sizeof *p);
+    p->radius_features = 20.f;
+    p->radius_nms = 4.f;
+    p->threshold = (double)0.85f;
+    p->n_annulus = 5;
+    p->n_bins = 10;
+    p->non_maxima = 1;
+    p->draws_remove = 0;
+    p->draws_threshold = 0.f;
+    p->normals_mode = KPL_NORMALS_KNN;
+    p->k_normals = 10;
+    p->flip_normals = 0;
+    p->cells_per_radius = 4;
+    p->grid_forced = 0;
+    return KPL_OK;
+}
+
+int kpl_create(int device, kpl_ctx** out)
+{
+    if (!out) return KPL_E_INVALID;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || device < 0 || device >= count) return KPL_E_CUDA;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return KPL_E_CUDA;
+    if (prop.major != 10) return KPL_E_CUDA;   // sm_100a cubin only: no fallback path exists
+    if (cudaSetDevice(device) != cudaSuccess) return KPL_E_CUDA;
+    kpl_ctx* ctx = new (std::nothrow) kpl_ctx();
+    if (!ctx) return KPL_E_NOMEM;
+    ctx->device = device;
+    kpl_params_default(&ctx->params);
+    memset(&ctx->timings, 0, sizeof ctx->timings);
+    memset(&ctx->stats, 0, sizeof ctx->stats);
+    bool ok = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess;
+    ctx->stream = ctx->own_stream;
+    for (int i = 0; ok && i < 8; ++i) ok = cudaEventCreate(&ctx->ev[i]) == cudaSuccess;
+    ok = ok && cudaMalloc((void**)&ctx->d_bbox, 8 * sizeof(uint32_t)) == cudaSuccess;
+    ok = ok && ensure(ctx->counters, 8) == cudaSuccess;
+    if (!ok) { kpl_destroy(ctx); return KPL_E_CUDA; }
+    *out = ctx;
+    return KPL_OK;
+}
+
+void kpl_destroy(kpl_ctx* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->own_stream) cudaStreamSynchronize(ctx->own_stream);
+    release(ctx->in_xyz); release(ctx->in_nrm); release(ctx->in_role); release(ctx->s_role);
+    release(ctx->key_a); release(ctx->key_b); release(ctx->idx_a); release(ctx->idx_b); release(ctx->cub_tmp);
+    release(ctx->cell_start); release(ctx->s_pos); release(ctx->s_nrm); release(ctx->feat);
+    release(ctx->s_score); release(ctx->score); release(ctx->flag); release(ctx->kp_idx);
+    release(ctx->scratch_f); release(ctx->scratch_i); release(ctx->counters);
+    if (ctx->d_bbox) cudaFree(ctx->d_bbox);
+    if (ctx->forest.d_nodes) cudaFree(ctx->forest.d_nodes);
+    if (ctx->forest.d_roots) cudaFree(ctx->forest.d_roots);
+    for (int i = 0; i < 8; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+}
+
+const char* kpl_last_error(const kpl_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int kpl_set_stream(kpl_ctx* ctx, void* s)
+{
+    if (!ctx) return KPL_E_INVALID;
+    ctx->stream = s ? (cudaStream_t)s : ctx->own_stream;
+    return KPL_OK;
+}
+
+int kpl_set_params(kpl_ctx* ctx, const kpl_params* p)
+{
+    if (!ctx || !p) return KPL_E_INVALID;
+    if (!(p->radius_features > 0.f) || !std::isfinite(p->radius_features)) return fail(ctx, KPL_E_INVALID, "radius_features must be > 0");
+    if (p->radius_nms < 0.f || !std::isfinite(p->radius_nms)) return fail(ctx, KPL_E_INVALID, "radius_nms must be >= 0");
+    if (p->n_annulus < 1 || p->n_bins < 1 || (int64_t)p->n_annulus * p->n_bins > 1022) return fail(ctx, KPL_E_INVALID, "annuli*bins must be in [1,1022]");
+    if (p->normals_mode < 0 || p->normals_mode > 2) return fail(ctx, KPL_E_INVALID, "bad normals_mode");
+    if (p->k_normals < 1 || p->k_normals > 64) return fail(ctx, KPL_E_INVALID, "k_normals must be in [1,64]");
+    if (p->cells_per_radius < 1 || p->cells_per_radius > 16) return fail(ctx, KPL_E_INVALID, "cells_per_radius must be in [1,16]");
+    if (p->draws_remove && p->non_maxima) return fail(ctx, KPL_E_UNSUPPORTED, "non_maxima_draws_remove is not implemented (off in TestDetector)");
+    ctx->params = *p;
+    return KPL_OK;
+}
+
+int kpl_get_params(const kpl_ctx* ctx, kpl_params* p)
+{
+    if (!ctx || !p) return KPL_E_INVALID;
+    *p = ctx->params;
+    return KPL_OK;
+}
+
+static int install_forest(kpl_ctx* ctx, const HostForestArrays& H)
+{
+    std::vector<PackedNode> nodes;
+    std::vector<int32_t> roots;
+    int max_depth = 0;
+    std::string err;
+    int rc = pack_forest(H, nodes, roots, max_depth, err);
+    if (rc) return fail(ctx, rc, err);
+    if (roots.empty()) return fail(ctx, KPL_E_FOREST, "forest has no trees");
+    KPL_CUDA(cudaSetDevice(ctx->device));
+    Forest& F = ctx->forest;
+    if (F.d_nodes) cudaFree(F.d_nodes);
+    if (F.d_roots) cudaFree(F.d_roots);
+    F.d_nodes = nullptr; F.d_roots = nullptr; F.ntrees = 0;
+    KPL_CUDA(cudaMalloc((void**)&F.d_nodes, nodes.size() * sizeof(PackedNode)));
+    KPL_CUDA(cudaMalloc((void**)&F.d_roots, roots.size() * sizeof(int32_t)));
+    KPL_CUDA(cudaMemcpy(F.d_nodes, nodes.data(), nodes.size() * sizeof(PackedNode), cudaMemcpyHostToDevice));
+    KPL_CUDA(cudaMemcpy(F.d_roots, roots.data(), roots.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    F.ntrees = (int32_t)roots.size(); F.nnodes = (int32_t)nodes.size(); F.var_count = H.var_count; F.max_depth = max_depth;
+    F.roots = roots;
+    return KPL_OK;
+}
+
+int kpl_load_forest(kpl_ctx* ctx, const char* path)
+{
+    if (!ctx || !path) return KPL_E_INVALID;
+    HostForestArrays H;
+    std::string err;
+    int rc = parse_forest_yaml(path, H, err);
+    if (rc) return fail(ctx, rc, err);
+    return install_forest(ctx, H);
+}
+
+int kpl_set_forest(kpl_ctx* ctx, int32_t ntrees, int32_t nnodes, const int32_t* roots, const int32_t* var, const float* thr,
+                   const int32_t* left, const int32_t* right, const float* value, int32_t var_count)
+{
+    if (!ctx || ntrees < 1 || nnodes < 1 || !roots || !var || !thr || !left || !right || !value) return KPL_E_INVALID;
+    HostForestArrays H;
+    H.roots.assign(roots, roots + ntrees); H.var.assign(var, var + nnodes); H.thr.assign(thr, thr + nnodes);
+    H.left.assign(left, left + nnodes); H.right.assign(right, right + nnodes); H.value.assign(value, value + nnodes);
+    H.var_count = var_count;
+    return install_forest(ctx, H);
+}
+
+int kpl_forest_info(const kpl_ctx* ctx, int32_t* ntrees, int32_t* nnodes, int32_t* var_count, int32_t* max_depth)
+{
+    if (!ctx) return KPL_E_INVALID;
+    if (ntrees) *ntrees = ctx->forest.ntrees;
+    if (nnodes) *nnodes = ctx->forest.nnodes;
+    if (var_count) *var_count = ctx->forest.var_count;
+    if (max_depth) *max_depth = ctx->forest.max_depth;
+    return KPL_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// stage orchestration (device pointers in, device results out)
+// ------------------------------------------------------------------------------------------------
+static int prepare_grid(kpl_ctx* ctx, const float4* d_xyz, const float4* d_nrm, const uint8_t* d_role, int64_t n)
+{
+    const kpl_params& P = ctx->params;
+    KPL_CUDA(launch_bbox(ctx, d_xyz, n, ctx->d_bbox));
+    uint32_t hb[8];
+    KPL_CUDA(cudaMemcpyAsync(hb, ctx->d_bbox, sizeof hb, cudaMemcpyDeviceToHost, ctx->stream));
+    KPL_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (hb[6]) return fail(ctx, KPL_E_NONFINITE, "input cloud holds non-finite points");
+    GridDesc& g = ctx->grid;
+    g.cell = (double)P.radius_features * (1.0 + 9.5367431640625e-07) / (double)P.cells_per_radius;
+    double ncells = 1.0;
+    for (int a = 0; a < 3; ++a) {
+        double lo = (double)dec_float(hb[a]), hi = (double)dec_float(hb[3 + a]);
+        if (P.grid_forced) { g.org[a] = P.grid_origin[a]; g.dim[a] = P.grid_dims[a]; }
+        else { g.org[a] = lo; g.dim[a] = (int32_t)std::min(2147483000.0, std::floor((hi - lo) / g.cell) + 1.0); }
+        if (g.dim[a] < 1) return fail(ctx, KPL_E_GRID, "bad grid dimensions");
+        ncells *= (double)g.dim[a];
+    }
+    if (ncells > 2147483646.0) return fail(ctx, KPL_E_GRID, "uniform grid would exceed 2^31-2 cells: cloud too sparse for radius_features/cells_per_radius");
+    g.ncells = (int64_t)ncells;
+    g.reach_feat = (int)std::floor((double)P.radius_features * (1.0 + 4.76837158203125e-07) / g.cell) + 1;
+    g.reach_nms = (int)std::floor((double)P.radius_nms * (1.0 + 4.76837158203125e-07) / g.cell) + 1;
+    ctx->cur_xyz = d_xyz;
+    ctx->cur_nrm = d_nrm;
+    KPL_CUDA(build_grid(ctx, d_xyz, d_nrm, d_role, n));
+    if (P.grid_forced) {
+        KPL_CUDA(cudaMemcpyAsync(hb, ctx->d_bbox, sizeof hb, cudaMemcpyDeviceToHost, ctx->stream));
+        KPL_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (hb[7]) return fail(ctx, KPL_E_GRID, "a point lies outside the forced grid");
+    }
+    ctx->stats.grid_cells = g.ncells;
+    for (int a = 0; a < 3; ++a) { ctx->stats.grid_dims[a] = g.dim[a]; ctx->stats.grid_origin[a] = g.org[a]; }
+    ctx->stats.grid_cell = g.cell;
+    ctx->last_n = n;
+    return KPL_OK;
+}
+
+static int prepare_normals(kpl_ctx* ctx, bool given, int64_t n)
+{
+    const kpl_params& P = ctx->params;
+    if (!given) {
+        if (P.normals_mode == KPL_NORMALS_KNN) KPL_CUDA(launch_normals_knn(ctx, n));
+        else if (P.normals_mode == KPL_NORMALS_RADIUS) {
+            cudaError_t e = launch_normals_radius(ctx, n);
+            if (e == cudaErrorNotSupported) return fail(ctx, KPL_E_UNSUPPORTED, "radius-mode normals are not implemented yet");
+            KPL_CUDA(e);
+        } else return fail(ctx, KPL_E_SIZE_MISMATCH, "normals_mode is GIVEN but no normals were passed");
+        if (P.flip_normals) KPL_CUDA(launch_flip_normals(ctx, n));
+    }
+    ctx->last_has_normals = true;
+    return KPL_OK;
+}
+
+static void begin_call(kpl_ctx* ctx)
+{
+    ctx->launches = 0;
+    ctx->err.clear();
+    ctx->last_has_normals = ctx->last_has_features = false;
+    memset(&ctx->timings, 0, sizeof ctx->timings);
+    memset(&ctx->stats, 0, sizeof ctx->stats);
+}
+
+static int run_detect(kpl_ctx* ctx, const float4* d_xyz, const float4* d_nrm, const uint8_t* d_role, int64_t n,
+                      float* d_scores_out, int32_t* d_kp_out, int64_t* n_kp_out)
+{
+    const kpl_params& P = ctx->params;
+    begin_call(ctx);
+    if (n_kp_out) *n_kp_out = 0;
+    if (n < 0 || n > 2147483000ll) return fail(ctx, KPL_E_INVALID, "point count out of range");
+    if (ctx->forest.ntrees < 1) return fail(ctx, KPL_E_FOREST, "no forest loaded");
+    const int F = P.n_annulus * P.n_bins;
+    if (ctx->forest.var_count > 0 && ctx->forest.var_count != F) return fail(ctx, KPL_E_VARCOUNT, "annuli*bins does not match the forest's var_count");
+    ctx->stats.n_points = n;
+    if (n == 0) return KPL_OK;
+    KPL_CUDA(cudaSetDevice(ctx->device));
+    KPL_CUDA(cudaMemsetAsync(ctx->counters.p, 0, 8 * sizeof(unsigned long long), ctx->stream));
+    KPL_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
+    int rc = prepare_grid(ctx, d_xyz, d_nrm, d_role, n);
+    if (rc) return rc;
+    KPL_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
+    rc = prepare_normals(ctx, d_nrm != nullptr, n);
+    if (rc) return rc;
+    KPL_CUDA(launch_check_normals(ctx, n));
+    KPL_CUDA(cudaEventRecord(ctx->ev[2], ctx->stream));
+    KPL_CUDA(launch_features(ctx, n, d_role != nullptr));
+    ctx->last_has_features = true; ctx->last_F = F;
+    KPL_CUDA(cudaEventRecord(ctx->ev[3], ctx->stream));
+    KPL_CUDA(launch_forest(ctx, n, d_role != nullptr));
+    KPL_CUDA(cudaEventRecord(ctx->ev[4], ctx->stream));
+    if (P.non_maxima) KPL_CUDA(launch_nms(ctx, n, d_role != nullptr));
+    else KPL_CUDA(launch_all_flags(ctx, n));
+    KPL_CUDA(launch_compact(ctx, n, d_kp_out));
+    if (d_scores_out) KPL_CUDA(cudaMemcpyAsync(d_scores_out, ctx->score.p, (size_t)n * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+    KPL_CUDA(cudaEventRecord(ctx->ev[5], ctx->stream));
+    unsigned long long hc[8];
+    KPL_CUDA(cudaMemcpyAsync(hc, ctx->counters.p, sizeof hc, cudaMemcpyDeviceToHost, ctx->stream));
+    KPL_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (hc[4]) return fail(ctx, KPL_E_NONFINITE, "a query normal is not finite (the reference mis-aligns its response cloud here)");
+    const int32_t nkp = (int32_t)(hc[3] & 0xFFFFFFFFull);
+    if (n_kp_out) *n_kp_out = nkp;
+    kpl_timings& T = ctx->timings;
+    cudaEventElapsedTime(&T.grid_ms, ctx->ev[0], ctx->ev[1]);
+    cudaEventElapsedTime(&T.normals_ms, ctx->ev[1], ctx->ev[2]);
+    cudaEventElapsedTime(&T.features_ms, ctx->ev[2], ctx->ev[3]);
+    cudaEventElapsedTime(&T.forest_ms, ctx->ev[3], ctx->ev[4]);
+    cudaEventElapsedTime(&T.nms_ms, ctx->ev[4], ctx->ev[5]);
+    cudaEventElapsedTime(&T.total_ms, ctx->ev[0], ctx->ev[5]);
+    kpl_stats& S = ctx->stats;
+    S.feature_pairs = (int64_t)hc[0]; S.candidate_pairs = (int64_t)hc[1]; S.n_above_threshold = (int64_t)hc[2];
+    S.n_keypoints = nkp; S.kernel_launches = ctx->launches; S.n_scored = n;
+    return KPL_OK;
+}
+
+// host (possibly strided) -> device float4 staging
+static int upload_vec3(kpl_ctx* ctx, DevBuf<float4>& dst, const float* src, int32_t stride, int64_t n)
+{
+    if (stride < 12 || (stride & 3)) return fail(ctx, KPL_E_INVALID, "stride must be a multiple of 4 and >= 12 bytes");
+    KPL_CUDA(ensure(dst, (size_t)n));
+    if (stride == 16) KPL_CUDA(cudaMemcpyAsync(dst.p, src, (size_t)n * 16, cudaMemcpyHostToDevice, ctx->stream));
+    else KPL_CUDA(cudaMemcpy2DAsync(dst.p, 16, src, (size_t)stride, stride >= 16 ? 16 : 12, (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    return KPL_OK;
+}
+
+static int upload_inputs(kpl_ctx* ctx, const float* xyz, int32_t xs, const float* normals, int32_t ns, const uint8_t* role, int64_t n)
+{
+    if (!xyz && n > 0) return fail(ctx, KPL_E_INVALID, "xyz is NULL");
+    KPL_CUDA(cudaSetDevice(ctx->device));
+    if (n == 0) return KPL_OK;
+    int rc = upload_vec3(ctx, ctx->in_xyz, xyz, xs, n);
+    if (rc) return rc;
+    if (normals) { rc = upload_vec3(ctx, ctx->in_nrm, normals, ns, n); if (rc) return rc; }
+    if (role) {
+        KPL_CUDA(ensure(ctx->in_role, (size_t)n));
+        KPL_CUDA(cudaMemcpyAsync(ctx->in_role.p, role, (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    return KPL_OK;
+}
+
+extern "C" {
+
+int kpl_detect(kpl_ctx* ctx, const float* xyz, int32_t xyz_stride, const float* normals, int32_t normals_stride,
+               const uint8_t* role, int64_t n, float* scores_out, int32_t* kp_idx_out, int64_t* n_kp_out)
+{
+    if (!ctx) return KPL_E_INVALID;
+    if (n > 0 && !kp_idx_out) return fail(ctx, KPL_E_INVALID, "kp_idx_out is NULL");
+    int rc = upload_inputs(ctx, xyz, xyz_stride, normals, normals_stride, role, n);
+    if (rc) return rc;
+    if (n > 0) KPL_CUDA(ensure(ctx->kp_idx, (size_t)n));
+    int64_t nkp = 0;
+    rc = run_detect(ctx, ctx->in_xyz.p, normals ? ctx->in_nrm.p : nullptr, role ? ctx->in_role.p : nullptr, n, nullptr, ctx->kp_idx.p, &nkp);
+    if (rc) return rc;
+    if (n > 0) {
+        if (scores_out) KPL_CUDA(cudaMemcpyAsync(scores_out, ctx->score.p, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+        if (nkp > 0) KPL_CUDA(cudaMemcpyAsync(kp_idx_out, ctx->kp_idx.p, (size_t)nkp * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        KPL_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    if (n_kp_out) *n_kp_out = nkp;
+    return KPL_OK;
+}
+
+int kpl_detect_device(kpl_ctx* ctx, const void* d_xyz4, const void* d_normals4, const void* d_role, int64_t n,
+                      void* d_scores, void* d_kp_idx, int64_t* n_kp_out)
+{
+    if (!ctx) return KPL_E_INVALID;
+    if (n > 0 && (!d_xyz4 || !d_kp_idx)) return fail(ctx, KPL_E_INVALID, "NULL device pointer");
+    return run_detect(ctx, (const float4*)d_xyz4, (const float4*)d_normals4, (const uint8_t*)d_role, n, (float*)d_scores,
+                      (int32_t*)d_kp_idx, n_kp_out);
+}
+
+int kpl_normals(kpl_ctx* ctx, const float* xyz, int32_t xyz_stride, int64_t n, float* normals_out)
+{
+    if (!ctx || (n > 0 && !normals_out)) return KPL_E_INVALID;
+    begin_call(ctx);
+    if (n == 0) return KPL_OK;
+    if (ctx->params.normals_mode == KPL_NORMALS_GIVEN) return fail(ctx, KPL_E_INVALID, "normals_mode must be KNN or RADIUS");
+    int rc = upload_inputs(ctx, xyz, xyz_stride, nullptr, 0, nullptr, n);
+    if (rc) return rc;
+    if ((rc = prepare_grid(ctx, ctx->in_xyz.p, nullptr, nullptr, n))) return rc;
+    if ((rc = prepare_normals(ctx, false, n))) return rc;
+    KPL_CUDA(ensure(ctx->scratch_f, (size_t)n * 4));
+    KPL_CUDA(launch_unsort_normals(ctx, n, (float4*)ctx->scratch_f.p));
+    KPL_CUDA(cudaMemcpyAsync(normals_out, ctx->scratch_f.p, (size_t)n * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    KPL_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->stats.kernel_launches = ctx->launches;
+    return KPL_OK;
+}
+
+int kpl_features(kpl_ctx* ctx, const float* xyz, int32_t xyz_stride, const float* normals, int32_t normals_stride,
+                 int64_t n, const int32_t* indices, int64_t m, float* features_out)
+{
+    if (!ctx || m < 0 || (m > 0 && !features_out)) return KPL_E_INVALID;
+    begin_call(ctx);
+    if (!indices && m != n) return fail(ctx, KPL_E_INVALID, "indices == NULL requires m == n");
+    if (n == 0 || m == 0) return KPL_OK;
+    const int F = ctx->params.n_annulus * ctx->params.n_bins;
+    std::vector<uint8_t> role;
+    if (indices) {
+        role.assign((size_t)n, 0);
+        for (int64_t k = 0; k < m; ++k) {
+            if (indices[k] < 0 || indices[k] >= n) return fail(ctx, KPL_E_INVALID, "feature index out of range");
+            role[(size_t)indices[k]] = KPL_ROLE_SCORE;
+        }
+    }
+    int rc = upload_inputs(ctx, xyz, xyz_stride, normals, normals_stride, indices ? role.data() : nullptr, n);
+    if (rc) return rc;
+    KPL_CUDA(cudaMemsetAsync(ctx->counters.p, 0, 8 * sizeof(unsigned long long), ctx->stream));
+    if ((rc = prepare_grid(ctx, ctx->in_xyz.p, normals ? ctx->in_nrm.p : nullptr, indices ? ctx->in_role.p : nullptr, n))) return rc;
+    if ((rc = prepare_normals(ctx, normals != nullptr, n))) return rc;
+    KPL_CUDA(launch_features(ctx, n, indices != nullptr));
+    ctx->last_has_features = true; ctx->last_F = F;
+    KPL_CUDA(ensure(ctx->scratch_f, (size_t)n * F + (size_t)m * F));
+    float* d_orig = ctx->scratch_f.p;
+    KPL_CUDA(launch_unsort_rows(ctx, ctx->feat.p, n, F, d_orig));
+    const float* d_src = d_orig;
+    if (indices) {
+        KPL_CUDA(ensure(ctx->scratch_i, (size_t)m));
+        KPL_CUDA(cudaMemcpyAsync(ctx->scratch_i.p, indices, (size_t)m * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+        float* d_sel = d_orig + (size_t)n * F;
+        KPL_CUDA(launch_gather_rows(ctx, d_orig, ctx->scratch_i.p, m, F, d_sel));
+        d_src = d_sel;
+    }
+    KPL_CUDA(cudaMemcpyAsync(features_out, d_src, (size_t)m * F * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    unsigned long long hc[8];
+    KPL_CUDA(cudaMemcpyAsync(hc, ctx->counters.p, sizeof hc, cudaMemcpyDeviceToHost, ctx->stream));
+    KPL_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->stats.n_points = n; ctx->stats.n_scored = m; ctx->stats.feature_pairs = (int64_t)hc[0]; ctx->stats.candidate_pairs = (int64_t)hc[1];
+    ctx->stats.kernel_launches = ctx->launches;
+    return KPL_OK;
+}
+
+int kpl_radius_stats(kpl_ctx* ctx, const float* xyz, int32_t xyz_stride, int64_t n, double radius, int32_t* counts_out, uint64_t* hash_out)
+{
+    if (!ctx || !(radius >= 0)) return KPL_E_INVALID;
+    begin_call(ctx);
+    if (n == 0) return KPL_OK;
+    int rc = upload_inputs(ctx, xyz, xyz_stride, nullptr, 0, nullptr, n);
+    if (rc) return rc;
+    if ((rc = prepare_grid(ctx, ctx->in_xyz.p, nullptr, nullptr, n))) return rc;
+    KPL_CUDA(ensure(ctx->scratch_i, (size_t)n * 3 + 2));
+    int32_t* d_counts = ctx->scratch_i.p;
+    unsigned long long* d_hash = (unsigned long long*)(ctx->scratch_i.p + ((n + 1) & ~1ll));
+    KPL_CUDA(launch_radius_stats(ctx, n, radius, d_counts, d_hash));
+    if (counts_out) KPL_CUDA(cudaMemcpyAsync(counts_out, d_counts, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    if (hash_out) KPL_CUDA(cudaMemcpyAsync(hash_out, d_hash, (size_t)n * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    KPL_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->stats.kernel_launches = ctx->launches;
+    return KPL_OK;
+}
+
+int kpl_radius_neighbors(kpl_ctx* ctx, const float* xyz, int32_t xyz_stride, int64_t n, double radius,
+                         const int32_t* queries, int64_t m, int64_t* offsets_out, int32_t* indices_out)
+{
+    if (!ctx || !(radius >= 0) || m < 0 || !offsets_out || (m > 0 && !queries)) return KPL_E_INVALID;
+    begin_call(ctx);
+    offsets_out[0] = 0;
+    if (n == 0 || m == 0) { for (int64_t k = 0; k <= m; ++k) offsets_out[k] = 0; return KPL_OK; }
+    for (int64_t k = 0; k < m; ++k) if (queries[k] < 0 || queries[k] >= n) return fail(ctx, KPL_E_INVALID, "query index out of range");
+    int rc = upload_inputs(ctx, xyz, xyz_stride, nullptr, 0, nullptr, n);
+    if (rc) return rc;
+    if ((rc = prepare_grid(ctx, ctx->in_xyz.p, nullptr, nullptr, n))) return rc;
+    KPL_CUDA(ensure(ctx->scratch_i, (size_t)n + 2));
+    KPL_CUDA(launch_radius_stats(ctx, n, radius, ctx->scratch_i.p, nullptr));
+    std::vector<int32_t> counts((size_t)n), sidx((size_t)n);
+    KPL_CUDA(cudaMemcpyAsync(counts.data(), ctx->scratch_i.p, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    KPL_CUDA(cudaMemcpyAsync(sidx.data(), ctx->idx_b.p, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    KPL_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int64_t k = 0; k < m; ++k) offsets_out[k + 1] = offsets_out[k] + counts[(size_t)queries[k]];
+    if (!indices_out) return KPL_OK;
+    std::vector<int32_t> inv((size_t)n), qpos((size_t)m);
+    for (int64_t i = 0; i < n; ++i) inv[(size_t)sidx[(size_t)i]] = (int32_t)i;
+    for (int64_t k = 0; k < m; ++k) qpos[(size_t)k] = inv[(size_t)queries[k]];
+    const int64_t total = offsets_out[m];
+    int32_t *d_q = nullptr, *d_idx = nullptr;
+    int64_t* d_off = nullptr;
+    KPL_CUDA(cudaMalloc((void**)&d_q, (size_t)m * sizeof(int32_t)));
+    KPL_CUDA(cudaMalloc((void**)&d_off, (size_t)(m + 1) * sizeof(int64_t)));
+    KPL_CUDA(cudaMalloc((void**)&d_idx, (size_t)std::max<int64_t>(total, 1) * sizeof(int32_t)));
+    cudaError_t e = cudaMemcpyAsync(d_q, qpos.data(), (size_t)m * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream);
+    if (!e) e = cudaMemcpyAsync(d_off, offsets_out, (size_t)(m + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream);
+    if (!e) e = launch_radius_lists(ctx, n, radius, d_q, m, d_off, d_idx);
+    if (!e && total > 0) e = cudaMemcpyAsync(indices_out, d_idx, (size_t)total * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream);
+    if (!e) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_q); cudaFree(d_off); cudaFree(d_idx);
+    KPL_CUDA(e);
+    for (int64_t k = 0; k < m; ++k) std::sort(indices_out + offsets_out[k], indices_out + offsets_out[k + 1]);
+    ctx->stats.kernel_launches = ctx->launches;
+    return KPL_OK;
+}
+
+int kpl_get_timings(const kpl_ctx* ctx, kpl_timings* t)
+{
+    if (!ctx || !t) return KPL_E_INVALID;
+    *t = ctx->timings;
+    return KPL_OK;
+}
+
+int kpl_get_stats(const kpl_ctx* ctx, kpl_stats* s)
+{
+    if (!ctx || !s) return KPL_E_INVALID;
+    *s = ctx->stats;
+    return KPL_OK;
+}
+
+int kpl_fetch(kpl_ctx* ctx, const char* what, float* out, int64_t capacity_floats)
+{
+    if (!ctx || !what || !out) return KPL_E_INVALID;
+    const int64_t n = ctx->last_n;
+    if (n <= 0) return fail(ctx, KPL_E_INVALID, "nothing to fetch");
+    KPL_CUDA(cudaSetDevice(ctx->device));
+    if (!strcmp(what, "normals")) {
+        if (!ctx->last_has_normals) return fail(ctx, KPL_E_INVALID, "no normals from the last call");
+        if (capacity_floats < n * 4) return fail(ctx, KPL_E_INVALID, "fetch buffer too small");
+        KPL_CUDA(ensure(ctx->scratch_f, (size_t)n * 4));
+        KPL_CUDA(launch_unsort_normals(ctx, n, (float4*)ctx->scratch_f.p));
+        KPL_CUDA(cudaMemcpyAsync(out, ctx->scratch_f.p, (size_t)n * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    } else if (!strcmp(what, "features")) {
+        if (!ctx->last_has_features) return fail(ctx, KPL_E_INVALID, "no features from the last call");
+        const int F = ctx->last_F;
+        if (capacity_floats < n * F) return fail(ctx, KPL_E_INVALID, "fetch buffer too small");
+        KPL_CUDA(ensure(ctx->scratch_f, (size_t)n * F));
+        KPL_CUDA(launch_unsort_rows(ctx, ctx->feat.p, n, F, ctx->scratch_f.p));
+        KPL_CUDA(cudaMemcpyAsync(out, ctx->scratch_f.p, (size_t)n * F * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    } else return fail(ctx, KPL_E_INVALID, "unknown fetch target");
+    KPL_CUDA(cudaStreamSynchronize(ctx->stream));
+    return KPL_OK;
+}
+
+}  // extern "C"

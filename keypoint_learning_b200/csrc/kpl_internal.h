@@ -1,0 +1,124 @@
+// kpl_internal.h -- shared declarations of the CUDA implementation behind include/kpl.h.
+// Built for sm_100a only, with -fmad=false: every float expression below is evaluated with
+// separately rounded multiplies and adds, which is the arithmetic contract of the hot path
+// (FLANN L2_Simple / Eigen / the reference's own helpers are FMA-free on the authors' platform).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "../../include/kpl.h"
+
+namespace kpl {
+
+// Canonical uniform grid.  cell = r_feat*(1+2^-20)/cells_per_radius; coordinates are computed in
+// double so that two points closer than r_feat are never more than cells_per_radius cells apart.
+struct GridDesc {
+    double org[3];
+    double cell;
+    int32_t dim[3];
+    int32_t reach_feat;   // cells to search for radius_features
+    int32_t reach_nms;    // cells to search for radius_nms
+    int64_t ncells;
+};
+
+// One forest node, 8 bytes: thr_or_value + packed(right_offset << 10 | var); var == 1023 => leaf.
+// The left child of node i is i+1 (pre-order), the right child is i + right_offset.
+struct __align__(8) PackedNode {
+    float thr;
+    uint32_t packed;
+};
+static constexpr uint32_t KPL_LEAF_VAR = 1023u;
+
+struct Forest {
+    int32_t ntrees = 0, nnodes = 0, var_count = 0, max_depth = 0;
+    std::vector<int32_t> roots;           // host copy (pre-order node index of each root)
+    PackedNode* d_nodes = nullptr;
+    int32_t* d_roots = nullptr;
+};
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t cap = 0;  // elements
+};
+
+struct HostForestArrays {
+    std::vector<int32_t> roots, var, left, right;
+    std::vector<float> thr, value;
+    int32_t var_count = 0;
+};
+
+// forest_yaml.cpp
+int parse_forest_yaml(const char* path, HostForestArrays& out, std::string& err);
+
+}  // namespace kpl
+
+struct kpl_ctx {
+    int device = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    kpl_params params;
+    kpl::Forest forest;
+    kpl::GridDesc grid;
+    kpl_timings timings;
+    kpl_stats stats;
+    std::string err;
+    int launches = 0;
+
+    // device buffers (grown on demand, never shrunk)
+    kpl::DevBuf<float4> in_xyz, in_nrm;          // staged host input (host API only)
+    kpl::DevBuf<uint8_t> in_role, s_role;
+    kpl::DevBuf<uint32_t> key_a, key_b, idx_a, idx_b;
+    kpl::DevBuf<uint8_t> cub_tmp;
+    kpl::DevBuf<int32_t> cell_start;
+    kpl::DevBuf<float4> s_pos, s_nrm;            // cell-sorted positions (w = original index bits) / normals
+    kpl::DevBuf<float> feat;                     // n x F, sorted order
+    kpl::DevBuf<float> s_score, score;           // sorted order / original order
+    kpl::DevBuf<uint8_t> flag;                   // keypoint flag, original order
+    kpl::DevBuf<int32_t> kp_idx;
+    kpl::DevBuf<float> scratch_f;                // fetch / reorder scratch
+    kpl::DevBuf<int32_t> scratch_i;
+    kpl::DevBuf<unsigned long long> counters;    // [0] feature pairs [1] candidate pairs [2] above th [3] n_kp [4] nonfinite flag [5] scored
+    const float4* cur_xyz = nullptr;             // original-order inputs of the call in flight (device)
+    const float4* cur_nrm = nullptr;
+    float* d_bbox = nullptr;                     // 6 ordered-int encoded floats + flags
+    int64_t last_n = 0;
+    int last_F = 0;
+    bool last_has_normals = false, last_has_features = false;
+    cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+};
+
+namespace kpl {
+
+// ---- launch wrappers implemented in the .cu files; all enqueue on ctx->stream and return cudaError_t
+cudaError_t launch_bbox(kpl_ctx* c, const float4* xyz, int64_t n, float* d_bbox /* 8 uint32 */);
+cudaError_t build_grid(kpl_ctx* c, const float4* xyz, const float4* nrm_or_null, const uint8_t* role_or_null, int64_t n);
+cudaError_t launch_normals_knn(kpl_ctx* c, int64_t n);
+cudaError_t launch_normals_radius(kpl_ctx* c, int64_t n);
+cudaError_t launch_flip_normals(kpl_ctx* c, int64_t n);
+cudaError_t launch_check_normals(kpl_ctx* c, int64_t n);
+cudaError_t launch_features(kpl_ctx* c, int64_t n, bool use_role);
+cudaError_t launch_forest(kpl_ctx* c, int64_t n, bool use_role);
+cudaError_t launch_nms(kpl_ctx* c, int64_t n, bool use_role);
+cudaError_t launch_compact(kpl_ctx* c, int64_t n, int32_t* d_kp_idx_out);
+cudaError_t launch_radius_stats(kpl_ctx* c, int64_t n, double radius, int32_t* d_counts, unsigned long long* d_hash);
+cudaError_t launch_radius_lists(kpl_ctx* c, int64_t n, double radius, const int32_t* d_queries, int64_t m,
+                                const int64_t* d_offsets, int32_t* d_indices);
+cudaError_t launch_unsort_rows(kpl_ctx* c, const float* d_sorted_rows, int64_t n, int width, float* d_out_orig_order);
+cudaError_t launch_unsort_normals(kpl_ctx* c, int64_t n, float4* d_out_orig_order);
+cudaError_t launch_gather_rows(kpl_ctx* c, const float* d_rows_orig_order, const int32_t* d_indices, int64_t m, int width, float* d_out);
+
+template <typename T>
+cudaError_t ensure(DevBuf<T>& b, size_t n)
+{
+    if (n <= b.cap) return cudaSuccess;
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr; b.cap = 0;
+    size_t want = n + n / 8 + 64;
+    cudaError_t e = cudaMalloc((void**)&b.p, want * sizeof(T));
+    if (e == cudaSuccess) b.cap = want;
+    return e;
+}
+
+}  // namespace kpl

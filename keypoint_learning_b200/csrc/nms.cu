@@ -1,0 +1,155 @@
+// nms.cu -- threshold + radius non-maxima suppression over the same uniform grid, and the plain
+// radius-search kernels used for neighbour-set parity and for the exact work counters.
+// Replaces the NMS loop of KeypointLearningDetector::detectKeypoints
+// (impl/KeypointLearning.hpp:202-256, draws-remove branch off as in TestDetector :128).
+#include "kpl_internal.h"
+#include "kpl_math.cuh"
+
+namespace kpl {
+
+__device__ __forceinline__ void key_to_cell_n(uint32_t key, int dimx, int dimy, int& cx, int& cy, int& cz)
+{
+    uint32_t t = key / (uint32_t)dimx;
+    cx = (int)(key - t * (uint32_t)dimx);
+    cz = (int)(t / (uint32_t)dimy);
+    cy = (int)(t - (uint32_t)cz * (uint32_t)dimy);
+}
+
+// keypoint iff score >= th (compared in double, hpp:207) and no point with d2 < r_nms^2 has a
+// strictly larger score (hpp:219).  A pure local-maximum test: order independent.
+__global__ void __launch_bounds__(128)
+nms_kernel(const float4* __restrict__ s_pos, const float* __restrict__ s_score, const uint32_t* __restrict__ skey,
+           const int32_t* __restrict__ cell_start, const uint8_t* __restrict__ s_role, int dimx, int dimy, int dimz,
+           int n, float rn2, int reach, double th, uint8_t* __restrict__ flag, unsigned long long* __restrict__ counters)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool above = false;
+    if (i < n) {
+        const float4 p = __ldg(s_pos + i);
+        const uint32_t orig = __float_as_uint(p.w);
+        const float my = __ldg(s_score + i);
+        const bool owned = !s_role || ((s_role[i] & 3) == 3);
+        above = owned && isfinite(my) && !((double)my < th);
+        bool is_max = above;
+        if (above) {
+            int cx, cy, cz;
+            key_to_cell_n(__ldg(skey + i), dimx, dimy, cx, cy, cz);
+            const int z0 = max(cz - reach, 0), z1 = min(cz + reach, dimz - 1);
+            const int y0 = max(cy - reach, 0), y1 = min(cy + reach, dimy - 1);
+            const int x0 = max(cx - reach, 0), x1 = min(cx + reach, dimx - 1);
+            for (int z = z0; z <= z1 && is_max; ++z)
+                for (int y = y0; y <= y1 && is_max; ++y) {
+                    const int64_t base = ((int64_t)z * dimy + y) * dimx;
+                    const int s = __ldg(cell_start + base + x0), e = __ldg(cell_start + base + x1 + 1);
+                    for (int j = s; j < e; ++j) {
+                        const float4 c = __ldg(s_pos + j);
+                        if (dist2(p.x, p.y, p.z, c.x, c.y, c.z) < rn2 && my < __ldg(s_score + j)) { is_max = false; break; }
+                    }
+                }
+        }
+        flag[orig] = is_max ? 1 : 0;
+    }
+    unsigned m = __ballot_sync(0xFFFFFFFFu, above);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(counters + 2, (unsigned long long)__popc(m));
+}
+
+cudaError_t launch_nms(kpl_ctx* c, int64_t n, bool use_role)
+{
+    const kpl_params& U = c->params;
+    cudaError_t e;
+    if ((e = ensure(c->flag, n))) return e;
+    const double rn = (double)U.radius_nms;
+    nms_kernel<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(c->s_pos.p, c->s_score.p, c->key_b.p, c->cell_start.p,
+                                                                   use_role ? c->s_role.p : nullptr,
+                                                                   c->grid.dim[0], c->grid.dim[1], c->grid.dim[2], (int)n,
+                                                                   (float)(rn * rn), c->grid.reach_nms, U.threshold, c->flag.p, c->counters.p);
+    c->launches++;
+    return cudaGetLastError();
+}
+
+// setNonMaxima(false) (hpp:189-196): every scored point is a keypoint.
+__global__ void __launch_bounds__(256) all_flags_kernel(const float* __restrict__ score, int64_t n, uint8_t* __restrict__ flag)
+{
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) flag[i] = isnan(score[i]) ? 0 : 1;
+}
+cudaError_t launch_all_flags(kpl_ctx* c, int64_t n)
+{
+    cudaError_t e;
+    if ((e = ensure(c->flag, n))) return e;
+    all_flags_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->score.p, n, c->flag.p);
+    c->launches++;
+    return cudaGetLastError();
+}
+
+// ---- plain radius search (FLANN radiusSearch semantics: d2 < (float)(r*r), self included) -----
+static constexpr unsigned long long HASH_MUL = 0x9E3779B97F4A7C15ull;
+
+template <bool LISTS>
+__global__ void __launch_bounds__(128)
+radius_kernel(const float4* __restrict__ s_pos, const uint32_t* __restrict__ skey, const int32_t* __restrict__ cell_start,
+              const int32_t* __restrict__ inv_or_queries, int dimx, int dimy, int dimz, int n, int64_t m, float r2, int reach,
+              int32_t* __restrict__ counts, unsigned long long* __restrict__ hash,
+              const int64_t* __restrict__ offsets, int32_t* __restrict__ indices)
+{
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= m) return;
+    // LISTS: t indexes the query list, inv_or_queries[t] is the SORTED position of that query.
+    const int i = LISTS ? inv_or_queries[t] : (int)t;
+    const float4 p = __ldg(s_pos + i);
+    int cx, cy, cz;
+    key_to_cell_n(__ldg(skey + i), dimx, dimy, cx, cy, cz);
+    const int z0 = max(cz - reach, 0), z1 = min(cz + reach, dimz - 1);
+    const int y0 = max(cy - reach, 0), y1 = min(cy + reach, dimy - 1);
+    const int x0 = max(cx - reach, 0), x1 = min(cx + reach, dimx - 1);
+    int cnt = 0;
+    unsigned long long h = 0;
+    int64_t w = LISTS ? offsets[t] : 0;
+    for (int z = z0; z <= z1; ++z)
+        for (int y = y0; y <= y1; ++y) {
+            const int64_t base = ((int64_t)z * dimy + y) * dimx;
+            const int s = __ldg(cell_start + base + x0), e = __ldg(cell_start + base + x1 + 1);
+            for (int j = s; j < e; ++j) {
+                const float4 c = __ldg(s_pos + j);
+                if (dist2(p.x, p.y, p.z, c.x, c.y, c.z) < r2) {
+                    const uint32_t oj = __float_as_uint(c.w);
+                    if (LISTS) indices[w++] = (int32_t)oj;
+                    cnt++;
+                    h += ((unsigned long long)oj + 1ull) * HASH_MUL;
+                }
+            }
+        }
+    if (!LISTS) {
+        const uint32_t orig = __float_as_uint(p.w);
+        if (counts) counts[orig] = cnt;
+        if (hash) hash[orig] = h;
+    }
+}
+
+static int reach_for(const GridDesc& g, double radius)
+{
+    return (int)floor(radius * (1.0 + 4.76837158203125e-07) / g.cell) + 1;
+}
+
+cudaError_t launch_radius_stats(kpl_ctx* c, int64_t n, double radius, int32_t* d_counts, unsigned long long* d_hash)
+{
+    radius_kernel<false><<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(
+        c->s_pos.p, c->key_b.p, c->cell_start.p, nullptr, c->grid.dim[0], c->grid.dim[1], c->grid.dim[2], (int)n, n,
+        (float)(radius * radius), reach_for(c->grid, radius), d_counts, d_hash, nullptr, nullptr);
+    c->launches++;
+    return cudaGetLastError();
+}
+
+// d_queries holds SORTED positions of the m queries; d_offsets[m+1] their output offsets.
+cudaError_t launch_radius_lists(kpl_ctx* c, int64_t n, double radius, const int32_t* d_queries, int64_t m,
+                                const int64_t* d_offsets, int32_t* d_indices)
+{
+    if (m == 0) return cudaSuccess;
+    radius_kernel<true><<<(unsigned)((m + 127) / 128), 128, 0, c->stream>>>(
+        c->s_pos.p, c->key_b.p, c->cell_start.p, d_queries, c->grid.dim[0], c->grid.dim[1], c->grid.dim[2], (int)n, m,
+        (float)(radius * radius), reach_for(c->grid, radius), nullptr, nullptr, d_offsets, d_indices);
+    c->launches++;
+    return cudaGetLastError();
+}
+
+}  // namespace kpl

@@ -1,0 +1,158 @@
+// normals.cu -- PCA normals on the cell-sorted cloud.
+//
+// kNN mode replaces pcl::NormalEstimation with setKSearch(10) over a sorted search::KdTree
+// (reference call site src/main_test_detector.cpp:162-169): the k nearest points (the query
+// itself included) ordered by (d2, index), PCL 1.8.0's single-pass un-centred FP32 moment sums in
+// that order, eigen33, viewpoint flip.  One thread per point keeps the whole sequential
+// accumulation in registers, which is what makes the result bit-identical to the oracle.
+#include "kpl_internal.h"
+#include "kpl_math.cuh"
+
+namespace kpl {
+
+__device__ __forceinline__ bool less_d2_idx(float d2, uint32_t idx, float bd2, uint32_t bidx)
+{
+    return d2 < bd2 || (d2 == bd2 && idx < bidx);
+}
+
+__device__ __forceinline__ void key_to_cell(uint32_t key, const GridDesc& g, int& cx, int& cy, int& cz)
+{
+    uint32_t t = key / (uint32_t)g.dim[0];
+    cx = (int)(key - t * (uint32_t)g.dim[0]);
+    cz = (int)(t / (uint32_t)g.dim[1]);
+    cy = (int)(t - (uint32_t)cz * (uint32_t)g.dim[1]);
+}
+
+// K > 0: compile-time k, candidates in registers.  K == 0: runtime k <= 64, candidates in local memory.
+template <int K>
+__global__ void __launch_bounds__(128) normals_knn_kernel(const float4* __restrict__ s_pos, const uint32_t* __restrict__ skey,
+                                                          const int32_t* __restrict__ cell_start, const float4* __restrict__ xyz,
+                                                          GridDesc g, int n, int k_rt, float vpx, float vpy, float vpz,
+                                                          float4* __restrict__ s_nrm)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    constexpr int KM = (K > 0) ? K : 64;
+    const int k = (K > 0) ? K : k_rt;
+    float bd2[KM];
+    uint32_t bi[KM];
+    const float4 p = s_pos[i];
+    int cx, cy, cz;
+    key_to_cell(skey[i], g, cx, cy, cz);
+    int maxdim = max(g.dim[0], max(g.dim[1], g.dim[2]));
+    int seen = 0;
+    for (int R = 1; R <= maxdim; ++R) {
+#pragma unroll
+        for (int t = 0; t < KM; ++t) { bd2[t] = CUDART_INF_F; bi[t] = 0xFFFFFFFFu; }
+        seen = 0;
+        int z0 = max(cz - R, 0), z1 = min(cz + R, g.dim[2] - 1);
+        int y0 = max(cy - R, 0), y1 = min(cy + R, g.dim[1] - 1);
+        int x0 = max(cx - R, 0), x1 = min(cx + R, g.dim[0] - 1);
+        for (int z = z0; z <= z1; ++z)
+            for (int y = y0; y <= y1; ++y) {
+                int64_t base = ((int64_t)z * g.dim[1] + y) * g.dim[0];
+                int s = __ldg(cell_start + base + x0), e = __ldg(cell_start + base + x1 + 1);
+                for (int j = s; j < e; ++j) {
+                    float4 c = __ldg(s_pos + j);
+                    float d2 = dist2(p.x, p.y, p.z, c.x, c.y, c.z);
+                    uint32_t oi = __float_as_uint(c.w);
+                    seen++;
+                    if (less_d2_idx(d2, oi, bd2[k - 1], bi[k - 1])) {
+                        if (K > 0) {
+#pragma unroll
+                            for (int t = KM - 1; t >= 0; --t) {
+                                float pd = (t > 0) ? bd2[t > 0 ? t - 1 : 0] : -CUDART_INF_F;
+                                uint32_t pi = (t > 0) ? bi[t > 0 ? t - 1 : 0] : 0u;
+                                if (less_d2_idx(d2, oi, pd, pi)) { bd2[t] = pd; bi[t] = pi; }
+                                else if (less_d2_idx(d2, oi, bd2[t], bi[t])) { bd2[t] = d2; bi[t] = oi; }
+                            }
+                        } else {
+                            int t = k - 1;
+                            while (t > 0 && less_d2_idx(d2, oi, bd2[t - 1], bi[t - 1])) { bd2[t] = bd2[t - 1]; bi[t] = bi[t - 1]; --t; }
+                            bd2[t] = d2; bi[t] = oi;
+                        }
+                    }
+                }
+            }
+        bool all = (z0 == 0 && y0 == 0 && x0 == 0 && z1 == g.dim[2] - 1 && y1 == g.dim[1] - 1 && x1 == g.dim[0] - 1);
+        if (all) break;
+        if (seen >= k) {
+            double guard = (double)R * g.cell;
+            guard = guard * guard * (1.0 - 1e-6);
+            if ((double)bd2[k - 1] < guard) break;
+        }
+    }
+    int cnt = min(seen, k);
+    float accu[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int t = 0; t < KM; ++t) {
+        if (t < cnt) {
+            float4 c = __ldg(xyz + bi[t]);
+            accu[0] = __fadd_rn(accu[0], __fmul_rn(c.x, c.x));
+            accu[1] = __fadd_rn(accu[1], __fmul_rn(c.x, c.y));
+            accu[2] = __fadd_rn(accu[2], __fmul_rn(c.x, c.z));
+            accu[3] = __fadd_rn(accu[3], __fmul_rn(c.y, c.y));
+            accu[4] = __fadd_rn(accu[4], __fmul_rn(c.y, c.z));
+            accu[5] = __fadd_rn(accu[5], __fmul_rn(c.z, c.z));
+            accu[6] = __fadd_rn(accu[6], c.x);
+            accu[7] = __fadd_rn(accu[7], c.y);
+            accu[8] = __fadd_rn(accu[8], c.z);
+        }
+    }
+    s_nrm[i] = normal_from_moments(accu, cnt, p.x, p.y, p.z, vpx, vpy, vpz);
+}
+
+cudaError_t launch_normals_knn(kpl_ctx* c, int64_t n)
+{
+    const kpl_params& P = c->params;
+    int blocks = (int)((n + 127) / 128);
+    const float4* xyz = c->cur_xyz;
+    if (P.k_normals == 10)
+        normals_knn_kernel<10><<<blocks, 128, 0, c->stream>>>(c->s_pos.p, c->key_b.p, c->cell_start.p, xyz, c->grid, (int)n, 10,
+                                                               P.viewpoint[0], P.viewpoint[1], P.viewpoint[2], c->s_nrm.p);
+    else
+        normals_knn_kernel<0><<<blocks, 128, 0, c->stream>>>(c->s_pos.p, c->key_b.p, c->cell_start.p, xyz, c->grid, (int)n, P.k_normals,
+                                                              P.viewpoint[0], P.viewpoint[1], P.viewpoint[2], c->s_nrm.p);
+    c->launches++;
+    return cudaGetLastError();
+}
+
+// --flipNormals (src/main_test_detector.cpp:173-179): negate the three components.
+__global__ void __launch_bounds__(256) flip_normals_kernel(float4* __restrict__ s_nrm, int64_t n)
+{
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 v = s_nrm[i];
+    v.x = __fmul_rn(v.x, -1.0f); v.y = __fmul_rn(v.y, -1.0f); v.z = __fmul_rn(v.z, -1.0f);
+    s_nrm[i] = v;
+}
+cudaError_t launch_flip_normals(kpl_ctx* c, int64_t n)
+{
+    flip_normals_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->s_nrm.p, n);
+    c->launches++;
+    return cudaGetLastError();
+}
+
+// The reference silently mis-aligns its response cloud when a query normal is not finite
+// (impl/KeypointLearning.hpp:277-290); we detect it and fail the call instead.  counters[4] |= 1.
+__global__ void __launch_bounds__(256) check_normals_kernel(const float4* __restrict__ s_nrm, const uint8_t* __restrict__ s_role,
+                                                            int64_t n, unsigned long long* __restrict__ counters)
+{
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    bool bad = false;
+    if (i < n && (!s_role || (s_role[i] & 1))) {
+        float4 v = s_nrm[i];
+        bad = !(isfinite(v.x) && isfinite(v.y) && isfinite(v.z));
+    }
+    if (__any_sync(0xFFFFFFFFu, bad) && (threadIdx.x & 31) == 0) atomicOr(counters + 4, 1ull);
+}
+cudaError_t launch_check_normals(kpl_ctx* c, int64_t n)
+{
+    check_normals_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->s_nrm.p, nullptr, n, c->counters.p);
+    c->launches++;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_normals_radius(kpl_ctx*, int64_t) { return cudaErrorNotSupported; }
+
+}  // namespace kpl
