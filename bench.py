@@ -244,7 +244,7 @@ def run_b200(args):
                 "candidate_tests_per_s": st["candidate_pairs"] / feat_s,
                 "acceptance": st["feature_pairs"] / max(1, st["candidate_pairs"]),
                 "pipeline_frac_rank0": (pipe_bytes / (ms_per_step * 1e-3) / 1e9) / peak_gbs if world == 1 else None,
-                "stage_ms": stage}
+                "stage_ms": stage, "fast_math_selftest_passed": bool(st["fast_math"])}
 
     if rank == 0:
         cpu = None

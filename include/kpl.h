@@ -93,6 +93,8 @@ typedef struct kpl_stats {
     int32_t kernel_launches;  /* kernels launched by the last call                    */
     double grid_origin[3];
     double grid_cell;
+    int32_t fast_math;        /* 1: the self-tested FMA-corrected sqrt/div sequences were used (bit-identical) */
+    int32_t reserved;
 } kpl_stats;
 
 /* ---- lifetime ------------------------------------------------------------------------------- */

@@ -126,7 +126,6 @@ int kpl_set_params(kpl_ctx* ctx, const kpl_params* p)
     if (p->normals_mode < 0 || p->normals_mode > 2) return fail(ctx, KPL_E_INVALID, "bad normals_mode");
     if (p->k_normals < 1 || p->k_normals > 64) return fail(ctx, KPL_E_INVALID, "k_normals must be in [1,64]");
     if (p->cells_per_radius < 1 || p->cells_per_radius > 16) return fail(ctx, KPL_E_INVALID, "cells_per_radius must be in [1,16]");
-    if (p->draws_remove && p->non_maxima) return fail(ctx, KPL_E_UNSUPPORTED, "non_maxima_draws_remove is not implemented (off in TestDetector)");
     ctx->params = *p;
     return KPL_OK;
 }
@@ -267,6 +266,7 @@ static int run_detect(kpl_ctx* ctx, const float4* d_xyz, const float4* d_nrm, co
     if (n_kp_out) *n_kp_out = 0;
     if (n < 0 || n > 2147483000ll) return fail(ctx, KPL_E_INVALID, "point count out of range");
     if (ctx->forest.ntrees < 1) return fail(ctx, KPL_E_FOREST, "no forest loaded");
+    if (P.draws_remove && P.non_maxima) return fail(ctx, KPL_E_UNSUPPORTED, "non_maxima_draws_remove is not implemented (off in TestDetector)");
     const int F = P.n_annulus * P.n_bins;
     if (ctx->forest.var_count > 0 && ctx->forest.var_count != F) return fail(ctx, KPL_E_VARCOUNT, "annuli*bins does not match the forest's var_count");
     ctx->stats.n_points = n;
@@ -306,7 +306,7 @@ static int run_detect(kpl_ctx* ctx, const float4* d_xyz, const float4* d_nrm, co
     cudaEventElapsedTime(&T.total_ms, ctx->ev[0], ctx->ev[5]);
     kpl_stats& S = ctx->stats;
     S.feature_pairs = (int64_t)hc[0]; S.candidate_pairs = (int64_t)hc[1]; S.n_above_threshold = (int64_t)hc[2];
-    S.n_keypoints = nkp; S.kernel_launches = ctx->launches; S.n_scored = n;
+    S.n_keypoints = nkp; S.kernel_launches = ctx->launches; S.n_scored = n; S.fast_math = ctx->fast_math ? 1 : 0;
     return KPL_OK;
 }
 
@@ -422,6 +422,7 @@ int kpl_features(kpl_ctx* ctx, const float* xyz, int32_t xyz_stride, const float
     unsigned long long hc[8];
     KPL_CUDA(cudaMemcpyAsync(hc, ctx->counters.p, sizeof hc, cudaMemcpyDeviceToHost, ctx->stream));
     KPL_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->stats.fast_math = ctx->fast_math ? 1 : 0;
     ctx->stats.n_points = n; ctx->stats.n_scored = m; ctx->stats.feature_pairs = (int64_t)hc[0]; ctx->stats.candidate_pairs = (int64_t)hc[1];
     ctx->stats.kernel_launches = ctx->launches;
     return KPL_OK;

@@ -6,11 +6,22 @@
 // Mapping: one warp owns 32 consecutive cell-sorted query points, one lane per query.  The warp
 // walks the cell rows that can hold neighbours of any of its queries; each row is ONE contiguous
 // range of the sorted arrays (grid.cu), staged 32 candidates at a time into a per-warp shared
-// tile with coalesced float4 loads.  Every lane then visits the 32 staged candidates in order
-// (shared-memory broadcast reads), so each query sees its neighbours in ascending sorted position
-// = canonical (cell key, index) order, and accumulates its votes sequentially in FP32 into a
-// lane-private histogram column hist[cell][lane] (bank == lane: conflict-free, no atomics).
-// That fixed order is what makes the histogram bit-identical to the oracle.
+// tile with coalesced float4 loads (the next tile's loads are in flight while the current one is
+// consumed).  A tile is consumed in two phases:
+//   1. membership: every lane tests all 32 candidates (shared-memory broadcast reads, 12
+//      instructions each) and records the exact FLANN predicate d2 < r2 in a 32-bit mask;
+//   2. votes: every lane walks the set bits of ITS mask in ascending order, so the expensive vote
+//      arithmetic runs only for real neighbours instead of for every (lane, candidate) pair.
+// Each query therefore sees its neighbours in ascending sorted position = canonical
+// (cell key, index) order and accumulates its votes sequentially in FP32 into a lane-private
+// histogram column hist[cell][lane] (bank == lane: conflict-free, no atomics).  That fixed order
+// is what makes the histogram bit-identical to the oracle.
+//
+// Arithmetic: IEEE binary32 RN without contraction, as the reference evaluates it.  The FAST
+// variant replaces the IEEE square root and the divisions by the two run constants (annulus and
+// bin width) with short FMA-corrected sequences; they are used only after selftest_kernel has
+// proved them bit-identical to __fsqrt_rn / __fdiv_rn for every input mantissa on this device.
+#include <cstdlib>
 #include "kpl_internal.h"
 #include "kpl_math.cuh"
 
@@ -19,8 +30,8 @@ namespace kpl {
 static constexpr int FEAT_WARPS = 4;
 
 struct FeatParams {
-    int n, A, B, F, reach;
-    float r2, support, adim, ahalf, bdim, bhalf, cellf, rcull2;
+    int n, A, B, F, reach, span;
+    float r2, support, adim, ahalf, ainv, bdim, bhalf, binv, cellf, rcull2;
 };
 
 __device__ __forceinline__ void key_to_cell_f(uint32_t key, int dimx, int dimy, int& cx, int& cy, int& cz)
@@ -31,6 +42,79 @@ __device__ __forceinline__ void key_to_cell_f(uint32_t key, int dimx, int dimy, 
     cy = (int)(t - (uint32_t)cz * (uint32_t)dimy);
 }
 
+// ---- verified-fast arithmetic --------------------------------------------------------------------
+static constexpr float FAST_SQRT_LO = 9.094947017729282e-13f;   // 2^-40
+static constexpr float FAST_SQRT_HI = 1.099511627776e12f;       // 2^40
+
+__device__ __forceinline__ float fast_sqrt_core(float x)
+{
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    const float s = __fmul_rn(x, y), h = __fmul_rn(y, 0.5f);
+    const float e = __fmaf_rn(-s, s, x);
+    return __fmaf_rn(e, h, s);
+}
+template <bool FAST>
+__device__ __forceinline__ float ksqrt(float x)
+{
+    if (!FAST) return __fsqrt_rn(x);
+    if (!(x >= FAST_SQRT_LO && x < FAST_SQRT_HI)) return __fsqrt_rn(x);   // zero (duplicates), denormal, huge
+    return fast_sqrt_core(x);
+}
+__device__ __forceinline__ float fast_div_core(float x, float c, float cinv)
+{
+    const float q = __fmul_rn(x, cinv);
+    const float r = __fmaf_rn(-q, c, x);
+    return __fmaf_rn(r, cinv, q);
+}
+template <bool FAST>
+__device__ __forceinline__ float kdiv(float x, float c, float cinv)
+{
+    return FAST ? fast_div_core(x, c, cinv) : __fdiv_rn(x, c);
+}
+
+// One thread per (binade, mantissa): result[0] counts sqrt mismatches over [2^-40, 2^40), result[1]
+// / result[2] division mismatches for the annulus / bin width over every mantissa of [1, 2) and [-2,-1)
+// (exact power-of-two scaling extends the proof to every binade without under/overflow).
+__global__ void __launch_bounds__(256) selftest_kernel(float adim, float ainv, float bdim, float binv, unsigned* __restrict__ result)
+{
+    const uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;   // 2^23 mantissas
+    if (m >= (1u << 23)) return;
+    unsigned bad_s = 0, bad_a = 0, bad_b = 0;
+    for (int ex = 127 - 40; ex < 127 + 40; ++ex) {
+        const float x = __uint_as_float(((uint32_t)ex << 23) | m);
+        bad_s += (__float_as_uint(fast_sqrt_core(x)) != __float_as_uint(__fsqrt_rn(x)));
+    }
+    const float x1 = __uint_as_float((127u << 23) | m);
+    bad_a += (__float_as_uint(fast_div_core(x1, adim, ainv)) != __float_as_uint(__fdiv_rn(x1, adim)));
+    bad_a += (__float_as_uint(fast_div_core(-x1, adim, ainv)) != __float_as_uint(__fdiv_rn(-x1, adim)));
+    bad_b += (__float_as_uint(fast_div_core(x1, bdim, binv)) != __float_as_uint(__fdiv_rn(x1, bdim)));
+    bad_b += (__float_as_uint(fast_div_core(-x1, bdim, binv)) != __float_as_uint(__fdiv_rn(-x1, bdim)));
+    bad_s = __reduce_add_sync(0xFFFFFFFFu, bad_s);
+    bad_a = __reduce_add_sync(0xFFFFFFFFu, bad_a);
+    bad_b = __reduce_add_sync(0xFFFFFFFFu, bad_b);
+    if ((threadIdx.x & 31) == 0) {
+        if (bad_s) atomicAdd(result + 0, bad_s);
+        if (bad_a) atomicAdd(result + 1, bad_a);
+        if (bad_b) atomicAdd(result + 2, bad_b);
+    }
+}
+
+// src/KeypointLearning.cpp:41-65 / :68-92 with float abs; dim = bin width, half = dim/2, inv = fl(1/dim).
+template <bool FAST>
+__device__ __forceinline__ void soft_bin_k(float v, float dim, float half, float inv, int n, int& idx, int& pair, float& w)
+{
+    int i = __float2int_rd(kdiv<FAST>(v, dim, inv));     // static_cast<int>(floor(v/dim))
+    if (i == n) i--;
+    const float center = __fadd_rn(__fmul_rn((float)i, dim), half);
+    const float ww = kdiv<FAST>(__fsub_rn(v, center), dim, inv);
+    int p = (ww > 0.0f) ? i + 1 : i - 1;
+    if (p == -1) p = 0;
+    if (p == n) p = i;
+    idx = i; pair = p; w = fabsf(ww);
+}
+
+template <bool FAST>
 __global__ void __launch_bounds__(FEAT_WARPS * 32)
 feature_kernel(const float4* __restrict__ s_pos, const float4* __restrict__ s_nrm, const uint32_t* __restrict__ skey,
                const int32_t* __restrict__ cell_start, const uint8_t* __restrict__ s_role,
@@ -38,10 +122,11 @@ feature_kernel(const float4* __restrict__ s_pos, const float4* __restrict__ s_nr
 {
     extern __shared__ __align__(16) float smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int per_warp = P.F * 32 + 256;
+    const int per_warp = P.F * 32 + 320;
     float* hist = smem + warp * per_warp;
-    float4* tpos = reinterpret_cast<float4*>(hist + P.F * 32);
-    float4* tnrm = tpos + 32;
+    float4* tpos = reinterpret_cast<float4*>(hist + P.F * 32);   // AoS tile for the broadcast membership pass
+    float* sx = hist + P.F * 32 + 128;                            // SoA tile for the per-lane vote pass
+    float* sy = sx + 32; float* sz = sy + 32; float* snx = sz + 32; float* sny = snx + 32; float* snz = sny + 32;
 
     const int q0 = (blockIdx.x * FEAT_WARPS + warp) * 32;
     if (q0 >= P.n) return;
@@ -49,8 +134,7 @@ feature_kernel(const float4* __restrict__ s_pos, const float4* __restrict__ s_nr
     bool active = q < P.n;
     if (active && s_role) active = (s_role[q] & 1) != 0;
     if (!__any_sync(0xFFFFFFFFu, active)) {
-        // nothing to score in this warp: rows stay zero
-        int nvalid = min(32, P.n - q0);
+        const int nvalid = min(32, P.n - q0);
         for (int e = lane; e < nvalid * P.F; e += 32) feat[(int64_t)q0 * P.F + e] = 0.0f;
         return;
     }
@@ -62,78 +146,115 @@ feature_kernel(const float4* __restrict__ s_pos, const float4* __restrict__ s_nr
         key_to_cell_f(__ldg(skey + q), dimx, dimy, cx, cy, cz);
     }
     const uint32_t qidx = __float_as_uint(qp.w);
-    const int BIG = 0x3FFFFFFF;
-    const int minx = __reduce_min_sync(0xFFFFFFFFu, active ? cx : BIG), maxx = __reduce_max_sync(0xFFFFFFFFu, active ? cx : -BIG);
-    const int miny = __reduce_min_sync(0xFFFFFFFFu, active ? cy : BIG), maxy = __reduce_max_sync(0xFFFFFFFFu, active ? cy : -BIG);
-    const int minz = __reduce_min_sync(0xFFFFFFFFu, active ? cz : BIG), maxz = __reduce_max_sync(0xFFFFFFFFu, active ? cz : -BIG);
 
     for (int f = 0; f < P.F; ++f) hist[f * 32 + lane] = 0.0f;
-
-    const int y0 = max(miny - P.reach, 0), y1 = min(maxy + P.reach, dimy - 1);
-    const int z0 = max(minz - P.reach, 0), z1 = min(maxz + P.reach, dimz - 1);
-    const int ny = y1 - y0 + 1, nrows = ny * (z1 - z0 + 1);
     unsigned npairs = 0, ncand = 0;
 
-    for (int rb = 0; rb < nrows; rb += 32) {
-        // each lane resolves one cell row: [s, e) in the sorted arrays, after conservative culling
-        int s = 0, e = 0;
-        {
-            int r = rb + lane;
-            if (r < nrows) {
-                int zz = z0 + r / ny, yy = y0 + r % ny;
-                int gy = max(max(miny - yy, yy - maxy) - 1, 0), gz = max(max(minz - zz, zz - maxz) - 1, 0);
-                float gap2 = (float)(gy * gy + gz * gz) * P.cellf * P.cellf;
-                if (gap2 < P.rcull2) {
-                    int rx = (int)(sqrtf(P.rcull2 - gap2) / P.cellf) + 1;
-                    rx = min(rx, P.reach);
-                    int xa = max(minx - rx, 0), xb = min(maxx + rx, dimx - 1);
-                    int64_t base = ((int64_t)zz * dimy + yy) * dimx;
-                    s = __ldg(cell_start + base + xa);
-                    e = __ldg(cell_start + base + xb + 1);
+    // The 32 queries are consecutive in (z, y, x) cell order but may straddle the end of a cell row
+    // (or sit in far-apart cells of a sparse row).  They are processed in groups of lanes that share
+    // one cell row and span at most P.span + 1 cells in x, so the candidate region of a pass is always
+    // a tight box around the group; lanes outside the group idle for that pass (their px is NaN).
+    unsigned remaining = __ballot_sync(0xFFFFFFFFu, active);
+    while (remaining) {
+        const int leader = __ffs(remaining) - 1;
+        const int minx = __shfl_sync(0xFFFFFFFFu, cx, leader);
+        const int gy0 = __shfl_sync(0xFFFFFFFFu, cy, leader), gz0 = __shfl_sync(0xFFFFFFFFu, cz, leader);
+        const bool member = active && ((remaining >> lane) & 1u) && cy == gy0 && cz == gz0 && (unsigned)(cx - minx) <= (unsigned)P.span;
+        remaining &= ~__ballot_sync(0xFFFFFFFFu, member);
+        const int maxx = __reduce_max_sync(0xFFFFFFFFu, member ? cx : minx);
+        const float px = member ? qp.x : CUDART_NAN_F;
+
+        const int y0 = max(gy0 - P.reach, 0), y1 = min(gy0 + P.reach, dimy - 1);
+        const int z0 = max(gz0 - P.reach, 0), z1 = min(gz0 + P.reach, dimz - 1);
+        const int ny = y1 - y0 + 1, nrows = ny * (z1 - z0 + 1);
+
+        // ---- warp-uniform iterator over the candidate tiles: rows in ascending (z, y), 32 points per tile
+        int rb = 0, nr = 0, l = 0, row_s = 0, row_e = 0, cur = 0, end = 0;
+        auto next_tile = [&](int& tb, int& te) -> bool {
+            while (cur >= end) {
+                if (l >= nr) {
+                    if (rb >= nrows) return false;
+                    // each lane resolves one cell row: [s, e) in the sorted arrays, after conservative culling
+                    row_s = 0; row_e = 0;
+                    const int r = rb + lane;
+                    if (r < nrows) {
+                        const int zz = z0 + r / ny, yy = y0 + r % ny;
+                        const int gy = max(abs(yy - gy0) - 1, 0), gz = max(abs(zz - gz0) - 1, 0);
+                        const float gap2 = (float)(gy * gy + gz * gz) * P.cellf * P.cellf;
+                        if (gap2 < P.rcull2) {
+                            int rx = (int)(sqrtf(P.rcull2 - gap2) / P.cellf) + 1;
+                            rx = min(rx, P.reach);
+                            const int xa = max(minx - rx, 0), xb = min(maxx + rx, dimx - 1);
+                            const int64_t base = ((int64_t)zz * dimy + yy) * dimx;
+                            row_s = __ldg(cell_start + base + xa);
+                            row_e = __ldg(cell_start + base + xb + 1);
+                        }
+                    }
+                    nr = min(32, nrows - rb);
+                    rb += 32;
+                    l = 0;
+                }
+                cur = __shfl_sync(0xFFFFFFFFu, row_s, l);
+                end = __shfl_sync(0xFFFFFFFFu, row_e, l);
+                ++l;
+            }
+            tb = cur; te = end;
+            cur += 32;
+            return true;
+        };
+
+        int tb = 0, te = 0;
+        bool have = next_tile(tb, te);
+        float4 cp = make_float4(CUDART_NAN_F, 0.f, 0.f, 0.f), cn = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (have && tb + lane < te) { cp = __ldg(s_pos + tb + lane); cn = __ldg(s_nrm + tb + lane); }
+
+        while (have) {
+            // neighbours with a non-finite normal never vote (hpp:338): poison the position
+            if (!(isfinite(cn.x) && isfinite(cn.y) && isfinite(cn.z))) cp.x = CUDART_NAN_F;
+            __syncwarp();                          // previous tile fully consumed
+            tpos[lane] = cp;
+            sx[lane] = cp.x; sy[lane] = cp.y; sz[lane] = cp.z;
+            snx[lane] = cn.x; sny[lane] = cn.y; snz[lane] = cn.z;
+            const int cnt = min(32, te - tb);
+            have = next_tile(tb, te);
+            cp = make_float4(CUDART_NAN_F, 0.f, 0.f, 0.f);
+            if (have && tb + lane < te) { cp = __ldg(s_pos + tb + lane); cn = __ldg(s_nrm + tb + lane); }
+            __syncwarp();
+            ncand += cnt;
+
+            // phase 1: membership mask (slots >= cnt hold NaN positions and can never pass)
+            uint32_t mask = 0;
+            for (int k0 = 0; k0 < cnt; k0 += 8) {
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const float4 c = tpos[k0 + u];
+                    const float d2 = dist2(px, qp.y, qp.z, c.x, c.y, c.z);
+                    if (d2 < P.r2 && __float_as_uint(c.w) != qidx) mask |= 1u << (k0 + u);
                 }
             }
-        }
-        const int nr = min(32, nrows - rb);
-        for (int l = 0; l < nr; ++l) {
-            const int sl = __shfl_sync(0xFFFFFFFFu, s, l), el = __shfl_sync(0xFFFFFFFFu, e, l);
-            for (int base = sl; base < el; base += 32) {
-                const int j = base + lane;
-                float4 cp, cn;
-                if (j < el) {
-                    cp = __ldg(s_pos + j);
-                    cn = __ldg(s_nrm + j);
-                    // neighbours with a non-finite normal never vote (hpp:338): poison the position
-                    if (!(isfinite(cn.x) && isfinite(cn.y) && isfinite(cn.z))) cp.x = CUDART_NAN_F;
-                }
-                __syncwarp();
-                if (j < el) { tpos[lane] = cp; tnrm[lane] = cn; }
-                __syncwarp();
-                const int cnt = min(32, el - base);
-                ncand += cnt;
-                for (int k = 0; k < cnt; ++k) {
-                    const float4 c = tpos[k];
-                    const float d2 = dist2(qp.x, qp.y, qp.z, c.x, c.y, c.z);
-                    if (d2 < P.r2 && __float_as_uint(c.w) != qidx) {
-                        const float4 nj = tnrm[k];
-                        float cosine = __fsub_rn(1.0f, dot3_eigen(qn.x, qn.y, qn.z, nj.x, nj.y, nj.z));
-                        const float dist = __fsqrt_rn(d2);
-                        int a, ap, b, bp;
-                        float wa, wb;
-                        soft_bin(dist, P.adim, P.ahalf, P.A, a, ap, wa);
-                        if (cosine < 0.0f) cosine = 0.0f;
-                        if (cosine > 2.0f) cosine = 2.0f;
-                        soft_bin(cosine, P.bdim, P.bhalf, P.B, b, bp, wb);
-                        const float ua = __fsub_rn(1.0f, wa), ub = __fsub_rn(1.0f, wb);
-                        float* h0 = hist + (a * P.B) * 32 + lane;
-                        float* h1 = hist + (ap * P.B) * 32 + lane;
-                        // the four `+=` of hpp:350-355, in source order (cells may coincide)
-                        h0[b * 32] = __fadd_rn(h0[b * 32], __fmul_rn(ub, ua));
-                        h0[bp * 32] = __fadd_rn(h0[bp * 32], __fmul_rn(wb, ua));
-                        h1[b * 32] = __fadd_rn(h1[b * 32], __fmul_rn(ub, wa));
-                        h1[bp * 32] = __fadd_rn(h1[bp * 32], __fmul_rn(wb, wa));
-                        npairs++;
-                    }
-                }
+            npairs += __popc(mask);
+
+            // phase 2: votes of this lane's neighbours, ascending sorted position
+            while (mask) {
+                const int k = __ffs(mask) - 1;
+                mask &= mask - 1;
+                const float d2 = dist2(qp.x, qp.y, qp.z, sx[k], sy[k], sz[k]);
+                float cosine = __fsub_rn(1.0f, dot3_eigen(qn.x, qn.y, qn.z, snx[k], sny[k], snz[k]));   // hpp:341-342
+                const float dist = ksqrt<FAST>(d2);                                                     // hpp:345 sqrt(distances[..])
+                int a, ap, b, bp;
+                float wa, wb;
+                soft_bin_k<FAST>(dist, P.adim, P.ahalf, P.ainv, P.A, a, ap, wa);
+                if (cosine < 0.0f) cosine = 0.0f;
+                if (cosine > 2.0f) cosine = 2.0f;
+                soft_bin_k<FAST>(cosine, P.bdim, P.bhalf, P.binv, P.B, b, bp, wb);
+                const float ua = __fsub_rn(1.0f, wa), ub = __fsub_rn(1.0f, wb);
+                float* h0 = hist + (a * P.B) * 32 + lane;
+                float* h1 = hist + (ap * P.B) * 32 + lane;
+                // the four `+=` of hpp:350-355, in source order (cells may coincide)
+                h0[b * 32] = __fadd_rn(h0[b * 32], __fmul_rn(ub, ua));
+                h0[bp * 32] = __fadd_rn(h0[bp * 32], __fmul_rn(wb, ua));
+                h1[b * 32] = __fadd_rn(h1[b * 32], __fmul_rn(ub, wa));
+                h1[bp * 32] = __fadd_rn(h1[bp * 32], __fmul_rn(wb, wa));
             }
         }
     }
@@ -156,7 +277,7 @@ feature_kernel(const float4* __restrict__ s_pos, const float4* __restrict__ s_nr
         const int total = nvalid * P.F;
         float* dst = feat + (int64_t)q0 * P.F;
         for (int e = lane; e < total; e += 32) {
-            int row = e / P.F, f = e - row * P.F;
+            const int row = e / P.F, f = e - row * P.F;
             dst[e] = hist[f * 32 + row];
         }
     }
@@ -167,34 +288,62 @@ feature_kernel(const float4* __restrict__ s_pos, const float4* __restrict__ s_nr
     }
 }
 
+// Runs the exhaustive self-test once per (adim, bdim) pair and caches the verdict.
+static cudaError_t fast_math_verdict(kpl_ctx* c, const FeatParams& P, bool& fast)
+{
+    struct Verdict { float adim, bdim; int device; bool fast; };
+    static std::vector<Verdict> cache;
+    for (const Verdict& v : cache)
+        if (v.adim == P.adim && v.bdim == P.bdim && v.device == c->device) { fast = v.fast; return cudaSuccess; }
+    unsigned* d_res = reinterpret_cast<unsigned*>(c->counters.p + 6);   // counters[6..7] are scratch
+    cudaError_t e;
+    if ((e = cudaMemsetAsync(d_res, 0, 4 * sizeof(unsigned), c->stream))) return e;
+    selftest_kernel<<<(1u << 23) / 256, 256, 0, c->stream>>>(P.adim, P.ainv, P.bdim, P.binv, d_res);
+    unsigned h[3];
+    if ((e = cudaMemcpyAsync(h, d_res, sizeof h, cudaMemcpyDeviceToHost, c->stream))) return e;
+    if ((e = cudaStreamSynchronize(c->stream))) return e;
+    if ((e = cudaMemsetAsync(d_res, 0, 4 * sizeof(unsigned), c->stream))) return e;
+    fast = (h[0] == 0 && h[1] == 0 && h[2] == 0);
+    cache.push_back({P.adim, P.bdim, c->device, fast});
+    c->launches++;
+    return cudaGetLastError();
+}
+
 cudaError_t launch_features(kpl_ctx* c, int64_t n, bool use_role)
 {
     const kpl_params& U = c->params;
     FeatParams P;
     P.n = (int)n; P.A = U.n_annulus; P.B = U.n_bins; P.F = P.A * P.B; P.reach = c->grid.reach_feat;
+    P.span = (U.cells_per_radius + 3) / 4;
     const double r = (double)U.radius_features;
     P.r2 = (float)(r * r);                       // static_cast<float>(radius*radius), KdTreeFLANN::radiusSearch
     P.support = (float)r;                        // findAnnulusPair(.., (float)search_radius_, ..) hpp:345
     P.adim = P.support / (float)P.A;             // src/KeypointLearning.cpp:43
     P.ahalf = P.adim / 2.0f;                     // :52
+    P.ainv = 1.0f / P.adim;
     P.bdim = 2.0f / (float)P.B;                  // :75
     P.bhalf = P.bdim / 2.0f;                     // :84
+    P.binv = 1.0f / P.bdim;
     P.cellf = (float)c->grid.cell;
     P.rcull2 = (float)(r * r * (1.0 + 1e-5));
     cudaError_t e;
     if ((e = ensure(c->feat, (size_t)n * P.F))) return e;
-    size_t smem = (size_t)FEAT_WARPS * (P.F * 32 + 256) * sizeof(float);
+    bool fast = false;
+    if (!getenv("KPL_NO_FAST_MATH") && (e = fast_math_verdict(c, P, fast))) return e;
+    c->fast_math = fast;
+    size_t smem = (size_t)FEAT_WARPS * (P.F * 32 + 320) * sizeof(float);
     if (smem > 227 * 1024) return cudaErrorInvalidValue;
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        if ((e = cudaFuncSetAttribute(feature_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return e;
-        configured = smem;
+    static size_t configured[2] = {0, 0};
+    auto kern = fast ? feature_kernel<true> : feature_kernel<false>;
+    if (smem > 48 * 1024 && smem > configured[fast]) {
+        if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return e;
+        configured[fast] = smem;
     }
     int warps = (int)((n + 31) / 32);
     int blocks = (warps + FEAT_WARPS - 1) / FEAT_WARPS;
-    feature_kernel<<<blocks, FEAT_WARPS * 32, smem, c->stream>>>(c->s_pos.p, c->s_nrm.p, c->key_b.p, c->cell_start.p,
-                                                                 use_role ? c->s_role.p : nullptr,
-                                                                 c->grid.dim[0], c->grid.dim[1], c->grid.dim[2], P, c->feat.p, c->counters.p);
+    kern<<<blocks, FEAT_WARPS * 32, smem, c->stream>>>(c->s_pos.p, c->s_nrm.p, c->key_b.p, c->cell_start.p,
+                                                       use_role ? c->s_role.p : nullptr,
+                                                       c->grid.dim[0], c->grid.dim[1], c->grid.dim[2], P, c->feat.p, c->counters.p);
     c->launches++;
     return cudaGetLastError();
 }

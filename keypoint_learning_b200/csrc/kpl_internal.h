@@ -86,6 +86,7 @@ struct kpl_ctx {
     int64_t last_n = 0;
     int last_F = 0;
     bool last_has_normals = false, last_has_features = false;
+    bool fast_math = false;                      // feature kernel variant chosen by the arithmetic self-test
     cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 

@@ -272,7 +272,7 @@ def test_non_maxima_off_returns_every_point(kpl, views, oracle):
 def test_error_codes(kpl, views):
     xyz = np.ascontiguousarray(views["cheff001"][:3000])
     d = kpl.KeypointLearningDetector()
-    d.setRadiusSearch(R_FEAT)
+    d.setRadiusSearch(R_FEAT); d.setNonMaxRadius(R_NMS); d.setNonMaximaDrawsRemove(False)
     d.setInputCloud(xyz)
     with pytest.raises(kpl.KplError) as e:
         d.compute()
