@@ -35,8 +35,8 @@ enum kpl_status {
     KPL_E_INVALID = 1,        /* bad argument / parameter combination                                   */
     KPL_E_FOREST = 2,         /* forest missing, unreadable or empty  (loadForest -> false, hpp:165-174)  */
     KPL_E_SIZE_MISMATCH = 3,  /* normals/points size mismatch         (initCompute -> false, hpp:149-153) */
-    KPL_E_NONFINITE = 4,      /* non-finite point or query normal: the reference mis-aligns its response
-                                 cloud in that case (hpp:277-290 vs :203-253); we refuse instead          */
+    KPL_E_NONFINITE = 4,      /* non-finite input point (a point without a finite NORMAL is not an error:
+                                 it gets no score, as in runForest hpp:277, see kpl_stats.n_unscored)      */
     KPL_E_VARCOUNT = 5,       /* annuli*bins != forest var_count                                          */
     KPL_E_CUDA = 6,           /* CUDA runtime failure or no usable device                                 */
     KPL_E_GRID = 7,           /* uniform grid would exceed 2^31-2 cells / point outside a forced grid     */
@@ -70,9 +70,10 @@ typedef struct kpl_params {
     float viewpoint[3];       /* PCD VIEWPOINT / sensor_origin_, (0,0,0)                             */
     int32_t flip_normals;     /* --flipNormals (:173-179), applied to normals computed here          */
     int32_t cells_per_radius; /* grid resolution: cell = r_feat*(1+2^-20)/cells_per_radius, default 4 */
-    int32_t grid_forced;      /* 1: use grid_origin/grid_dims below (slab of a larger cloud)         */
-    double grid_origin[3];
-    int32_t grid_dims[3];
+    int32_t grid_forced;      /* 1: use the grid below (slab of a larger cloud): a point's cell is    */
+    double grid_origin[3];    /*    floor((v - grid_origin)/cell) - grid_offset, which must lie in     */
+    int32_t grid_dims[3];     /*    [0, grid_dims); origin is the GLOBAL one so keys order globally    */
+    int32_t grid_offset[3];
 } kpl_params;
 
 /* Device-time breakdown of the last detect call (CUDA events on the context stream), ms. */
@@ -95,6 +96,7 @@ typedef struct kpl_stats {
     double grid_cell;
     int32_t fast_math;        /* 1: the self-tested FMA-corrected sqrt/div sequences were used (bit-identical) */
     int32_t reserved;
+    int64_t n_unscored;       /* points without a finite normal: score NaN, never a keypoint (hpp:277)        */
 } kpl_stats;
 
 /* ---- lifetime ------------------------------------------------------------------------------- */

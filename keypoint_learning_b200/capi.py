@@ -30,7 +30,8 @@ class KplParams(C.Structure):
                 ("n_annulus", C.c_int32), ("n_bins", C.c_int32), ("non_maxima", C.c_int32), ("draws_remove", C.c_int32),
                 ("draws_threshold", C.c_float), ("normals_mode", C.c_int32), ("k_normals", C.c_int32),
                 ("viewpoint", C.c_float * 3), ("flip_normals", C.c_int32), ("cells_per_radius", C.c_int32),
-                ("grid_forced", C.c_int32), ("grid_origin", C.c_double * 3), ("grid_dims", C.c_int32 * 3)]
+                ("grid_forced", C.c_int32), ("grid_origin", C.c_double * 3), ("grid_dims", C.c_int32 * 3),
+                ("grid_offset", C.c_int32 * 3)]
 
 
 class KplTimings(C.Structure):
@@ -41,7 +42,7 @@ class KplStats(C.Structure):
     _fields_ = [("n_points", C.c_int64), ("n_scored", C.c_int64), ("feature_pairs", C.c_int64), ("candidate_pairs", C.c_int64),
                 ("n_above_threshold", C.c_int64), ("n_keypoints", C.c_int64), ("grid_cells", C.c_int64),
                 ("grid_dims", C.c_int32 * 3), ("kernel_launches", C.c_int32), ("grid_origin", C.c_double * 3), ("grid_cell", C.c_double),
-                ("fast_math", C.c_int32), ("reserved", C.c_int32)]
+                ("fast_math", C.c_int32), ("reserved", C.c_int32), ("n_unscored", C.c_int64)]
 
 
 class KplError(RuntimeError):
@@ -175,13 +176,13 @@ class KeypointLearningDetector:
 
     def setCellsPerRadius(self, cpr): self._p.cells_per_radius = int(cpr)
 
-    def setForcedGrid(self, origin=None, dims=None):
+    def setForcedGrid(self, origin=None, dims=None, offset=(0, 0, 0)):
         if origin is None:
             self._p.grid_forced = 0
             return
         self._p.grid_forced = 1
         for i in range(3):
-            self._p.grid_origin[i] = float(origin[i]); self._p.grid_dims[i] = int(dims[i])
+            self._p.grid_origin[i] = float(origin[i]); self._p.grid_dims[i] = int(dims[i]); self._p.grid_offset[i] = int(offset[i])
 
     def setStream(self, cuda_stream_ptr):
         self._check(self._L.kpl_set_stream(self._h, C.c_void_p(cuda_stream_ptr or 0)))

@@ -209,7 +209,8 @@ static int prepare_grid(kpl_ctx* ctx, const float4* d_xyz, const float4* d_nrm, 
     double ncells = 1.0;
     for (int a = 0; a < 3; ++a) {
         double lo = (double)dec_float(hb[a]), hi = (double)dec_float(hb[3 + a]);
-        if (P.grid_forced) { g.org[a] = P.grid_origin[a]; g.dim[a] = P.grid_dims[a]; }
+        g.off[a] = 0;
+        if (P.grid_forced) { g.org[a] = P.grid_origin[a]; g.dim[a] = P.grid_dims[a]; g.off[a] = P.grid_offset[a]; }
         else { g.org[a] = lo; g.dim[a] = (int32_t)std::min(2147483000.0, std::floor((hi - lo) / g.cell) + 1.0); }
         if (g.dim[a] < 1) return fail(ctx, KPL_E_GRID, "bad grid dimensions");
         ncells *= (double)g.dim[a];
@@ -294,7 +295,6 @@ static int run_detect(kpl_ctx* ctx, const float4* d_xyz, const float4* d_nrm, co
     unsigned long long hc[8];
     KPL_CUDA(cudaMemcpyAsync(hc, ctx->counters.p, sizeof hc, cudaMemcpyDeviceToHost, ctx->stream));
     KPL_CUDA(cudaStreamSynchronize(ctx->stream));
-    if (hc[4]) return fail(ctx, KPL_E_NONFINITE, "a query normal is not finite (the reference mis-aligns its response cloud here)");
     const int32_t nkp = (int32_t)(hc[3] & 0xFFFFFFFFull);
     if (n_kp_out) *n_kp_out = nkp;
     kpl_timings& T = ctx->timings;
@@ -306,7 +306,7 @@ static int run_detect(kpl_ctx* ctx, const float4* d_xyz, const float4* d_nrm, co
     cudaEventElapsedTime(&T.total_ms, ctx->ev[0], ctx->ev[5]);
     kpl_stats& S = ctx->stats;
     S.feature_pairs = (int64_t)hc[0]; S.candidate_pairs = (int64_t)hc[1]; S.n_above_threshold = (int64_t)hc[2];
-    S.n_keypoints = nkp; S.kernel_launches = ctx->launches; S.n_scored = n; S.fast_math = ctx->fast_math ? 1 : 0;
+    S.n_keypoints = nkp; S.kernel_launches = ctx->launches; S.n_scored = n; S.n_unscored = (int64_t)hc[4]; S.fast_math = ctx->fast_math ? 1 : 0;
     return KPL_OK;
 }
 

@@ -144,6 +144,8 @@ feature_kernel(const float4* __restrict__ s_pos, const float4* __restrict__ s_nr
         qp = __ldg(s_pos + q);
         qn = __ldg(s_nrm + q);
         key_to_cell_f(__ldg(skey + q), dimx, dimy, cx, cy, cz);
+        // a query without a finite normal is not scored (hpp:277): its row stays zero
+        if (!(isfinite(qn.x) && isfinite(qn.y) && isfinite(qn.z))) { active = false; qp.x = CUDART_NAN_F; }
     }
     const uint32_t qidx = __float_as_uint(qp.w);
 

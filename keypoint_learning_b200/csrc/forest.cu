@@ -18,6 +18,7 @@ static constexpr int TREES_IN_FLIGHT = 4;
 __global__ void __launch_bounds__(FOREST_THREADS)
 forest_kernel(const float* __restrict__ feat, const PackedNode* __restrict__ nodes, const int32_t* __restrict__ roots,
               int ntrees, int F, int n, const uint8_t* __restrict__ s_role, const float4* __restrict__ s_pos,
+              const float4* __restrict__ s_nrm,
               float* __restrict__ s_score, float* __restrict__ score, unsigned long long* __restrict__ counters)
 {
     extern __shared__ __align__(16) float sf[];
@@ -33,7 +34,9 @@ forest_kernel(const float* __restrict__ feat, const PackedNode* __restrict__ nod
     const int i = base + tid;
     if (i >= n) return;
     const uint32_t orig = __float_as_uint(__ldg(s_pos + i).w);
-    if (s_role && !(s_role[i] & 1)) {
+    const float4 qn = __ldg(s_nrm + i);
+    // unscored: halo role, or no finite normal (the reference skips the point, hpp:277)
+    if ((s_role && !(s_role[i] & 1)) || !(isfinite(qn.x) && isfinite(qn.y) && isfinite(qn.z))) {
         s_score[i] = CUDART_NAN_F;
         score[orig] = CUDART_NAN_F;
         return;
@@ -94,7 +97,7 @@ cudaError_t launch_forest(kpl_ctx* c, int64_t n, bool use_role)
     }
     int blocks = (int)((n + FOREST_THREADS - 1) / FOREST_THREADS);
     forest_kernel<<<blocks, FOREST_THREADS, smem, c->stream>>>(c->feat.p, c->forest.d_nodes, c->forest.d_roots, c->forest.ntrees, F, (int)n,
-                                                               use_role ? c->s_role.p : nullptr, c->s_pos.p, c->s_score.p, c->score.p,
+                                                               use_role ? c->s_role.p : nullptr, c->s_pos.p, c->s_nrm.p, c->s_score.p, c->score.p,
                                                                c->counters.p);
     c->launches++;
     return cudaGetLastError();

@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(256) cell_key_kernel(const float4* __restrict_
     bool out = false;
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
-        double q = floor(__ddiv_rn(__dsub_rn((double)v[a], g.org[a]), g.cell));
+        double q = floor(__ddiv_rn(__dsub_rn((double)v[a], g.org[a]), g.cell)) - (double)g.off[a];
         if (!(q >= 0.0)) { out = true; q = 0.0; }
         if (q > (double)(g.dim[a] - 1)) { out = true; q = (double)(g.dim[a] - 1); }
         cc[a] = (int)q;

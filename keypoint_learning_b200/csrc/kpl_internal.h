@@ -17,6 +17,7 @@ struct GridDesc {
     double org[3];
     double cell;
     int32_t dim[3];
+    int32_t off[3];       // cell offset of a forced (slab) grid, 0 otherwise
     int32_t reach_feat;   // cells to search for radius_features
     int32_t reach_nms;    // cells to search for radius_nms
     int64_t ncells;

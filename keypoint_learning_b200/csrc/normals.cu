@@ -133,8 +133,10 @@ cudaError_t launch_flip_normals(kpl_ctx* c, int64_t n)
     return cudaGetLastError();
 }
 
-// The reference silently mis-aligns its response cloud when a query normal is not finite
-// (impl/KeypointLearning.hpp:277-290); we detect it and fail the call instead.  counters[4] |= 1.
+// The reference skips points whose normal is not finite in runForest (impl/KeypointLearning.hpp:277)
+// and thereby mis-aligns its response cloud against the indices NMS uses (:203-253).  We keep the
+// alignment instead: such a point gets no score (NaN), is never a keypoint and never suppresses a
+// neighbour; counters[4] counts them (kpl_stats.n_unscored).
 __global__ void __launch_bounds__(256) check_normals_kernel(const float4* __restrict__ s_nrm, const uint8_t* __restrict__ s_role,
                                                             int64_t n, unsigned long long* __restrict__ counters)
 {
@@ -144,7 +146,8 @@ __global__ void __launch_bounds__(256) check_normals_kernel(const float4* __rest
         float4 v = s_nrm[i];
         bad = !(isfinite(v.x) && isfinite(v.y) && isfinite(v.z));
     }
-    if (__any_sync(0xFFFFFFFFu, bad) && (threadIdx.x & 31) == 0) atomicOr(counters + 4, 1ull);
+    const unsigned m = __ballot_sync(0xFFFFFFFFu, bad);
+    if (m && (threadIdx.x & 31) == 0) atomicAdd(counters + 4, (unsigned long long)__popc(m));
 }
 cudaError_t launch_check_normals(kpl_ctx* c, int64_t n)
 {

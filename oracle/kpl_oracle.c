@@ -574,6 +574,11 @@ static void feature_row(const float* xyz, const float* normals4, int64_t q, nb_t
     (void)xyz;
     for (int t = 0; t < A * B; ++t) hist[t] = 0.0f;
     const float* ni = normals4 + 4 * q;
+    if (!(isfinite(ni[0]) && isfinite(ni[1]) && isfinite(ni[2]))) {
+        /* runForest never calls computePointFeatures for such a point (hpp:277): zero row, no score */
+        for (int t = 0; t < A * B; ++t) out[t] = 0.0f;
+        return;
+    }
     for (int64_t t = 0; t < cnt; ++t) {
         int64_t j = nb[t].idx;
         if (j == q) continue;
@@ -664,6 +669,17 @@ KPLO_API void kplo_forest_sum(const int32_t* roots, int ntrees, const int32_t* v
 KPLO_API void kplo_scores(const float* sums, int64_t m, int ntrees, float* scores)
 {
     for (int64_t i = 0; i < m; ++i) scores[i] = 1 - (sums[i] / ((float)ntrees * 1.0f));
+}
+/* runForest skips points whose normal is not finite (hpp:277): they get no score.  (The reference then
+ * mis-aligns response indices; the restatement keeps the alignment and marks the score NaN.) */
+KPLO_API int64_t kplo_mask_unscored(const float* normals4, int64_t n, float* scores)
+{
+    int64_t cnt = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        const float* v = normals4 + 4 * i;
+        if (!(isfinite(v[0]) && isfinite(v[1]) && isfinite(v[2]))) { scores[i] = NAN; cnt++; }
+    }
+    return cnt;
 }
 
 /* ------------------------------------------------------------------------------------------ */
@@ -762,6 +778,7 @@ KPLO_API int64_t kplo_detect(const float* xyz, float* normals4, int64_t n, int n
     double t2 = now_ms(); if (stage_ms) stage_ms[1] = t2 - t1;
     kplo_forest_sum(roots, ntrees, var, thr, left, right, value, features, n, A * B, scores);
     kplo_scores(scores, n, ntrees, scores);
+    kplo_mask_unscored(normals4, n, scores);
     double t3 = now_ms(); if (stage_ms) stage_ms[2] = t3 - t2;
     int64_t cnt = kplo_nms(xyz, scores, n, r_nms, th, kp_idx);
     double t4 = now_ms(); if (stage_ms) { stage_ms[3] = t4 - t3; stage_ms[4] = t4 - t0; }

@@ -49,6 +49,8 @@ def lib():
                                     f64p, C.c_double, i32p, i32p, C.c_int64, f32p]
         L.kplo_forest_sum.argtypes = [i32p, C.c_int, i32p, f32p, i32p, i32p, f32p, f32p, C.c_int64, C.c_int, f32p]
         L.kplo_scores.argtypes = [f32p, C.c_int64, C.c_int, f32p]
+        L.kplo_mask_unscored.restype = C.c_int64
+        L.kplo_mask_unscored.argtypes = [f32p, C.c_int64, f32p]
         L.kplo_nms.restype = C.c_int64
         L.kplo_nms.argtypes = [f32p, f32p, C.c_int64, C.c_double, C.c_double, i32p]
         L.kplo_nms_draws.restype = C.c_int64
@@ -205,6 +207,15 @@ def scores_from_sums(sums, ntrees):
     out = np.empty_like(sums)
     lib().kplo_scores(_p(sums, C.c_float), len(sums), int(ntrees), _p(out, C.c_float))
     return out
+
+
+def scores(forest, feat, normals4=None):
+    """forest sums -> 1 - sum/ntrees (hpp:287); points without a finite normal get NaN (hpp:277)."""
+    sc = scores_from_sums(forest_sum(forest, feat), forest["ntrees"])
+    if normals4 is not None:
+        nrm = np.ascontiguousarray(normals4, np.float32)
+        lib().kplo_mask_unscored(_p(nrm, C.c_float), len(sc), _p(sc, C.c_float))
+    return sc
 
 
 def nms(xyz, scores, r_nms, th, draws_remove=False, draws_thr=0.0):

@@ -303,11 +303,10 @@ def test_empty_and_tiny_clouds(kpl, oracle):
     d.setInputCloud(np.zeros((0, 3), np.float32))
     kp, idx = d.compute()
     assert len(idx) == 0 and kp.shape == (0, 4)
-    # fewer than 3 points: kNN normals are NaN -> refused (the reference would mis-align its output)
+    # fewer than 3 points: kNN normals are NaN -> the points get no score (hpp:277) and no keypoint
     d.setInputCloud(np.array([[0, 0, 0], [1, 0, 0]], np.float32))
-    with pytest.raises(kpl.KplError) as e:
-        d.compute()
-    assert e.value.code == 4
+    kp, idx = d.compute()
+    assert len(idx) == 0 and np.all(np.isnan(d.getResponse())) and d.stats()["n_unscored"] == 2
     # 5 points, k = 10 > n: all points are neighbours
     pts = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [1, 1, 0.1], [0.5, 0.5, 0.3]], np.float32)
     d.setInputCloud(pts)
@@ -379,4 +378,60 @@ def test_synthetic_view_properties(kpl, oracle, main_forest):
     f_cpu = oracle.features(xyz, nrm_g, R_FEAT, 5, 10, order=1, qidx=sub)
     f_gpu = d.fetch("features", len(xyz), 50)[sub]
     assert np.array_equal(f_gpu.view(np.uint32), f_cpu.view(np.uint32))
+    d.close()
+
+
+def test_query_without_finite_normal_is_unscored(kpl, views, oracle, main_forest):
+    """hpp:277: a point whose normal is NaN gets no score, is no keypoint and suppresses nobody."""
+    xyz = np.ascontiguousarray(views["cheff000"][:25000])
+    nrm = oracle.normals_knn(xyz, 10)
+    bad = np.arange(3, len(xyz), 17)
+    nrm[bad, 1] = np.nan
+    d = make_detector(kpl)
+    d.setInputCloud(xyz); d.setNormals(nrm)
+    _, idx = d.compute()
+    sc_gpu = d.getResponse()
+    feat = oracle.features(xyz, nrm, R_FEAT, 5, 10, order=1)
+    sc = oracle.scores(main_forest, feat, nrm)
+    assert np.all(np.isnan(sc_gpu[bad])) and d.stats()["n_unscored"] == len(bad)
+    ok = ~np.isnan(sc)
+    assert np.array_equal(np.isnan(sc_gpu), ~ok)                      # NaN payloads differ between C and CUDA
+    assert np.array_equal(sc_gpu[ok].view(np.uint32), sc[ok].view(np.uint32))
+    assert np.array_equal(d.fetch("features", len(xyz), 50).view(np.uint32), feat.view(np.uint32))
+    assert np.array_equal(idx, oracle.nms(xyz, sc, R_NMS, TH))
+    d.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# slab sharding emulated on one GPU: union of the slabs' owned results == the unsharded run
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("world", [2, 3])
+def test_slab_results_equal_unsharded(kpl, views, golden, world):
+    from keypoint_learning_b200 import shard
+    xyz = views["cheff001"]
+    g = golden["cheff001"]
+    # shard along the longest axis of this view (y): rotate it onto x, the slab axis
+    xyz_r = np.ascontiguousarray(xyz[:, [1, 0, 2]])
+    d = make_detector(kpl)
+    d.setNormalsMode(1, k=10)
+    d.setInputCloud(xyz_r)
+    _, idx_full = d.compute()
+    sc_full = d.getResponse().copy()
+    plan = shard.plan_slabs(xyz_r, R_FEAT, R_NMS, 4, world)
+    kps, seen = [], np.zeros(len(xyz), bool)
+    for rank in range(world):
+        s = shard.reference_slab(xyz_r, plan, rank)
+        d.setForcedGrid(plan.origin, s["local_dims"], s["offset"])
+        d.setInputCloud(s["xyz4"])
+        _, idx = d.compute(role=s["role"])
+        sc = d.getResponse()
+        owned = s["role"] == 3
+        assert not seen[s["gidx"][owned]].any()
+        seen[s["gidx"][owned]] = True
+        assert np.array_equal(sc[owned].view(np.uint32), sc_full[s["gidx"][owned]].view(np.uint32))   # bit-identical scores
+        assert np.all(owned[idx])                                                                    # only owned points are output
+        kps.append(s["gidx"][idx])
+    assert seen.all()
+    assert np.array_equal(np.sort(np.concatenate(kps)), idx_full)
+    d.setForcedGrid(None)
     d.close()
