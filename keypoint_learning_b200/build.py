@@ -16,6 +16,7 @@ CSRC = os.path.join(HERE, "csrc")
 HOST = os.path.join(HERE, "host")
 LIB = os.path.join(HERE, "libkpl_b200.so")
 TEST_DETECTOR = os.path.join(HERE, "TestDetector")
+PCD_TOOL = os.path.join(HERE, "pcd_tool")
 
 CU_SOURCES = ["capi.cu", "grid.cu", "normals.cu", "features.cu", "forest.cu", "nms.cu", "forest_yaml.cpp"]
 NVCC_FLAGS = [
@@ -73,16 +74,16 @@ def build_lib(force: bool = False, verbose: bool = False) -> str:
 
 def build_host(force: bool = False) -> str:
     """C++ facade + TestDetector CLI (links against libkpl_b200.so with an $ORIGIN rpath)."""
-    main = os.path.join(HOST, "main_test_detector.cpp")
-    if not os.path.exists(main):
+    if not os.path.isdir(HOST):
         return ""
-    deps = [os.path.join(HOST, f) for f in os.listdir(HOST)] + [LIB]
-    if not force and not _stale(TEST_DETECTOR, deps):
-        return TEST_DETECTOR
-    srcs = [os.path.join(HOST, f) for f in sorted(os.listdir(HOST)) if f.endswith(".cpp")]
-    cmd = [_host_cxx(), "-O2", "-std=c++17", "-Wall", "-Wextra", "-I", os.path.join(ROOT, "include"), "-I", HOST, *srcs,
-           "-o", TEST_DETECTOR, "-L", HERE, "-lkpl_b200", "-Wl,-rpath,$ORIGIN"]
-    subprocess.check_call(cmd)
+    deps = [os.path.join(HOST, f) for f in os.listdir(HOST)] + [LIB, os.path.join(ROOT, "include", "kpl.h")]
+    common = [os.path.join(HOST, f) for f in sorted(os.listdir(HOST)) if f.endswith(".cpp") and not f.startswith("main_")]
+    for main, exe in (("main_test_detector.cpp", TEST_DETECTOR), ("main_pcd_tool.cpp", PCD_TOOL)):
+        if not os.path.exists(os.path.join(HOST, main)) or (not force and not _stale(exe, deps)):
+            continue
+        cmd = [_host_cxx(), "-O2", "-std=c++17", "-Wall", "-Wextra", "-I", os.path.join(ROOT, "include"), "-I", HOST,
+               os.path.join(HOST, main), *common, "-o", exe, "-L", HERE, "-lkpl_b200", "-Wl,-rpath,$ORIGIN"]
+        subprocess.check_call(cmd)
     return TEST_DETECTOR
 
 

@@ -1,0 +1,182 @@
+// KeypointLearning.h -- pcl::keypoints::KeypointLearningDetector over the C ABI of include/kpl.h.
+//
+// Same class name, template parameters, constructor defaults and method names as the reference's
+// include/KeypointLearning.h:55-206 (+ the pcl::Keypoint members its driver calls: setRadiusSearch,
+// compute, getKeypointsIndices), so src/main_test_detector.cpp:123-187 compiles against this header
+// unchanged apart from the include lines.  Every call forwards to libkpl_b200.so; nothing is computed
+// on the host.  Error behaviour follows the reference: loadForest -> false, initCompute failure ->
+// message on stderr and an empty output cloud (impl/KeypointLearning.hpp:119-123,149-153,165-174).
+#pragma once
+#include <algorithm>
+#include <cstdio>
+#include <memory>
+#include <string>
+#include <vector>
+#include "kpl.h"
+#include "pcl_shim.h"
+
+namespace pcl {
+namespace keypoints {
+
+template <typename PointInT, typename PointOutT, typename NormalT = pcl::Normal>
+class KeypointLearningDetector {
+public:
+    typedef std::shared_ptr<KeypointLearningDetector<PointInT, PointOutT, NormalT>> Ptr;
+    typedef std::shared_ptr<const KeypointLearningDetector<PointInT, PointOutT, NormalT>> ConstPtr;
+    typedef pcl::PointCloud<PointInT> PointCloudIn;
+    typedef pcl::PointCloud<PointOutT> PointCloudOut;
+    typedef typename PointCloudIn::ConstPtr PointCloudInConstPtr;
+    typedef pcl::PointCloud<NormalT> PointCloudN;
+    typedef typename PointCloudN::Ptr PointCloudNPtr;
+    typedef typename PointCloudN::ConstPtr PointCloudNConstPtr;
+
+    // include/KeypointLearning.h:81-90
+    KeypointLearningDetector(double prediction_th = 0.5f, bool non_maxima = true, bool non_maxima_draws_remove = true,
+                             double non_max_radius = 0.0f, int n_annulus = 5, int n_bins = 10, int device = 0)
+        : name_("Keypoint_Learnining_Detector"), keypoints_indices_(new pcl::PointIndices)
+    {
+        kpl_params_default(&p_);
+        p_.threshold = prediction_th;
+        p_.non_maxima = non_maxima;
+        p_.draws_remove = non_maxima_draws_remove;
+        p_.radius_nms = (float)non_max_radius;
+        p_.n_annulus = n_annulus;
+        p_.n_bins = n_bins;
+        p_.radius_features = 0.f;            // pcl::Keypoint::search_radius_ starts at 0: setRadiusSearch is mandatory
+        create_rc_ = kpl_create(device, &ctx_);
+        if (create_rc_ != KPL_OK) std::fprintf(stderr, "[pcl::%s] no usable sm_100 device (kpl_create -> %d); there is no CPU path\n", name_.c_str(), create_rc_);
+    }
+    virtual ~KeypointLearningDetector() { kpl_destroy(ctx_); }
+    KeypointLearningDetector(const KeypointLearningDetector&) = delete;
+    KeypointLearningDetector& operator=(const KeypointLearningDetector&) = delete;
+
+    // impl/KeypointLearning.hpp:49-57
+    virtual void setInputCloud(const PointCloudInConstPtr& cloud)
+    {
+        if (normals_ && input_ && cloud != input_) normals_.reset();
+        input_ = cloud;
+    }
+    virtual void setNormals(const PointCloudNConstPtr& normals) { normals_ = normals; }
+    virtual void setNonMaxima(bool v) { p_.non_maxima = v; }
+    virtual void setNonMaximaDrawsRemove(bool v) { p_.draws_remove = v; }
+    virtual void setNonMaximaDrawsThreshold(float v) { p_.draws_threshold = v; }
+    virtual void setPredictionThreshold(double th) { p_.threshold = th; }
+    virtual void setNonMaxRadius(double r) { p_.radius_nms = (float)r; }
+    virtual void setNAnnulus(int n) { p_.n_annulus = n; }
+    virtual void setNBins(int n) { p_.n_bins = n; }
+    void setRadiusSearch(double r) { p_.radius_features = (float)r; }          // pcl::Keypoint
+    void setKSearch(int) {}                                                     // pcl::Keypoint (k search is an error with a radius, see initCompute)
+    void setCellsPerRadius(int cpr) { p_.cells_per_radius = cpr; }             // B200 build only
+
+    // impl/KeypointLearning.hpp:159-176
+    virtual bool loadForest(const std::string& path)
+    {
+        if (!ctx_) return false;
+        if (kpl_load_forest(ctx_, path.c_str()) != KPL_OK) {
+            std::fprintf(stderr, "[pcl::%s::loadForest] impossible to load random forest with path %s (%s)\n", name_.c_str(), path.c_str(), kpl_last_error(ctx_));
+            return false;
+        }
+        int32_t ntrees = 0;
+        kpl_forest_info(ctx_, &ntrees, nullptr, nullptr, nullptr);
+        return ntrees != 0;
+    }
+
+    // pcl::Keypoint::compute -> initCompute / detectKeypoints (impl/KeypointLearning.hpp:116-156,179-263)
+    void compute(PointCloudOut& output)
+    {
+        output.points.clear(); output.width = output.height = 0;
+        keypoints_indices_.reset(new pcl::PointIndices);
+        if (!initCompute()) return;
+        const int64_t n = (int64_t)input_->size();
+        response_.assign((size_t)n, 0.f);
+        std::vector<int32_t> idx((size_t)std::max<int64_t>(n, 1));
+        int64_t nkp = 0;
+        const float* nrm = normals_ ? reinterpret_cast<const float*>(normals_->points.data()) : nullptr;
+        int rc = kpl_detect(ctx_, reinterpret_cast<const float*>(input_->points.data()), (int32_t)sizeof(PointInT), nrm, (int32_t)sizeof(NormalT),
+                            nullptr, n, response_.data(), idx.data(), &nkp);
+        if (rc != KPL_OK) {
+            std::fprintf(stderr, "[pcl::%s::compute] %s\n", name_.c_str(), kpl_last_error(ctx_));
+            return;
+        }
+        output.points.reserve((size_t)nkp);
+        for (int64_t k = 0; k < nkp; ++k) {
+            const PointInT& in = input_->points[(size_t)idx[(size_t)k]];
+            PointOutT o;
+            o.x = in.x; o.y = in.y; o.z = in.z;
+            o.intensity = response_[(size_t)idx[(size_t)k]];
+            output.points.push_back(o);
+            keypoints_indices_->indices.push_back(idx[(size_t)k]);
+        }
+        output.height = 1;
+        output.width = (uint32_t)output.points.size();
+        output.is_dense = p_.non_maxima ? true : input_->is_dense;               // hpp:192-193,258-260
+    }
+    pcl::PointIndicesConstPtr getKeypointsIndices() const { return keypoints_indices_; }
+    const std::vector<float>& getResponse() const { return response_; }          // the `response` cloud's intensities (hpp:181-187)
+
+    // impl/KeypointLearning.hpp:299-318 (cv::Mat -> KplFeatureMatrix)
+    KplFeatureMatrix computePointsForTrainingFeatures(pcl::PointIndicesConstPtr indices)
+    {
+        KplFeatureMatrix m;
+        if (!indices || !initCompute()) return m;
+        const int F = p_.n_annulus * p_.n_bins;
+        m.data.assign(indices->indices.size() * (size_t)F, 0.f);
+        const float* nrm = normals_ ? reinterpret_cast<const float*>(normals_->points.data()) : nullptr;
+        int rc = kpl_features(ctx_, reinterpret_cast<const float*>(input_->points.data()), (int32_t)sizeof(PointInT), nrm, (int32_t)sizeof(NormalT),
+                              (int64_t)input_->size(), indices->indices.data(), (int64_t)indices->indices.size(), m.data.data());
+        if (rc != KPL_OK) {
+            std::fprintf(stderr, "[pcl::%s::computePointsForTrainingFeatures] %s\n", name_.c_str(), kpl_last_error(ctx_));
+            m.data.clear();
+            return m;
+        }
+        m.rows = (int)indices->indices.size(); m.cols = F;
+        return m;
+    }
+
+    kpl_ctx* context() { return ctx_; }
+
+protected:
+    bool initCompute()
+    {
+        if (!ctx_ || !input_) {
+            std::fprintf(stderr, "[pcl::%s::initCompute] init failed!\n", name_.c_str());
+            return false;
+        }
+        if (!(p_.radius_features > 0.f)) {        // pcl::Keypoint::initCompute: neither radius nor k set
+            std::fprintf(stderr, "[pcl::%s::initCompute] Neither radius nor K defined! Set one of them to zero first and then re-run compute ().\n", name_.c_str());
+            return false;
+        }
+        if (normals_ && normals_->size() != input_->size()) {
+            std::fprintf(stderr, "[pcl::%s::initCompute] normals given, but the number of normals does not match the number of input points!\n", name_.c_str());
+            return false;
+        }
+        kpl_params q = p_;
+        if (!normals_) {
+            // hpp:125-148: unorganized -> NormalEstimation.setRadiusSearch(search_radius_); organized -> integral images (unsupported)
+            std::printf("Computing normals for KPL\n");
+            if (input_->isOrganized()) {
+                std::fprintf(stderr, "[pcl::%s::initCompute] organized clouds (IntegralImageNormalEstimation) are not supported by the B200 build\n", name_.c_str());
+                return false;
+            }
+            q.normals_mode = KPL_NORMALS_RADIUS;
+            q.viewpoint[0] = input_->sensor_origin_[0]; q.viewpoint[1] = input_->sensor_origin_[1]; q.viewpoint[2] = input_->sensor_origin_[2];
+        }
+        if (kpl_set_params(ctx_, &q) != KPL_OK) {
+            std::fprintf(stderr, "[pcl::%s::initCompute] %s\n", name_.c_str(), kpl_last_error(ctx_));
+            return false;
+        }
+        return true;
+    }
+
+    std::string name_;
+    kpl_ctx* ctx_ = nullptr;
+    int create_rc_ = KPL_OK;
+    kpl_params p_;
+    PointCloudInConstPtr input_;
+    PointCloudNConstPtr normals_;
+    pcl::PointIndicesPtr keypoints_indices_;
+    std::vector<float> response_;
+};
+
+}  // namespace keypoints
+}  // namespace pcl
