@@ -229,8 +229,25 @@ def run_b200(args):
                "api": "kpl_detect (host xyz, pinned; normals estimated on device; scores + keypoint indices copied back)"}
         del sc_host
     else:
-        e2e = {"value": value, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
-               "note": "multi-GPU e2e = device-resident slabs + NCCL halo exchange inside the timed step"}
+        # every step: owned slab H2D from pinned host memory, halo exchange + detection, keypoints D2H on rank 0
+        steps_e2e = max(1, min(args.steps, 3))
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        n_kp_host = 0
+        for _ in range(steps_e2e):
+            job.xyz4.copy_(job.host_xyz4, non_blocking=True)
+            job.step(det)
+            if rank == 0:
+                n_kp_host = len(job.last_global_keypoints.cpu())
+        e1.record(stream)
+        barrier()
+        tms = torch.tensor([e0.elapsed_time(e1) / steps_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        e2e_ms = float(tms.item())
+        e2e = {"value": n_total / (e2e_ms * 1e-3), "unit": "points/s", "h2d_bytes_per_step": int(n_total * 16),
+               "d2h_bytes_per_step": int(n_kp_host * 8), "ms_per_step": e2e_ms,
+               "api": "SlabJob.step: owned slab H2D from pinned host, NCCL halo exchange, kpl_detect_device, global keypoint list to host"}
 
     # ---- roofline of the dominant kernel (feature_kernel), algorithmic bytes per SURVEY.md 8d -------
     pairs_self = st["feature_pairs"] + st["n_scored"]            # K_f with the query itself included

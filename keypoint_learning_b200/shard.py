@@ -113,7 +113,10 @@ class SlabJob:
         self.n_total = len(xyz)
         xyz4 = np.ones((len(own), 4), np.float32)
         xyz4[:, :3] = xyz[own]
-        self.xyz4 = torch.from_numpy(xyz4).to(self.device)
+        self.host_xyz4 = torch.from_numpy(xyz4)
+        if self.device.type == "cuda":
+            self.host_xyz4 = self.host_xyz4.pin_memory()
+        self.xyz4 = self.host_xyz4.to(self.device)
         self.gidx = torch.from_numpy(own.astype(np.int64)).to(self.device)
         self.cx = torch.from_numpy(cx[own].astype(np.int32)).to(self.device)
         # the local grid: global origin, x offset so that local keys stay small
