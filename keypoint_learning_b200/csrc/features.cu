@@ -32,6 +32,7 @@ static constexpr int FEAT_WARPS = 4;
 struct FeatParams {
     int n, A, B, F, reach, span;
     float r2, support, adim, ahalf, ainv, bdim, bhalf, binv, cellf, rcull2;
+    uint64_t one2;   // (1.0f, 1.0f), opaque to the compiler: see dist2_x2
 };
 
 __device__ __forceinline__ void key_to_cell_f(uint32_t key, int dimx, int dimy, int& cx, int& cy, int& cz)
@@ -54,12 +55,14 @@ __device__ __forceinline__ float fast_sqrt_core(float x)
     const float e = __fmaf_rn(-s, s, x);
     return __fmaf_rn(e, h, s);
 }
+// The caller guarantees x < FAST_SQRT_HI (x < r2, and the FAST variant is only launched when r2 <= 2^40).
 template <bool FAST>
 __device__ __forceinline__ float ksqrt(float x)
 {
     if (!FAST) return __fsqrt_rn(x);
-    if (!(x >= FAST_SQRT_LO && x < FAST_SQRT_HI)) return __fsqrt_rn(x);   // zero (duplicates), denormal, huge
-    return fast_sqrt_core(x);
+    float r = fast_sqrt_core(x);
+    if (!(x >= FAST_SQRT_LO)) r = __fsqrt_rn(x);   // zero (duplicate points) and denormal-range d2: rare
+    return r;
 }
 __device__ __forceinline__ float fast_div_core(float x, float c, float cinv)
 {
@@ -73,14 +76,55 @@ __device__ __forceinline__ float kdiv(float x, float c, float cinv)
     return FAST ? fast_div_core(x, c, cinv) : __fdiv_rn(x, c);
 }
 
+// ---- packed FP32 (sm_100 FADD2 / FMUL2 / FFMA2): two IEEE RN operations per issued instruction ---
+__device__ __forceinline__ uint64_t pack2(float lo, float hi)
+{
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b)
+{
+    uint64_t r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b)
+{
+    uint64_t r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c)
+{
+    uint64_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+// FLANN L2_Simple for two candidates at once: ((dx*dx) + dy*dy) + dz*dz, every product and sum rounded.
+// The sums are written RN(m*1 + acc) with `one` = (1.0f, 1.0f) passed at RUN time: ptxas 12.9 contracts a
+// packed mul feeding a packed add into FFMA2 even for .rn operands, which would change d2 and with it
+// the neighbour sets; a product by an opaque 1.0 is exact, rounds once and cannot be folded.
+__device__ __forceinline__ uint64_t dist2_x2(uint64_t qx, uint64_t qy, uint64_t qz, uint64_t cx, uint64_t cy, uint64_t cz, uint64_t one)
+{
+    const uint64_t dx = sub2(qx, cx), dy = sub2(qy, cy), dz = sub2(qz, cz);
+    const uint64_t mx = mul2(dx, dx), my = mul2(dy, dy), mz = mul2(dz, dz);
+    return fma2(mz, one, fma2(my, one, mx));     // RN(RN(mx + my) + mz); addition commutes bit-exactly
+}
+
 // One thread per (binade, mantissa): result[0] counts sqrt mismatches over [2^-40, 2^40), result[1]
 // / result[2] division mismatches for the annulus / bin width over every mantissa of [1, 2) and [-2,-1)
-// (exact power-of-two scaling extends the proof to every binade without under/overflow).
-__global__ void __launch_bounds__(256) selftest_kernel(float adim, float ainv, float bdim, float binv, unsigned* __restrict__ result)
+// (exact power-of-two scaling extends the proof to every binade without under/overflow), result[3]
+// mismatches of the packed squared distance against the scalar dist2() on values built from the mantissa.
+__global__ void __launch_bounds__(256) selftest_kernel(float adim, float ainv, float bdim, float binv, uint64_t one2, unsigned* __restrict__ result)
 {
     const uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;   // 2^23 mantissas
     if (m >= (1u << 23)) return;
-    unsigned bad_s = 0, bad_a = 0, bad_b = 0;
+    unsigned bad_s = 0, bad_a = 0, bad_b = 0, bad_p = 0;
     for (int ex = 127 - 40; ex < 127 + 40; ++ex) {
         const float x = __uint_as_float(((uint32_t)ex << 23) | m);
         bad_s += (__float_as_uint(fast_sqrt_core(x)) != __float_as_uint(__fsqrt_rn(x)));
@@ -90,28 +134,57 @@ __global__ void __launch_bounds__(256) selftest_kernel(float adim, float ainv, f
     bad_a += (__float_as_uint(fast_div_core(-x1, adim, ainv)) != __float_as_uint(__fdiv_rn(-x1, adim)));
     bad_b += (__float_as_uint(fast_div_core(x1, bdim, binv)) != __float_as_uint(__fdiv_rn(x1, bdim)));
     bad_b += (__float_as_uint(fast_div_core(-x1, bdim, binv)) != __float_as_uint(__fdiv_rn(-x1, bdim)));
+    {
+        uint32_t h = m * 2654435761u + 12345u;
+        float v[9];
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+            h = h * 1664525u + 1013904223u;
+            v[t] = __uint_as_float(((h >> 31) << 31) | ((118u + ((h >> 23) & 15u)) << 23) | (h & 0x7FFFFFu));   // +-[2^-9, 2^7)
+        }
+        const uint64_t d = dist2_x2(pack2(v[0], v[0]), pack2(v[1], v[1]), pack2(v[2], v[2]),
+                                    pack2(v[3], v[6]), pack2(v[4], v[7]), pack2(v[5], v[8]), one2);
+        float d0, d1;
+        unpack2(d, d0, d1);
+        bad_p += (__float_as_uint(d0) != __float_as_uint(dist2(v[0], v[1], v[2], v[3], v[4], v[5])));
+        bad_p += (__float_as_uint(d1) != __float_as_uint(dist2(v[0], v[1], v[2], v[6], v[7], v[8])));
+    }
     bad_s = __reduce_add_sync(0xFFFFFFFFu, bad_s);
     bad_a = __reduce_add_sync(0xFFFFFFFFu, bad_a);
     bad_b = __reduce_add_sync(0xFFFFFFFFu, bad_b);
+    bad_p = __reduce_add_sync(0xFFFFFFFFu, bad_p);
     if ((threadIdx.x & 31) == 0) {
         if (bad_s) atomicAdd(result + 0, bad_s);
         if (bad_a) atomicAdd(result + 1, bad_a);
         if (bad_b) atomicAdd(result + 2, bad_b);
+        if (bad_p) atomicAdd(result + 3, bad_p);
     }
 }
 
 // src/KeypointLearning.cpp:41-65 / :68-92 with float abs; dim = bin width, half = dim/2, inv = fl(1/dim).
+// v >= 0 and RN(v/dim) <= n on this path, so `if (i == n) i--` is min(i, n-1) and the two pair clamps
+// (`-1 -> 0`, `n -> i`) are a clamp of i +- 1 to [0, n-1].
 template <bool FAST>
-__device__ __forceinline__ void soft_bin_k(float v, float dim, float half, float inv, int n, int& idx, int& pair, float& w)
+__device__ __forceinline__ void soft_bin_k(float v, float dim, float half, float inv, int nm1, int& idx, int& pair, float& w)
 {
-    int i = __float2int_rd(kdiv<FAST>(v, dim, inv));     // static_cast<int>(floor(v/dim))
-    if (i == n) i--;
+    const int i = min(__float2int_rd(kdiv<FAST>(v, dim, inv)), nm1);   // static_cast<int>(floor(v/dim)); if (i == n) i--
     const float center = __fadd_rn(__fmul_rn((float)i, dim), half);
     const float ww = kdiv<FAST>(__fsub_rn(v, center), dim, inv);
-    int p = (ww > 0.0f) ? i + 1 : i - 1;
-    if (p == -1) p = 0;
-    if (p == n) p = i;
+    const int p = min(max(i + ((ww > 0.0f) ? 1 : -1), 0), nm1);
     idx = i; pair = p; w = fabsf(ww);
+}
+
+// shared-memory accesses of the vote loop by 32-bit shared address (keeps the address arithmetic to one
+// add per cell and the four read-modify-writes in source order)
+__device__ __forceinline__ float lds_f32(unsigned a)
+{
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts_f32(unsigned a, float v)
+{
+    asm volatile("st.shared.f32 [%0], %1;" :: "r"(a), "f"(v));
 }
 
 template <bool FAST>
@@ -122,10 +195,9 @@ feature_kernel(const float4* __restrict__ s_pos, const float4* __restrict__ s_nr
 {
     extern __shared__ __align__(16) float smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int per_warp = P.F * 32 + 320;
+    const int per_warp = P.F * 32 + 192;
     float* hist = smem + warp * per_warp;
-    float4* tpos = reinterpret_cast<float4*>(hist + P.F * 32);   // AoS tile for the broadcast membership pass
-    float* sx = hist + P.F * 32 + 128;                            // SoA tile for the per-lane vote pass
+    float* sx = hist + P.F * 32;                                  // SoA candidate tile: x, y, z, nx, ny, nz
     float* sy = sx + 32; float* sz = sy + 32; float* snx = sz + 32; float* sny = snx + 32; float* snz = sny + 32;
 
     const int q0 = (blockIdx.x * FEAT_WARPS + warp) * 32;
@@ -147,10 +219,13 @@ feature_kernel(const float4* __restrict__ s_pos, const float4* __restrict__ s_nr
         // a query without a finite normal is not scored (hpp:277): its row stays zero
         if (!(isfinite(qn.x) && isfinite(qn.y) && isfinite(qn.z))) { active = false; qp.x = CUDART_NAN_F; }
     }
-    const uint32_t qidx = __float_as_uint(qp.w);
 
     for (int f = 0; f < P.F; ++f) hist[f * 32 + lane] = 0.0f;
     unsigned npairs = 0, ncand = 0;
+    const unsigned hb = (unsigned)__cvta_generic_to_shared(hist) + (unsigned)lane * 4u;   // this lane's histogram column
+    const unsigned row_bytes = (unsigned)P.B * 128u;
+    const int Am1 = P.A - 1, Bm1 = P.B - 1;
+    const uint64_t QY = pack2(qp.y, qp.y), QZ = pack2(qp.z, qp.z);
 
     // The 32 queries are consecutive in (z, y, x) cell order but may straddle the end of a cell row
     // (or sit in far-apart cells of a sparse row).  They are processed in groups of lanes that share
@@ -165,6 +240,7 @@ feature_kernel(const float4* __restrict__ s_pos, const float4* __restrict__ s_nr
         remaining &= ~__ballot_sync(0xFFFFFFFFu, member);
         const int maxx = __reduce_max_sync(0xFFFFFFFFu, member ? cx : minx);
         const float px = member ? qp.x : CUDART_NAN_F;
+        const uint64_t QX = pack2(px, px);
 
         const int y0 = max(gy0 - P.reach, 0), y1 = min(gy0 + P.reach, dimy - 1);
         const int z0 = max(gz0 - P.reach, 0), z1 = min(gz0 + P.reach, dimz - 1);
@@ -214,49 +290,61 @@ feature_kernel(const float4* __restrict__ s_pos, const float4* __restrict__ s_nr
             // neighbours with a non-finite normal never vote (hpp:338): poison the position
             if (!(isfinite(cn.x) && isfinite(cn.y) && isfinite(cn.z))) cp.x = CUDART_NAN_F;
             __syncwarp();                          // previous tile fully consumed
-            tpos[lane] = cp;
             sx[lane] = cp.x; sy[lane] = cp.y; sz[lane] = cp.z;
             snx[lane] = cn.x; sny[lane] = cn.y; snz[lane] = cn.z;
             const int cnt = min(32, te - tb);
+            const unsigned self = (unsigned)(q - tb);   // slot of the query itself when it lies in this tile
             have = next_tile(tb, te);
             cp = make_float4(CUDART_NAN_F, 0.f, 0.f, 0.f);
             if (have && tb + lane < te) { cp = __ldg(s_pos + tb + lane); cn = __ldg(s_nrm + tb + lane); }
             __syncwarp();
             ncand += cnt;
 
-            // phase 1: membership mask (slots >= cnt hold NaN positions and can never pass)
+            // phase 1: membership mask, candidate k -> bit 31-k (slots >= cnt hold NaN positions and never
+            // pass).  Four candidates per step: broadcast 128-bit loads of the SoA tile, packed FP32 math.
             uint32_t mask = 0;
-            for (int k0 = 0; k0 < cnt; k0 += 8) {
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const float4 c = tpos[k0 + u];
-                    const float d2 = dist2(px, qp.y, qp.z, c.x, c.y, c.z);
-                    if (d2 < P.r2 && __float_as_uint(c.w) != qidx) mask |= 1u << (k0 + u);
+            for (int k0 = 0; k0 < 32; k0 += 8) {
+                if (k0 < cnt) {
+#pragma unroll
+                    for (int u = 0; u < 8; u += 4) {
+                        const ulonglong2 X = *reinterpret_cast<const ulonglong2*>(sx + k0 + u);
+                        const ulonglong2 Y = *reinterpret_cast<const ulonglong2*>(sy + k0 + u);
+                        const ulonglong2 Z = *reinterpret_cast<const ulonglong2*>(sz + k0 + u);
+                        float d0, d1, d2, d3;
+                        unpack2(dist2_x2(QX, QY, QZ, X.x, Y.x, Z.x, P.one2), d0, d1);
+                        unpack2(dist2_x2(QX, QY, QZ, X.y, Y.y, Z.y, P.one2), d2, d3);
+                        if (d0 < P.r2) mask |= 0x80000000u >> (k0 + u);
+                        if (d1 < P.r2) mask |= 0x80000000u >> (k0 + u + 1);
+                        if (d2 < P.r2) mask |= 0x80000000u >> (k0 + u + 2);
+                        if (d3 < P.r2) mask |= 0x80000000u >> (k0 + u + 3);
+                    }
                 }
             }
+            if (self < 32u) mask &= ~(0x80000000u >> self);   // the query is not its own neighbour (hpp:336)
             npairs += __popc(mask);
 
             // phase 2: votes of this lane's neighbours, ascending sorted position
             while (mask) {
-                const int k = __ffs(mask) - 1;
-                mask &= mask - 1;
-                const float d2 = dist2(qp.x, qp.y, qp.z, sx[k], sy[k], sz[k]);
-                float cosine = __fsub_rn(1.0f, dot3_eigen(qn.x, qn.y, qn.z, snx[k], sny[k], snz[k]));   // hpp:341-342
-                const float dist = ksqrt<FAST>(d2);                                                     // hpp:345 sqrt(distances[..])
+                const int msb = 31 - __clz(mask);              // candidate k sits at bit 31-k: highest bit = smallest k
+                mask &= ~(1u << msb);
+                const float* t = sx + 31 - msb;
+                const float d2 = dist2(qp.x, qp.y, qp.z, t[0], t[32], t[64]);
+                float cosine = __fsub_rn(1.0f, dot3_eigen(qn.x, qn.y, qn.z, t[96], t[128], t[160]));   // hpp:341-342
+                const float dist = ksqrt<FAST>(d2);                                                    // hpp:345 sqrt(distances[..])
                 int a, ap, b, bp;
                 float wa, wb;
-                soft_bin_k<FAST>(dist, P.adim, P.ahalf, P.ainv, P.A, a, ap, wa);
-                if (cosine < 0.0f) cosine = 0.0f;
-                if (cosine > 2.0f) cosine = 2.0f;
-                soft_bin_k<FAST>(cosine, P.bdim, P.bhalf, P.binv, P.B, b, bp, wb);
+                soft_bin_k<FAST>(dist, P.adim, P.ahalf, P.ainv, Am1, a, ap, wa);
+                cosine = fminf(fmaxf(cosine, 0.0f), 2.0f);          // src/KeypointLearning.cpp:70-73 (cosine is finite here)
+                soft_bin_k<FAST>(cosine, P.bdim, P.bhalf, P.binv, Bm1, b, bp, wb);
                 const float ua = __fsub_rn(1.0f, wa), ub = __fsub_rn(1.0f, wb);
-                float* h0 = hist + (a * P.B) * 32 + lane;
-                float* h1 = hist + (ap * P.B) * 32 + lane;
+                const unsigned ra = hb + (unsigned)a * row_bytes, rp = hb + (unsigned)ap * row_bytes;
+                const unsigned ob = (unsigned)b << 7, op = (unsigned)bp << 7;
                 // the four `+=` of hpp:350-355, in source order (cells may coincide)
-                h0[b * 32] = __fadd_rn(h0[b * 32], __fmul_rn(ub, ua));
-                h0[bp * 32] = __fadd_rn(h0[bp * 32], __fmul_rn(wb, ua));
-                h1[b * 32] = __fadd_rn(h1[b * 32], __fmul_rn(ub, wa));
-                h1[bp * 32] = __fadd_rn(h1[bp * 32], __fmul_rn(wb, wa));
+                sts_f32(ra + ob, __fadd_rn(lds_f32(ra + ob), __fmul_rn(ub, ua)));
+                sts_f32(ra + op, __fadd_rn(lds_f32(ra + op), __fmul_rn(wb, ua)));
+                sts_f32(rp + ob, __fadd_rn(lds_f32(rp + ob), __fmul_rn(ub, wa)));
+                sts_f32(rp + op, __fadd_rn(lds_f32(rp + op), __fmul_rn(wb, wa)));
             }
         }
     }
@@ -300,12 +388,13 @@ static cudaError_t fast_math_verdict(kpl_ctx* c, const FeatParams& P, bool& fast
     unsigned* d_res = reinterpret_cast<unsigned*>(c->counters.p + 6);   // counters[6..7] are scratch
     cudaError_t e;
     if ((e = cudaMemsetAsync(d_res, 0, 4 * sizeof(unsigned), c->stream))) return e;
-    selftest_kernel<<<(1u << 23) / 256, 256, 0, c->stream>>>(P.adim, P.ainv, P.bdim, P.binv, d_res);
-    unsigned h[3];
+    selftest_kernel<<<(1u << 23) / 256, 256, 0, c->stream>>>(P.adim, P.ainv, P.bdim, P.binv, P.one2, d_res);
+    unsigned h[4];
     if ((e = cudaMemcpyAsync(h, d_res, sizeof h, cudaMemcpyDeviceToHost, c->stream))) return e;
     if ((e = cudaStreamSynchronize(c->stream))) return e;
     if ((e = cudaMemsetAsync(d_res, 0, 4 * sizeof(unsigned), c->stream))) return e;
-    fast = (h[0] == 0 && h[1] == 0 && h[2] == 0);
+    if (h[3] != 0) return cudaErrorAssert;   // packed FP32 is not IEEE RN on this device: no exact path exists
+    fast = (h[0] == 0 && h[1] == 0 && h[2] == 0) && P.r2 <= FAST_SQRT_HI;
     cache.push_back({P.adim, P.bdim, c->device, fast});
     c->launches++;
     return cudaGetLastError();
@@ -328,12 +417,13 @@ cudaError_t launch_features(kpl_ctx* c, int64_t n, bool use_role)
     P.binv = 1.0f / P.bdim;
     P.cellf = (float)c->grid.cell;
     P.rcull2 = (float)(r * r * (1.0 + 1e-5));
+    P.one2 = 0x3F8000003F800000ull;
     cudaError_t e;
     if ((e = ensure(c->feat, (size_t)n * P.F))) return e;
     bool fast = false;
     if (!getenv("KPL_NO_FAST_MATH") && (e = fast_math_verdict(c, P, fast))) return e;
     c->fast_math = fast;
-    size_t smem = (size_t)FEAT_WARPS * (P.F * 32 + 320) * sizeof(float);
+    size_t smem = (size_t)FEAT_WARPS * (P.F * 32 + 192) * sizeof(float);
     if (smem > 227 * 1024) return cudaErrorInvalidValue;
     static size_t configured[2] = {0, 0};
     auto kern = fast ? feature_kernel<true> : feature_kernel<false>;
