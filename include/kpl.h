@@ -156,6 +156,9 @@ KPL_API int kpl_detect_device(kpl_ctx* ctx, const void* d_xyz4, const void* d_no
                               void* d_scores, void* d_kp_idx, int64_t* n_kp_out);
 
 /* ---- introspection --------------------------------------------------------------------------- */
+/* kpl_detect* score each point inside the feature kernel and do not write the A*B feature rows
+ * (the cv::Mat of impl/KeypointLearning.hpp:366-369) to memory; on != 0 keeps them for kpl_fetch. */
+KPL_API int kpl_set_keep_intermediates(kpl_ctx* ctx, int on);
 KPL_API int kpl_get_timings(const kpl_ctx* ctx, kpl_timings* t);
 KPL_API int kpl_get_stats(const kpl_ctx* ctx, kpl_stats* s);
 /* Device copies of intermediate results of the last call, for parity tests: what = "normals"

@@ -2,6 +2,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include "kpl_internal.h"
@@ -114,6 +115,13 @@ int kpl_set_stream(kpl_ctx* ctx, void* s)
 {
     if (!ctx) return KPL_E_INVALID;
     ctx->stream = s ? (cudaStream_t)s : ctx->own_stream;
+    return KPL_OK;
+}
+
+int kpl_set_keep_intermediates(kpl_ctx* ctx, int on)
+{
+    if (!ctx) return KPL_E_INVALID;
+    ctx->keep_intermediates = on != 0;
     return KPL_OK;
 }
 
@@ -282,10 +290,13 @@ static int run_detect(kpl_ctx* ctx, const float4* d_xyz, const float4* d_nrm, co
     if (rc) return rc;
     KPL_CUDA(launch_check_normals(ctx, n));
     KPL_CUDA(cudaEventRecord(ctx->ev[2], ctx->stream));
-    KPL_CUDA(launch_features(ctx, n, d_role != nullptr));
-    ctx->last_has_features = true; ctx->last_F = F;
+    // the forest is evaluated in the tail of the feature kernel; KPL_NO_FUSE=1 keeps the two-kernel path for A/B tests
+    const bool fuse = getenv("KPL_NO_FUSE") == nullptr;
+    const bool rows = ctx->keep_intermediates || !fuse;
+    KPL_CUDA(launch_features(ctx, n, d_role != nullptr, fuse, rows));
+    ctx->last_has_features = rows; ctx->last_F = F;
     KPL_CUDA(cudaEventRecord(ctx->ev[3], ctx->stream));
-    KPL_CUDA(launch_forest(ctx, n, d_role != nullptr));
+    if (!fuse) KPL_CUDA(launch_forest(ctx, n, d_role != nullptr));
     KPL_CUDA(cudaEventRecord(ctx->ev[4], ctx->stream));
     if (P.non_maxima) KPL_CUDA(launch_nms(ctx, n, d_role != nullptr));
     else KPL_CUDA(launch_all_flags(ctx, n));
@@ -405,7 +416,7 @@ int kpl_features(kpl_ctx* ctx, const float* xyz, int32_t xyz_stride, const float
     KPL_CUDA(cudaMemsetAsync(ctx->counters.p, 0, 8 * sizeof(unsigned long long), ctx->stream));
     if ((rc = prepare_grid(ctx, ctx->in_xyz.p, normals ? ctx->in_nrm.p : nullptr, indices ? ctx->in_role.p : nullptr, n))) return rc;
     if ((rc = prepare_normals(ctx, normals != nullptr, n))) return rc;
-    KPL_CUDA(launch_features(ctx, n, indices != nullptr));
+    KPL_CUDA(launch_features(ctx, n, indices != nullptr, false, true));
     ctx->last_has_features = true; ctx->last_F = F;
     KPL_CUDA(ensure(ctx->scratch_f, (size_t)n * F + (size_t)m * F));
     float* d_orig = ctx->scratch_f.p;
@@ -514,7 +525,7 @@ int kpl_fetch(kpl_ctx* ctx, const char* what, float* out, int64_t capacity_float
         KPL_CUDA(launch_unsort_normals(ctx, n, (float4*)ctx->scratch_f.p));
         KPL_CUDA(cudaMemcpyAsync(out, ctx->scratch_f.p, (size_t)n * 16, cudaMemcpyDeviceToHost, ctx->stream));
     } else if (!strcmp(what, "features")) {
-        if (!ctx->last_has_features) return fail(ctx, KPL_E_INVALID, "no features from the last call");
+        if (!ctx->last_has_features) return fail(ctx, KPL_E_INVALID, "no feature rows from the last call (kpl_detect keeps them only after kpl_set_keep_intermediates(ctx, 1))");
         const int F = ctx->last_F;
         if (capacity_floats < n * F) return fail(ctx, KPL_E_INVALID, "fetch buffer too small");
         KPL_CUDA(ensure(ctx->scratch_f, (size_t)n * F));

@@ -24,6 +24,7 @@
 #include <cstdlib>
 #include "kpl_internal.h"
 #include "kpl_math.cuh"
+#include "forest.cuh"
 
 namespace kpl {
 
@@ -33,6 +34,17 @@ struct FeatParams {
     int n, A, B, F, reach, span;
     float r2, support, adim, ahalf, ainv, bdim, bhalf, binv, cellf, rcull2;
     uint64_t one2;   // (1.0f, 1.0f), opaque to the compiler: see dist2_x2
+};
+
+// Forest evaluation fused into the tail of the feature kernel (nodes == nullptr: not fused): the
+// normalised row is scored straight out of the lane's shared-memory histogram column, so the
+// A*B*4-byte row never travels to HBM and back.
+struct FusedForest {
+    const PackedNode* nodes;
+    const int32_t* roots;
+    int ntrees;
+    float* s_score;   // sorted order
+    float* score;     // original order
 };
 
 __device__ __forceinline__ void key_to_cell_f(uint32_t key, int dimx, int dimy, int& cx, int& cy, int& cz)
@@ -191,7 +203,8 @@ template <bool FAST>
 __global__ void __launch_bounds__(FEAT_WARPS * 32)
 feature_kernel(const float4* __restrict__ s_pos, const float4* __restrict__ s_nrm, const uint32_t* __restrict__ skey,
                const int32_t* __restrict__ cell_start, const uint8_t* __restrict__ s_role,
-               int dimx, int dimy, int dimz, FeatParams P, float* __restrict__ feat, unsigned long long* __restrict__ counters)
+               int dimx, int dimy, int dimz, FeatParams P, FusedForest FF, float* __restrict__ feat,
+               unsigned long long* __restrict__ counters)
 {
     extern __shared__ __align__(16) float smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -207,7 +220,12 @@ feature_kernel(const float4* __restrict__ s_pos, const float4* __restrict__ s_nr
     if (active && s_role) active = (s_role[q] & 1) != 0;
     if (!__any_sync(0xFFFFFFFFu, active)) {
         const int nvalid = min(32, P.n - q0);
-        for (int e = lane; e < nvalid * P.F; e += 32) feat[(int64_t)q0 * P.F + e] = 0.0f;
+        if (feat)
+            for (int e = lane; e < nvalid * P.F; e += 32) feat[(int64_t)q0 * P.F + e] = 0.0f;
+        if (FF.nodes && q < P.n) {
+            FF.s_score[q] = CUDART_NAN_F;
+            FF.score[__float_as_uint(__ldg(&s_pos[q].w))] = CUDART_NAN_F;
+        }
         return;
     }
     float4 qp = make_float4(CUDART_NAN_F, 0.f, 0.f, 0.f), qn = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -361,8 +379,16 @@ feature_kernel(const float4* __restrict__ s_pos, const float4* __restrict__ s_nr
         }
     }
     __syncwarp();
+    // fused forest: score = 1 - sum/ntrees (hpp:281-287); unscored points (halo role, no finite normal) get NaN
+    if (FF.nodes) {
+        const float sc = active ? forest_score(hist + lane, 32, FF.nodes, FF.roots, FF.ntrees) : CUDART_NAN_F;
+        if (q < P.n) {
+            FF.s_score[q] = sc;
+            FF.score[__float_as_uint(__ldg(&s_pos[q].w))] = sc;
+        }
+    }
     // coalesced store of the warp's 32 rows (row-major, sorted order)
-    {
+    if (feat) {
         const int nvalid = min(32, P.n - q0);
         const int total = nvalid * P.F;
         float* dst = feat + (int64_t)q0 * P.F;
@@ -400,12 +426,13 @@ static cudaError_t fast_math_verdict(kpl_ctx* c, const FeatParams& P, bool& fast
     return cudaGetLastError();
 }
 
-cudaError_t launch_features(kpl_ctx* c, int64_t n, bool use_role)
+cudaError_t launch_features(kpl_ctx* c, int64_t n, bool use_role, bool fuse_forest, bool store_rows)
 {
     const kpl_params& U = c->params;
     FeatParams P;
     P.n = (int)n; P.A = U.n_annulus; P.B = U.n_bins; P.F = P.A * P.B; P.reach = c->grid.reach_feat;
-    P.span = (U.cells_per_radius + 3) / 4;
+    P.span = (U.cells_per_radius + 1) / 2;      // measured on the 1 M-point view: 2 at 4 cells per radius (gpurun_out/sweep1.log)
+    if (const char* e = getenv("KPL_FEAT_SPAN")) P.span = atoi(e);   // tuning experiments only
     const double r = (double)U.radius_features;
     P.r2 = (float)(r * r);                       // static_cast<float>(radius*radius), KdTreeFLANN::radiusSearch
     P.support = (float)r;                        // findAnnulusPair(.., (float)search_radius_, ..) hpp:345
@@ -419,7 +446,12 @@ cudaError_t launch_features(kpl_ctx* c, int64_t n, bool use_role)
     P.rcull2 = (float)(r * r * (1.0 + 1e-5));
     P.one2 = 0x3F8000003F800000ull;
     cudaError_t e;
-    if ((e = ensure(c->feat, (size_t)n * P.F))) return e;
+    if (store_rows && (e = ensure(c->feat, (size_t)n * P.F))) return e;
+    FusedForest FF = {nullptr, nullptr, 0, nullptr, nullptr};
+    if (fuse_forest) {
+        if ((e = ensure(c->s_score, n)) || (e = ensure(c->score, n))) return e;
+        FF = {c->forest.d_nodes, c->forest.d_roots, c->forest.ntrees, c->s_score.p, c->score.p};
+    }
     bool fast = false;
     if (!getenv("KPL_NO_FAST_MATH") && (e = fast_math_verdict(c, P, fast))) return e;
     c->fast_math = fast;
@@ -435,7 +467,8 @@ cudaError_t launch_features(kpl_ctx* c, int64_t n, bool use_role)
     int blocks = (warps + FEAT_WARPS - 1) / FEAT_WARPS;
     kern<<<blocks, FEAT_WARPS * 32, smem, c->stream>>>(c->s_pos.p, c->s_nrm.p, c->key_b.p, c->cell_start.p,
                                                        use_role ? c->s_role.p : nullptr,
-                                                       c->grid.dim[0], c->grid.dim[1], c->grid.dim[2], P, c->feat.p, c->counters.p);
+                                                       c->grid.dim[0], c->grid.dim[1], c->grid.dim[2], P, FF,
+                                                       store_rows ? c->feat.p : nullptr, c->counters.p);
     c->launches++;
     return cudaGetLastError();
 }

@@ -9,11 +9,11 @@
 #include <algorithm>
 #include "kpl_internal.h"
 #include "kpl_math.cuh"
+#include "forest.cuh"
 
 namespace kpl {
 
 static constexpr int FOREST_THREADS = 128;
-static constexpr int TREES_IN_FLIGHT = 4;
 
 __global__ void __launch_bounds__(FOREST_THREADS)
 forest_kernel(const float* __restrict__ feat, const PackedNode* __restrict__ nodes, const int32_t* __restrict__ roots,
@@ -41,43 +41,7 @@ forest_kernel(const float* __restrict__ feat, const PackedNode* __restrict__ nod
         score[orig] = CUDART_NAN_F;
         return;
     }
-    const float* x = sf + tid;
-    double sum = 0.0;
-    for (int t0 = 0; t0 < ntrees; t0 += TREES_IN_FLIGHT) {
-        int nd[TREES_IN_FLIGHT];
-        float val[TREES_IN_FLIGHT];
-        bool live[TREES_IN_FLIGHT];
-#pragma unroll
-        for (int u = 0; u < TREES_IN_FLIGHT; ++u) {
-            live[u] = (t0 + u) < ntrees;
-            nd[u] = live[u] ? __ldg(roots + t0 + u) : 0;
-            val[u] = 0.0f;
-        }
-        bool any = true;
-        while (any) {
-            any = false;
-#pragma unroll
-            for (int u = 0; u < TREES_IN_FLIGHT; ++u) {
-                if (live[u]) {
-                    const uint2 raw = __ldg(reinterpret_cast<const uint2*>(nodes + nd[u]));
-                    PackedNode node;
-                    node.thr = __uint_as_float(raw.x);
-                    node.packed = raw.y;
-                    const uint32_t var = node.packed & 1023u;
-                    if (var == KPL_LEAF_VAR) { val[u] = node.thr; live[u] = false; }
-                    else {
-                        // DTreesImpl::predictTrees: go left iff value <= split.c
-                        nd[u] = (x[var * FOREST_THREADS] <= node.thr) ? nd[u] + 1 : nd[u] + (int)(node.packed >> 10);
-                        any = true;
-                    }
-                }
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < TREES_IN_FLIGHT; ++u) sum += (double)val[u];   // exact: leaf values are small integers
-    }
-    const float fsum = __double2float_rn(sum);                           // predict() returns float
-    const float sc = __fsub_rn(1.0f, __fdiv_rn(fsum, __fmul_rn((float)ntrees, 1.0f)));  // hpp:287
+    const float sc = forest_score(sf + tid, FOREST_THREADS, nodes, roots, ntrees);
     s_score[i] = sc;
     score[orig] = sc;
     (void)counters;

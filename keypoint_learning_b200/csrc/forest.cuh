@@ -1,0 +1,54 @@
+// forest.cuh -- per-thread traversal of the packed forest, shared by forest_kernel (forest.cu) and the
+// fused tail of feature_kernel (features.cu).  Semantics: cv::ml::RTrees::predict(.., PREDICT_SUM)
+// (OpenCV DTreesImpl::predictTrees: left iff x[var] <= split.c, sum of leaf values) followed by the
+// score line of KeypointLearningDetector::runForest (impl/KeypointLearning.hpp:281-287).
+#pragma once
+#include "kpl_internal.h"
+#include "kpl_math.cuh"
+
+namespace kpl {
+
+static constexpr int TREES_IN_FLIGHT = 4;
+
+// x[var * stride] is feature `var` of this thread's point (a shared-memory column: bank == lane for
+// stride 32 / 128, so the data-dependent var never conflicts).  Four trees are walked concurrently so
+// four independent 8-byte node loads (L1 / L2 resident) are in flight per thread.
+__device__ __forceinline__ float forest_score(const float* x, int stride, const PackedNode* __restrict__ nodes,
+                                              const int32_t* __restrict__ roots, int ntrees)
+{
+    double sum = 0.0;
+    for (int t0 = 0; t0 < ntrees; t0 += TREES_IN_FLIGHT) {
+        int nd[TREES_IN_FLIGHT];
+        float val[TREES_IN_FLIGHT];
+        bool live[TREES_IN_FLIGHT];
+#pragma unroll
+        for (int u = 0; u < TREES_IN_FLIGHT; ++u) {
+            live[u] = (t0 + u) < ntrees;
+            nd[u] = live[u] ? __ldg(roots + t0 + u) : 0;
+            val[u] = 0.0f;
+        }
+        bool any = true;
+        while (any) {
+            any = false;
+#pragma unroll
+            for (int u = 0; u < TREES_IN_FLIGHT; ++u) {
+                if (live[u]) {
+                    const uint2 raw = __ldg(reinterpret_cast<const uint2*>(nodes + nd[u]));
+                    const float thr = __uint_as_float(raw.x);
+                    const uint32_t var = raw.y & 1023u;
+                    if (var == KPL_LEAF_VAR) { val[u] = thr; live[u] = false; }
+                    else {
+                        nd[u] = (x[var * stride] <= thr) ? nd[u] + 1 : nd[u] + (int)(raw.y >> 10);
+                        any = true;
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < TREES_IN_FLIGHT; ++u) sum += (double)val[u];   // exact: leaf values are small integers
+    }
+    const float fsum = __double2float_rn(sum);                                           // predict() returns float
+    return __fsub_rn(1.0f, __fdiv_rn(fsum, __fmul_rn((float)ntrees, 1.0f)));             // hpp:287
+}
+
+}  // namespace kpl

@@ -88,6 +88,7 @@ struct kpl_ctx {
     int last_F = 0;
     bool last_has_normals = false, last_has_features = false;
     bool fast_math = false;                      // feature kernel variant chosen by the arithmetic self-test
+    bool keep_intermediates = false;             // kpl_set_keep_intermediates: materialise feature rows in kpl_detect*
     cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
@@ -100,7 +101,7 @@ cudaError_t launch_normals_knn(kpl_ctx* c, int64_t n);
 cudaError_t launch_normals_radius(kpl_ctx* c, int64_t n);
 cudaError_t launch_flip_normals(kpl_ctx* c, int64_t n);
 cudaError_t launch_check_normals(kpl_ctx* c, int64_t n);
-cudaError_t launch_features(kpl_ctx* c, int64_t n, bool use_role);
+cudaError_t launch_features(kpl_ctx* c, int64_t n, bool use_role, bool fuse_forest, bool store_rows);
 cudaError_t launch_forest(kpl_ctx* c, int64_t n, bool use_role);
 cudaError_t launch_nms(kpl_ctx* c, int64_t n, bool use_role);
 cudaError_t launch_compact(kpl_ctx* c, int64_t n, int32_t* d_kp_idx_out);

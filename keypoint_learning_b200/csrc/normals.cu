@@ -24,6 +24,12 @@ __device__ __forceinline__ void key_to_cell(uint32_t key, const GridDesc& g, int
 }
 
 // K > 0: compile-time k, candidates in registers.  K == 0: runtime k <= 64, candidates in local memory.
+//
+// Search order: the query's own cell, then those of the 26 surrounding cells whose box can still hold a
+// point closer than the current k-th best (conservative lower bound on the distance to the cell), then --
+// only if the k-th best is not provably inside the 3x3x3 block -- growing rings that rescan everything.
+// The result is the exact k smallest candidates under the total order (d2, index), whatever the visiting
+// order, so it equals the sorted-kd-tree result the reference consumes.
 template <int K>
 __global__ void __launch_bounds__(128) normals_knn_kernel(const float4* __restrict__ s_pos, const uint32_t* __restrict__ skey,
                                                           const int32_t* __restrict__ cell_start, const float4* __restrict__ xyz,
@@ -39,50 +45,102 @@ __global__ void __launch_bounds__(128) normals_knn_kernel(const float4* __restri
     const float4 p = s_pos[i];
     int cx, cy, cz;
     key_to_cell(skey[i], g, cx, cy, cz);
-    int maxdim = max(g.dim[0], max(g.dim[1], g.dim[2]));
     int seen = 0;
-    for (int R = 1; R <= maxdim; ++R) {
 #pragma unroll
-        for (int t = 0; t < KM; ++t) { bd2[t] = CUDART_INF_F; bi[t] = 0xFFFFFFFFu; }
-        seen = 0;
-        int z0 = max(cz - R, 0), z1 = min(cz + R, g.dim[2] - 1);
-        int y0 = max(cy - R, 0), y1 = min(cy + R, g.dim[1] - 1);
-        int x0 = max(cx - R, 0), x1 = min(cx + R, g.dim[0] - 1);
-        for (int z = z0; z <= z1; ++z)
-            for (int y = y0; y <= y1; ++y) {
-                int64_t base = ((int64_t)z * g.dim[1] + y) * g.dim[0];
-                int s = __ldg(cell_start + base + x0), e = __ldg(cell_start + base + x1 + 1);
-                for (int j = s; j < e; ++j) {
-                    float4 c = __ldg(s_pos + j);
-                    float d2 = dist2(p.x, p.y, p.z, c.x, c.y, c.z);
-                    uint32_t oi = __float_as_uint(c.w);
-                    seen++;
-                    if (less_d2_idx(d2, oi, bd2[k - 1], bi[k - 1])) {
-                        if (K > 0) {
+    for (int t = 0; t < KM; ++t) { bd2[t] = CUDART_INF_F; bi[t] = 0xFFFFFFFFu; }
+
+    auto scan = [&](int s, int e) {
+        for (int j = s; j < e; ++j) {
+            float4 c = __ldg(s_pos + j);
+            float d2 = dist2(p.x, p.y, p.z, c.x, c.y, c.z);
+            uint32_t oi = __float_as_uint(c.w);
+            seen++;
+            if (less_d2_idx(d2, oi, bd2[k - 1], bi[k - 1])) {
+                if (K > 0) {
 #pragma unroll
-                            for (int t = KM - 1; t >= 0; --t) {
-                                float pd = (t > 0) ? bd2[t > 0 ? t - 1 : 0] : -CUDART_INF_F;
-                                uint32_t pi = (t > 0) ? bi[t > 0 ? t - 1 : 0] : 0u;
-                                if (less_d2_idx(d2, oi, pd, pi)) { bd2[t] = pd; bi[t] = pi; }
-                                else if (less_d2_idx(d2, oi, bd2[t], bi[t])) { bd2[t] = d2; bi[t] = oi; }
-                            }
-                        } else {
-                            int t = k - 1;
-                            while (t > 0 && less_d2_idx(d2, oi, bd2[t - 1], bi[t - 1])) { bd2[t] = bd2[t - 1]; bi[t] = bi[t - 1]; --t; }
-                            bd2[t] = d2; bi[t] = oi;
-                        }
+                    for (int t = KM - 1; t >= 0; --t) {
+                        float pd = (t > 0) ? bd2[t > 0 ? t - 1 : 0] : -CUDART_INF_F;
+                        uint32_t pi = (t > 0) ? bi[t > 0 ? t - 1 : 0] : 0u;
+                        if (less_d2_idx(d2, oi, pd, pi)) { bd2[t] = pd; bi[t] = pi; }
+                        else if (less_d2_idx(d2, oi, bd2[t], bi[t])) { bd2[t] = d2; bi[t] = oi; }
                     }
+                } else {
+                    int t = k - 1;
+                    while (t > 0 && less_d2_idx(d2, oi, bd2[t - 1], bi[t - 1])) { bd2[t] = bd2[t - 1]; bi[t] = bi[t - 1]; --t; }
+                    bd2[t] = d2; bi[t] = oi;
                 }
             }
-        bool all = (z0 == 0 && y0 == 0 && x0 == 0 && z1 == g.dim[2] - 1 && y1 == g.dim[1] - 1 && x1 == g.dim[0] - 1);
+        }
+    };
+
+    // ---- ring 1 with per-cell culling ------------------------------------------------------------
+    // lo[a] / hi[a]: squared lower bounds on the distance to the neighbouring cell on the low / high side
+    // of axis a, shrunk by 1e-5 so that rounding in the cell assignment or in d2 can never hide a candidate.
+    float lo2[3], hi2[3];
+    {
+        const float v[3] = {p.x, p.y, p.z};
+        const int cc[3] = {cx, cy, cz};
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const double q = __ddiv_rn(__dsub_rn((double)v[a], g.org[a]), g.cell) - (double)g.off[a] - (double)cc[a];   // in [0, 1)
+            const float dl = fmaxf((float)(q * g.cell) * 0.99999f - 1e-30f, 0.0f);
+            const float dh = fmaxf((float)((1.0 - q) * g.cell) * 0.99999f - 1e-30f, 0.0f);
+            lo2[a] = dl * dl * 0.99999f; hi2[a] = dh * dh * 0.99999f;
+        }
+    }
+    {
+        const int64_t base0 = ((int64_t)cz * g.dim[1] + cy) * g.dim[0];
+        scan(__ldg(cell_start + base0 + cx), __ldg(cell_start + base0 + cx + 1));
+        for (int dz = -1; dz <= 1; ++dz) {
+            const int z = cz + dz;
+            if (z < 0 || z >= g.dim[2]) continue;
+            const float gz2 = dz < 0 ? lo2[2] : (dz > 0 ? hi2[2] : 0.0f);
+            for (int dy = -1; dy <= 1; ++dy) {
+                const int y = cy + dy;
+                if (y < 0 || y >= g.dim[1]) continue;
+                const float gyz2 = gz2 + (dy < 0 ? lo2[1] : (dy > 0 ? hi2[1] : 0.0f));
+                if (!(gyz2 <= bd2[k - 1])) continue;
+                const int l_ok = (cx > 0 && gyz2 + lo2[0] <= bd2[k - 1]) ? 1 : 0;
+                const int r_ok = (cx < g.dim[0] - 1 && gyz2 + hi2[0] <= bd2[k - 1]) ? 1 : 0;
+                const int64_t base = ((int64_t)z * g.dim[1] + y) * g.dim[0];
+                if (dz == 0 && dy == 0) {
+                    if (l_ok) scan(__ldg(cell_start + base + cx - 1), __ldg(cell_start + base + cx));
+                    if (r_ok) scan(__ldg(cell_start + base + cx + 1), __ldg(cell_start + base + cx + 2));
+                } else {
+                    scan(__ldg(cell_start + base + cx - l_ok), __ldg(cell_start + base + cx + r_ok + 1));
+                }
+            }
+        }
+    }
+    // ---- exactness guard; growing rings (rescan from scratch) when the block was not enough ---------
+    const int maxdim = max(g.dim[0], max(g.dim[1], g.dim[2]));
+    for (int R = 1; R <= maxdim; ++R) {
+        const int z0 = max(cz - R, 0), z1 = min(cz + R, g.dim[2] - 1);
+        const int y0 = max(cy - R, 0), y1 = min(cy + R, g.dim[1] - 1);
+        const int x0 = max(cx - R, 0), x1 = min(cx + R, g.dim[0] - 1);
+        if (R > 1) {
+#pragma unroll
+            for (int t = 0; t < KM; ++t) { bd2[t] = CUDART_INF_F; bi[t] = 0xFFFFFFFFu; }
+            seen = 0;
+            for (int z = z0; z <= z1; ++z)
+                for (int y = y0; y <= y1; ++y) {
+                    const int64_t base = ((int64_t)z * g.dim[1] + y) * g.dim[0];
+                    scan(__ldg(cell_start + base + x0), __ldg(cell_start + base + x1 + 1));
+                }
+        }
+        const bool all = (z0 == 0 && y0 == 0 && x0 == 0 && z1 == g.dim[2] - 1 && y1 == g.dim[1] - 1 && x1 == g.dim[0] - 1);
         if (all) break;
-        if (seen >= k) {
+        if (bd2[k - 1] < CUDART_INF_F) {       // k candidates found (culling never skips a cell while fewer than k are known)
             double guard = (double)R * g.cell;
             guard = guard * guard * (1.0 - 1e-6);
             if ((double)bd2[k - 1] < guard) break;
         }
     }
-    int cnt = min(seen, k);
+    // fewer than k points in the whole cloud: count the filled slots
+    int cnt = 0;
+#pragma unroll
+    for (int t = 0; t < KM; ++t) cnt += (t < k && bi[t] != 0xFFFFFFFFu) ? 1 : 0;
+    (void)seen;
     float accu[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int t = 0; t < KM; ++t) {

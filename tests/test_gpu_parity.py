@@ -231,6 +231,12 @@ def test_forest_against_opencv(kpl, views, oracle):
     d = make_detector(kpl)
     d.setInputCloud(xyz); d.setNormals(nrm)
     d.compute()
+    sc_fused = d.getResponse().copy()
+    with pytest.raises(kpl.KplError):                 # rows are not materialised by the fused default path
+        d.fetch("features", len(xyz), 50)
+    d.keepIntermediates(True)
+    d.compute()
+    assert np.array_equal(sc_fused.view(np.uint32), d.getResponse().view(np.uint32))
     feat = d.fetch("features", len(xyz), 50)
     _, res = rt.predict(feat, flags=cv2.ml.DTREES_PREDICT_SUM)
     ntrees = d.forestInfo()["ntrees"]
@@ -321,6 +327,7 @@ def test_duplicate_points(kpl, oracle, main_forest):
     base = np.load(os.path.join(os.path.dirname(__file__), "golden", "views", "cheff002.npz"))["xyz"][:8000]
     xyz = np.ascontiguousarray(np.concatenate([base, base[100:200], base[100:150]]))
     d = make_detector(kpl)
+    d.keepIntermediates(True)
     d.setInputCloud(xyz)
     _, idx = d.compute()
     nrm = oracle.normals_knn(xyz, 10)
@@ -340,6 +347,7 @@ def test_synthetic_view_properties(kpl, oracle, main_forest):
     from keypoint_learning_b200 import synth
     xyz, vp = synth.view_25d(300, 200, seed=9)
     d = make_detector(kpl)
+    d.keepIntermediates(True)
     d.setNormalsMode(1, k=10, viewpoint=vp)
     d.setInputCloud(xyz)
     _, idx = d.compute()
@@ -388,6 +396,7 @@ def test_query_without_finite_normal_is_unscored(kpl, views, oracle, main_forest
     bad = np.arange(3, len(xyz), 17)
     nrm[bad, 1] = np.nan
     d = make_detector(kpl)
+    d.keepIntermediates(True)
     d.setInputCloud(xyz); d.setNormals(nrm)
     _, idx = d.compute()
     sc_gpu = d.getResponse()
