@@ -21,19 +21,24 @@
 // variant replaces the IEEE square root and the divisions by the two run constants (annulus and
 // bin width) with short FMA-corrected sequences; they are used only after selftest_kernel has
 // proved them bit-identical to __fsqrt_rn / __fdiv_rn for every input mantissa on this device.
+#include <algorithm>
 #include <cstdlib>
+#include <cstring>
 #include "kpl_internal.h"
 #include "kpl_math.cuh"
 #include "forest.cuh"
 
 namespace kpl {
 
-static constexpr int FEAT_WARPS = 4;
+static constexpr int FEAT_WARPS = 4;       // upper bound; the launch uses FEAT_WARPS_DEFAULT warps per block
+static constexpr int FEAT_WARPS_DEFAULT = 1;   // one warp per block: its shared memory is released the moment it finishes (gpurun_out/sweep2.log)
 
 struct FeatParams {
     int n, A, B, F, reach, span;
     float r2, support, adim, ahalf, ainv, bdim, bhalf, binv, cellf, rcull2;
     uint64_t one2;   // (1.0f, 1.0f), opaque to the compiler: see dist2_x2
+    // packed (v, v) copies of the run constants for the two-votes-per-iteration loop; n* = negated
+    uint64_t adim2, nadim2, ainv2, ahalf2, bdim2, nbdim2, binv2, bhalf2;
 };
 
 // Forest evaluation fused into the tail of the feature kernel (nodes == nullptr: not fused): the
@@ -128,6 +133,57 @@ __device__ __forceinline__ uint64_t dist2_x2(uint64_t qx, uint64_t qy, uint64_t 
     return fma2(mz, one, fma2(my, one, mx));     // RN(RN(mx + my) + mz); addition commutes bit-exactly
 }
 
+// src/KeypointLearning.cpp:41-65 / :68-92 with float abs; dim = bin width, half = dim/2, inv = fl(1/dim).
+// v >= 0 and RN(v/dim) <= n on this path, so `if (i == n) i--` is min(i, n-1) and the two pair clamps
+// (`-1 -> 0`, `n -> i`) are a clamp of i +- 1 to [0, n-1].
+template <bool FAST>
+__device__ __forceinline__ void soft_bin_k(float v, float dim, float half, float inv, int nm1, int& idx, int& pair, float& w)
+{
+    const int i = min(__float2int_rd(kdiv<FAST>(v, dim, inv)), nm1);   // static_cast<int>(floor(v/dim)); if (i == n) i--
+    const float center = __fadd_rn(__fmul_rn((float)i, dim), half);
+    const float ww = kdiv<FAST>(__fsub_rn(v, center), dim, inv);
+    const int p = min(max(i + ((ww > 0.0f) ? 1 : -1), 0), nm1);
+    idx = i; pair = p; w = fabsf(ww);
+}
+
+// -a as RN(0 - a): one FADD2 instead of two sign flips (a == 0 never reaches the consumer: d2 == 0 takes the IEEE path)
+__device__ __forceinline__ uint64_t neg2(uint64_t a) { return sub2(0ull, a); }
+__device__ __forceinline__ uint64_t abs2(uint64_t a) { return a & 0x7FFFFFFF7FFFFFFFull; }
+// fast_div_core for two values: q = x*cinv; r = x - q*c; q + r*cinv  (nc = (-c, -c))
+__device__ __forceinline__ uint64_t fast_div_x2(uint64_t x, uint64_t nc, uint64_t cinv)
+{
+    const uint64_t q = mul2(x, cinv);
+    const uint64_t r = fma2(q, nc, x);
+    return fma2(r, cinv, q);
+}
+// fast_sqrt_core for two values (y = rsqrt.approx of each half)
+__device__ __forceinline__ uint64_t fast_sqrt_x2(uint64_t x, float x0, float x1)
+{
+    float y0, y1;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y0) : "f"(x0));
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y1) : "f"(x1));
+    const uint64_t y = pack2(y0, y1);
+    const uint64_t s = mul2(x, y), h = mul2(y, 0x3F0000003F000000ull);
+    const uint64_t e = fma2(neg2(s), s, x);
+    return fma2(e, h, s);
+}
+// soft_bin_k for two values at once (FAST arithmetic only): same expressions, packed where they are FP32
+__device__ __forceinline__ void soft_bin_x2(uint64_t v, uint64_t dim2, uint64_t ndim2, uint64_t inv2, uint64_t half2, uint64_t one2,
+                                            int nm1, int& i0, int& i1, int& p0, int& p1, uint64_t& w, uint64_t& u)
+{
+    float q0, q1, w0, w1;
+    unpack2(fast_div_x2(v, ndim2, inv2), q0, q1);
+    i0 = min(__float2int_rd(q0), nm1);
+    i1 = min(__float2int_rd(q1), nm1);
+    const uint64_t center = fma2(mul2(pack2((float)i0, (float)i1), dim2), one2, half2);   // RN(RN(i*dim) + half)
+    const uint64_t ww = fast_div_x2(sub2(v, center), ndim2, inv2);
+    unpack2(ww, w0, w1);
+    p0 = min(max(i0 + ((w0 > 0.0f) ? 1 : -1), 0), nm1);
+    p1 = min(max(i1 + ((w1 > 0.0f) ? 1 : -1), 0), nm1);
+    w = abs2(ww);
+    u = sub2(0x3F8000003F800000ull, w);
+}
+
 // One thread per (binade, mantissa): result[0] counts sqrt mismatches over [2^-40, 2^40), result[1]
 // / result[2] division mismatches for the annulus / bin width over every mantissa of [1, 2) and [-2,-1)
 // (exact power-of-two scaling extends the proof to every binade without under/overflow), result[3]
@@ -160,6 +216,24 @@ __global__ void __launch_bounds__(256) selftest_kernel(float adim, float ainv, f
         unpack2(d, d0, d1);
         bad_p += (__float_as_uint(d0) != __float_as_uint(dist2(v[0], v[1], v[2], v[3], v[4], v[5])));
         bad_p += (__float_as_uint(d1) != __float_as_uint(dist2(v[0], v[1], v[2], v[6], v[7], v[8])));
+        // the packed sqrt / division / soft-binning of the two-vote loop against their scalar forms
+        const float xa = fabsf(v[3]), xb = x1;
+        float r0, r1;
+        unpack2(fast_sqrt_x2(pack2(xa, xb), xa, xb), r0, r1);
+        bad_p += (__float_as_uint(r0) != __float_as_uint(fast_sqrt_core(xa))) + (__float_as_uint(r1) != __float_as_uint(fast_sqrt_core(xb)));
+        unpack2(fast_div_x2(pack2(v[4], x1), pack2(-adim, -adim), pack2(ainv, ainv)), r0, r1);
+        bad_p += (__float_as_uint(r0) != __float_as_uint(fast_div_core(v[4], adim, ainv))) + (__float_as_uint(r1) != __float_as_uint(fast_div_core(x1, adim, ainv)));
+        {
+            const float c0 = fminf(fabsf(v[5]), 2.0f), c1 = __fsub_rn(x1, 1.0f) * 2.0f;    // cosines in [0, 2]
+            int i0, i1, p0, p1, si, sp; uint64_t w, u; float sw, w0, w1, u0, u1;
+            soft_bin_x2(pack2(c0, c1), pack2(bdim, bdim), pack2(-bdim, -bdim), pack2(binv, binv), pack2(bdim / 2.0f, bdim / 2.0f), one2,
+                        (int)(2.0f / bdim + 0.5f) - 1, i0, i1, p0, p1, w, u);
+            unpack2(w, w0, w1); unpack2(u, u0, u1);
+            soft_bin_k<true>(c0, bdim, bdim / 2.0f, binv, (int)(2.0f / bdim + 0.5f) - 1, si, sp, sw);
+            bad_p += (si != i0) + (sw != 0.0f && sp != p0) + (__float_as_uint(sw) != __float_as_uint(w0)) + (__float_as_uint(__fsub_rn(1.0f, sw)) != __float_as_uint(u0));
+            soft_bin_k<true>(c1, bdim, bdim / 2.0f, binv, (int)(2.0f / bdim + 0.5f) - 1, si, sp, sw);
+            bad_p += (si != i1) + (sw != 0.0f && sp != p1) + (__float_as_uint(sw) != __float_as_uint(w1)) + (__float_as_uint(__fsub_rn(1.0f, sw)) != __float_as_uint(u1));
+        }
     }
     bad_s = __reduce_add_sync(0xFFFFFFFFu, bad_s);
     bad_a = __reduce_add_sync(0xFFFFFFFFu, bad_a);
@@ -173,19 +247,6 @@ __global__ void __launch_bounds__(256) selftest_kernel(float adim, float ainv, f
     }
 }
 
-// src/KeypointLearning.cpp:41-65 / :68-92 with float abs; dim = bin width, half = dim/2, inv = fl(1/dim).
-// v >= 0 and RN(v/dim) <= n on this path, so `if (i == n) i--` is min(i, n-1) and the two pair clamps
-// (`-1 -> 0`, `n -> i`) are a clamp of i +- 1 to [0, n-1].
-template <bool FAST>
-__device__ __forceinline__ void soft_bin_k(float v, float dim, float half, float inv, int nm1, int& idx, int& pair, float& w)
-{
-    const int i = min(__float2int_rd(kdiv<FAST>(v, dim, inv)), nm1);   // static_cast<int>(floor(v/dim)); if (i == n) i--
-    const float center = __fadd_rn(__fmul_rn((float)i, dim), half);
-    const float ww = kdiv<FAST>(__fsub_rn(v, center), dim, inv);
-    const int p = min(max(i + ((ww > 0.0f) ? 1 : -1), 0), nm1);
-    idx = i; pair = p; w = fabsf(ww);
-}
-
 // shared-memory accesses of the vote loop by 32-bit shared address (keeps the address arithmetic to one
 // add per cell and the four read-modify-writes in source order)
 __device__ __forceinline__ float lds_f32(unsigned a)
@@ -197,6 +258,28 @@ __device__ __forceinline__ float lds_f32(unsigned a)
 __device__ __forceinline__ void sts_f32(unsigned a, float v)
 {
     asm volatile("st.shared.f32 [%0], %1;" :: "r"(a), "f"(v));
+}
+
+// index of the most significant set bit (FLO); mask != 0
+__device__ __forceinline__ int msb_index(uint32_t mask)
+{
+    int r;
+    asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(mask));
+    return r;
+}
+
+// The four `+=` of hpp:350-355 for one neighbour, in source order (cells may coincide when a pair index
+// was clamped onto the primary one, so the read-modify-writes must stay sequential).  Loading the four
+// cells together and forwarding coinciding values was measured slower (more issue slots than it saves
+// in shared-memory latency at 28 resident warps: 211 ms vs 204 ms on the 10 M-point scene).
+__device__ __forceinline__ void vote4(unsigned hb, unsigned row_bytes, int a, int ap, int b, int bp, float v00, float v01, float v10, float v11)
+{
+    const unsigned ra = hb + (unsigned)a * row_bytes, rp = hb + (unsigned)ap * row_bytes;
+    const unsigned ob = (unsigned)b << 7, op = (unsigned)bp << 7;
+    sts_f32(ra + ob, __fadd_rn(lds_f32(ra + ob), v00));
+    sts_f32(ra + op, __fadd_rn(lds_f32(ra + op), v01));
+    sts_f32(rp + ob, __fadd_rn(lds_f32(rp + ob), v10));
+    sts_f32(rp + op, __fadd_rn(lds_f32(rp + op), v11));
 }
 
 template <bool FAST>
@@ -213,7 +296,7 @@ feature_kernel(const float4* __restrict__ s_pos, const float4* __restrict__ s_nr
     float* sx = hist + P.F * 32;                                  // SoA candidate tile: x, y, z, nx, ny, nz
     float* sy = sx + 32; float* sz = sy + 32; float* snx = sz + 32; float* sny = snx + 32; float* snz = sny + 32;
 
-    const int q0 = (blockIdx.x * FEAT_WARPS + warp) * 32;
+    const int q0 = (blockIdx.x * (blockDim.x >> 5) + warp) * 32;
     if (q0 >= P.n) return;
     const int q = q0 + lane;
     bool active = q < P.n;
@@ -243,7 +326,9 @@ feature_kernel(const float4* __restrict__ s_pos, const float4* __restrict__ s_nr
     const unsigned hb = (unsigned)__cvta_generic_to_shared(hist) + (unsigned)lane * 4u;   // this lane's histogram column
     const unsigned row_bytes = (unsigned)P.B * 128u;
     const int Am1 = P.A - 1, Bm1 = P.B - 1;
+    const float* sx31 = sx + 31;
     const uint64_t QY = pack2(qp.y, qp.y), QZ = pack2(qp.z, qp.z);
+    const uint64_t QNX = pack2(qn.x, qn.x), QNY = pack2(qn.y, qn.y), QNZ = pack2(qn.z, qn.z);
 
     // The 32 queries are consecutive in (z, y, x) cell order but may straddle the end of a cell row
     // (or sit in far-apart cells of a sparse row).  They are processed in groups of lanes that share
@@ -343,26 +428,63 @@ feature_kernel(const float4* __restrict__ s_pos, const float4* __restrict__ s_nr
             npairs += __popc(mask);
 
             // phase 2: votes of this lane's neighbours, ascending sorted position
-            while (mask) {
-                const int msb = 31 - __clz(mask);              // candidate k sits at bit 31-k: highest bit = smallest k
-                mask &= ~(1u << msb);
-                const float* t = sx + 31 - msb;
-                const float d2 = dist2(qp.x, qp.y, qp.z, t[0], t[32], t[64]);
-                float cosine = __fsub_rn(1.0f, dot3_eigen(qn.x, qn.y, qn.z, t[96], t[128], t[160]));   // hpp:341-342
-                const float dist = ksqrt<FAST>(d2);                                                    // hpp:345 sqrt(distances[..])
-                int a, ap, b, bp;
-                float wa, wb;
-                soft_bin_k<FAST>(dist, P.adim, P.ahalf, P.ainv, Am1, a, ap, wa);
-                cosine = fminf(fmaxf(cosine, 0.0f), 2.0f);          // src/KeypointLearning.cpp:70-73 (cosine is finite here)
-                soft_bin_k<FAST>(cosine, P.bdim, P.bhalf, P.binv, Bm1, b, bp, wb);
-                const float ua = __fsub_rn(1.0f, wa), ub = __fsub_rn(1.0f, wb);
-                const unsigned ra = hb + (unsigned)a * row_bytes, rp = hb + (unsigned)ap * row_bytes;
-                const unsigned ob = (unsigned)b << 7, op = (unsigned)bp << 7;
-                // the four `+=` of hpp:350-355, in source order (cells may coincide)
-                sts_f32(ra + ob, __fadd_rn(lds_f32(ra + ob), __fmul_rn(ub, ua)));
-                sts_f32(ra + op, __fadd_rn(lds_f32(ra + op), __fmul_rn(wb, ua)));
-                sts_f32(rp + ob, __fadd_rn(lds_f32(rp + ob), __fmul_rn(ub, wa)));
-                sts_f32(rp + op, __fadd_rn(lds_f32(rp + op), __fmul_rn(wb, wa)));
+            if constexpr (FAST) {
+                // two neighbours per iteration: every FP32 expression of the two votes is evaluated with one
+                // packed instruction (same IEEE RN operations, half the issue slots); the eight histogram
+                // read-modify-writes stay scalar and in order.  An odd last vote is paired with itself and
+                // its second set of updates is skipped.
+                while (mask) {
+                    const int m0 = msb_index(mask);                // candidate k sits at bit 31-k: highest bit = smallest k
+                    mask ^= 1u << m0;
+                    const bool two = mask != 0;
+                    const int m1 = two ? msb_index(mask) : m0;
+                    mask &= ~(1u << m1);
+                    const float* t0 = sx31 - m0;
+                    const float* t1 = sx31 - m1;
+                    const uint64_t D = dist2_x2(QX, QY, QZ, pack2(t0[0], t1[0]), pack2(t0[32], t1[32]), pack2(t0[64], t1[64]), P.one2);
+                    // 1 - (n0*m0 + (n1*m1 + n2*m2)), hpp:341-342 with Eigen's reduction order
+                    const uint64_t dot = fma2(mul2(QNX, pack2(t0[96], t1[96])), P.one2,
+                                              fma2(mul2(QNY, pack2(t0[128], t1[128])), P.one2, mul2(QNZ, pack2(t0[160], t1[160]))));
+                    float c0, c1, d0, d1;
+                    unpack2(sub2(0x3F8000003F800000ull, dot), c0, c1);
+                    unpack2(D, d0, d1);
+                    uint64_t DIST = fast_sqrt_x2(D, d0, d1);                                           // hpp:345 sqrt(distances[..])
+                    if (!(fminf(d0, d1) >= FAST_SQRT_LO)) DIST = pack2(__fsqrt_rn(d0), __fsqrt_rn(d1));   // zero / denormal-range d2: rare
+                    const uint64_t COS = pack2(fminf(fmaxf(c0, 0.0f), 2.0f), fminf(fmaxf(c1, 0.0f), 2.0f));   // src/KeypointLearning.cpp:70-73
+                    int a0, a1, ap0, ap1, b0, b1, bp0, bp1;
+                    uint64_t WA, UA, WB, UB;
+                    soft_bin_x2(DIST, P.adim2, P.nadim2, P.ainv2, P.ahalf2, P.one2, Am1, a0, a1, ap0, ap1, WA, UA);
+                    soft_bin_x2(COS, P.bdim2, P.nbdim2, P.binv2, P.bhalf2, P.one2, Bm1, b0, b1, bp0, bp1, WB, UB);
+                    float v00a, v00b, v01a, v01b, v10a, v10b, v11a, v11b;
+                    unpack2(mul2(UB, UA), v00a, v00b);
+                    unpack2(mul2(WB, UA), v01a, v01b);
+                    unpack2(mul2(UB, WA), v10a, v10b);
+                    unpack2(mul2(WB, WA), v11a, v11b);
+                    vote4(hb, row_bytes, a0, ap0, b0, bp0, v00a, v01a, v10a, v11a);
+                    if (two) vote4(hb, row_bytes, a1, ap1, b1, bp1, v00b, v01b, v10b, v11b);
+                }
+            } else {
+                while (mask) {
+                    const int msb = 31 - __clz(mask);              // candidate k sits at bit 31-k: highest bit = smallest k
+                    mask &= ~(1u << msb);
+                    const float* t = sx + 31 - msb;
+                    const float d2 = dist2(qp.x, qp.y, qp.z, t[0], t[32], t[64]);
+                    float cosine = __fsub_rn(1.0f, dot3_eigen(qn.x, qn.y, qn.z, t[96], t[128], t[160]));   // hpp:341-342
+                    const float dist = ksqrt<FAST>(d2);                                                    // hpp:345 sqrt(distances[..])
+                    int a, ap, b, bp;
+                    float wa, wb;
+                    soft_bin_k<FAST>(dist, P.adim, P.ahalf, P.ainv, Am1, a, ap, wa);
+                    cosine = fminf(fmaxf(cosine, 0.0f), 2.0f);          // src/KeypointLearning.cpp:70-73 (cosine is finite here)
+                    soft_bin_k<FAST>(cosine, P.bdim, P.bhalf, P.binv, Bm1, b, bp, wb);
+                    const float ua = __fsub_rn(1.0f, wa), ub = __fsub_rn(1.0f, wb);
+                    const unsigned ra = hb + (unsigned)a * row_bytes, rp = hb + (unsigned)ap * row_bytes;
+                    const unsigned ob = (unsigned)b << 7, op = (unsigned)bp << 7;
+                    // the four `+=` of hpp:350-355, in source order (cells may coincide)
+                    sts_f32(ra + ob, __fadd_rn(lds_f32(ra + ob), __fmul_rn(ub, ua)));
+                    sts_f32(ra + op, __fadd_rn(lds_f32(ra + op), __fmul_rn(wb, ua)));
+                    sts_f32(rp + ob, __fadd_rn(lds_f32(rp + ob), __fmul_rn(ub, wa)));
+                    sts_f32(rp + op, __fadd_rn(lds_f32(rp + op), __fmul_rn(wb, wa)));
+                }
             }
         }
     }
@@ -445,6 +567,9 @@ cudaError_t launch_features(kpl_ctx* c, int64_t n, bool use_role, bool fuse_fore
     P.cellf = (float)c->grid.cell;
     P.rcull2 = (float)(r * r * (1.0 + 1e-5));
     P.one2 = 0x3F8000003F800000ull;
+    auto dup = [](float v) { uint32_t b; memcpy(&b, &v, 4); return ((uint64_t)b << 32) | b; };
+    P.adim2 = dup(P.adim); P.nadim2 = dup(-P.adim); P.ainv2 = dup(P.ainv); P.ahalf2 = dup(P.ahalf);
+    P.bdim2 = dup(P.bdim); P.nbdim2 = dup(-P.bdim); P.binv2 = dup(P.binv); P.bhalf2 = dup(P.bhalf);
     cudaError_t e;
     if (store_rows && (e = ensure(c->feat, (size_t)n * P.F))) return e;
     FusedForest FF = {nullptr, nullptr, 0, nullptr, nullptr};
@@ -455,7 +580,9 @@ cudaError_t launch_features(kpl_ctx* c, int64_t n, bool use_role, bool fuse_fore
     bool fast = false;
     if (!getenv("KPL_NO_FAST_MATH") && (e = fast_math_verdict(c, P, fast))) return e;
     c->fast_math = fast;
-    size_t smem = (size_t)FEAT_WARPS * (P.F * 32 + 192) * sizeof(float);
+    int wpb = FEAT_WARPS_DEFAULT;
+    if (const char* e = getenv("KPL_FEAT_WARPS")) wpb = std::max(1, std::min(FEAT_WARPS, atoi(e)));   // tuning experiments only
+    size_t smem = (size_t)wpb * (P.F * 32 + 192) * sizeof(float);
     if (smem > 227 * 1024) return cudaErrorInvalidValue;
     static size_t configured[2] = {0, 0};
     auto kern = fast ? feature_kernel<true> : feature_kernel<false>;
@@ -464,8 +591,8 @@ cudaError_t launch_features(kpl_ctx* c, int64_t n, bool use_role, bool fuse_fore
         configured[fast] = smem;
     }
     int warps = (int)((n + 31) / 32);
-    int blocks = (warps + FEAT_WARPS - 1) / FEAT_WARPS;
-    kern<<<blocks, FEAT_WARPS * 32, smem, c->stream>>>(c->s_pos.p, c->s_nrm.p, c->key_b.p, c->cell_start.p,
+    int blocks = (warps + wpb - 1) / wpb;
+    kern<<<blocks, wpb * 32, smem, c->stream>>>(c->s_pos.p, c->s_nrm.p, c->key_b.p, c->cell_start.p,
                                                        use_role ? c->s_role.p : nullptr,
                                                        c->grid.dim[0], c->grid.dim[1], c->grid.dim[2], P, FF,
                                                        store_rows ? c->feat.p : nullptr, c->counters.p);

@@ -8,7 +8,10 @@
 
 namespace kpl {
 
-static constexpr int TREES_IN_FLIGHT = 4;
+#ifndef KPL_TREES_IN_FLIGHT
+#define KPL_TREES_IN_FLIGHT 4
+#endif
+static constexpr int TREES_IN_FLIGHT = KPL_TREES_IN_FLIGHT;
 
 // x[var * stride] is feature `var` of this thread's point (a shared-memory column: bank == lane for
 // stride 32 / 128, so the data-dependent var never conflicts).  Four trees are walked concurrently so
