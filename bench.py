@@ -28,6 +28,16 @@ FOREST = os.path.join(ROOT, "tests", "golden", "forests", "synthetic-T100-D15.ya
 R_FEAT, R_NMS, TH, A, B, K_NORMALS = 20.0, 4.0, 0.85, 5, 10, 10
 
 
+def measured_traffic(workload):
+    """DRAM bytes per feature-kernel launch from the committed `ncu --set full` capture of the same workload
+    (profiles/traffic.json, written by hand from profiles/*_ncu.txt); None when no capture exists."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f).get(workload)
+    return None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -256,7 +266,9 @@ def run_b200(args):
     achieved = feat_bytes / feat_s / 1e9
     pipe_bytes = 32.0 * pairs_self + 16.0 * K_NORMALS * st["n_points"] + 200.0 * st["n_points"]  # + 20*K_n*[above th], added below
     roofline = {"bound": "hbm", "kernel": "feature_kernel", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
-                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": feat_bytes,
+                "traffic": (measured_traffic(args.workload) or {}).get("dram_bytes_per_launch") if world == 1 else None,
+                "traffic_source": (measured_traffic(args.workload) or {}).get("source") if world == 1 else None,
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": feat_bytes,
                 "kernel_ms": feat_s * 1e3, "pairs_per_s": st["feature_pairs"] / feat_s,
                 "candidate_tests_per_s": st["candidate_pairs"] / feat_s,
                 "acceptance": st["feature_pairs"] / max(1, st["candidate_pairs"]),
@@ -292,7 +304,7 @@ def main():
     ap.add_argument("--workload", default="scene10m", choices=["scene10m", "view1m"])
     ap.add_argument("--points", type=int, default=10_000_000)
     ap.add_argument("--cpr", type=int, default=4, help="grid cells per radiusFeatures")
-    ap.add_argument("--cpu-sample", type=int, default=200_000)
+    ap.add_argument("--cpu-sample", type=int, default=1_500_000, help="points of the workload crop the CPU legs run on (~10-20 s of host work)")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

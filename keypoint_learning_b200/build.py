@@ -53,10 +53,11 @@ def build_lib(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(objdir, exist_ok=True)
     objs = []
     procs = []
+    extra = os.environ.get("KPL_NVCC_EXTRA", "").split()      # tuning experiments only, e.g. -DKPL_TREES_IN_FLIGHT=8
     for s in srcs:
         o = os.path.join(objdir, os.path.basename(s) + ".o")
         objs.append(o)
-        cmd = [_nvcc(), *NVCC_FLAGS, "-ccbin", _host_cxx(), "-x", "cu", "-c", s, "-o", o]
+        cmd = [_nvcc(), *NVCC_FLAGS, *extra, "-ccbin", _host_cxx(), "-x", "cu", "-c", s, "-o", o]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

@@ -93,46 +93,6 @@ __device__ __forceinline__ float kdiv(float x, float c, float cinv)
     return FAST ? fast_div_core(x, c, cinv) : __fdiv_rn(x, c);
 }
 
-// ---- packed FP32 (sm_100 FADD2 / FMUL2 / FFMA2): two IEEE RN operations per issued instruction ---
-__device__ __forceinline__ uint64_t pack2(float lo, float hi)
-{
-    uint64_t r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-    return r;
-}
-__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi)
-{
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
-__device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b)
-{
-    uint64_t r;
-    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-    return r;
-}
-__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b)
-{
-    uint64_t r;
-    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-    return r;
-}
-__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c)
-{
-    uint64_t r;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
-    return r;
-}
-// FLANN L2_Simple for two candidates at once: ((dx*dx) + dy*dy) + dz*dz, every product and sum rounded.
-// The sums are written RN(m*1 + acc) with `one` = (1.0f, 1.0f) passed at RUN time: ptxas 12.9 contracts a
-// packed mul feeding a packed add into FFMA2 even for .rn operands, which would change d2 and with it
-// the neighbour sets; a product by an opaque 1.0 is exact, rounds once and cannot be folded.
-__device__ __forceinline__ uint64_t dist2_x2(uint64_t qx, uint64_t qy, uint64_t qz, uint64_t cx, uint64_t cy, uint64_t cz, uint64_t one)
-{
-    const uint64_t dx = sub2(qx, cx), dy = sub2(qy, cy), dz = sub2(qz, cz);
-    const uint64_t mx = mul2(dx, dx), my = mul2(dy, dy), mz = mul2(dz, dz);
-    return fma2(mz, one, fma2(my, one, mx));     // RN(RN(mx + my) + mz); addition commutes bit-exactly
-}
-
 // src/KeypointLearning.cpp:41-65 / :68-92 with float abs; dim = bin width, half = dim/2, inv = fl(1/dim).
 // v >= 0 and RN(v/dim) <= n on this path, so `if (i == n) i--` is min(i, n-1) and the two pair clamps
 // (`-1 -> 0`, `n -> i`) are a clamp of i +- 1 to [0, n-1].

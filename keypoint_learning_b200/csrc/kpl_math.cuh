@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>
 #include <math_constants.h>
 #include <float.h>
+#include <stdint.h>
 
 namespace kpl {
 
@@ -24,6 +25,46 @@ __device__ __forceinline__ float dist2(float ax, float ay, float az, float bx, f
 __device__ __forceinline__ float dot3_eigen(float ax, float ay, float az, float bx, float by, float bz)
 {
     return __fadd_rn(__fmul_rn(ax, bx), __fadd_rn(__fmul_rn(ay, by), __fmul_rn(az, bz)));
+}
+
+// ---- packed FP32 (sm_100 FADD2 / FMUL2 / FFMA2): two IEEE RN operations per issued instruction ---
+__device__ __forceinline__ uint64_t pack2(float lo, float hi)
+{
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b)
+{
+    uint64_t r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b)
+{
+    uint64_t r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c)
+{
+    uint64_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+// FLANN L2_Simple for two candidates at once: ((dx*dx) + dy*dy) + dz*dz, every product and sum rounded.
+// The sums are written RN(m*1 + acc) with `one` = (1.0f, 1.0f) passed at RUN time: ptxas 12.9 contracts a
+// packed mul feeding a packed add into FFMA2 even for .rn operands, which would change d2 and with it
+// the neighbour sets; a product by an opaque 1.0 is exact, rounds once and cannot be folded.
+__device__ __forceinline__ uint64_t dist2_x2(uint64_t qx, uint64_t qy, uint64_t qz, uint64_t cx, uint64_t cy, uint64_t cz, uint64_t one)
+{
+    const uint64_t dx = sub2(qx, cx), dy = sub2(qy, cy), dz = sub2(qz, cz);
+    const uint64_t mx = mul2(dx, dx), my = mul2(dy, dy), mz = mul2(dz, dz);
+    return fma2(mz, one, fma2(my, one, mx));     // RN(RN(mx + my) + mz); addition commutes bit-exactly
 }
 
 // ---- libm-independent trig: double-precision series, rounded to float once -----------------

@@ -214,6 +214,161 @@ cudaError_t launch_check_normals(kpl_ctx* c, int64_t n)
     return cudaGetLastError();
 }
 
-cudaError_t launch_normals_radius(kpl_ctx*, int64_t) { return cudaErrorNotSupported; }
+// Radius mode replaces the fallback of KeypointLearningDetector::initCompute (impl/KeypointLearning.hpp:130-137):
+// pcl::NormalEstimation with setRadiusSearch(search_radius_), i.e. PCA over the whole r_feat ball, query
+// included.  Same traversal as the feature kernel (features.cu): a warp owns 32 consecutive sorted
+// points, candidate rows are staged 32 at a time in shared memory, a packed-FP32 pass builds the exact
+// membership mask and each lane then adds its neighbours' un-centred FP32 moments
+// (computeMeanAndCovarianceMatrix, PCL 1.8.0) one by one in ascending sorted position.  PCL adds them in
+// its sorted-search order (d2, index); reproducing that would mean sorting ~2500 neighbours per point, so
+// the order here is the canonical (cell key, index) one -- the oracle's `order 1` -- and differs from
+// PCL's by FP32 re-association only.
+struct NormRadParams {
+    int n, reach, span;
+    float r2, cellf, rcull2, vpx, vpy, vpz;
+    uint64_t one2;
+};
+
+__global__ void __launch_bounds__(32)
+normals_radius_kernel(const float4* __restrict__ s_pos, const uint32_t* __restrict__ skey, const int32_t* __restrict__ cell_start,
+                      int dimx, int dimy, int dimz, NormRadParams P, float4* __restrict__ s_nrm)
+{
+    __shared__ __align__(16) float tile[96];
+    float* sx = tile; float* sy = tile + 32; float* sz = tile + 64;
+    const int lane = threadIdx.x;
+    const int q0 = blockIdx.x * 32;
+    if (q0 >= P.n) return;
+    const int q = q0 + lane;
+    const bool active = q < P.n;
+    float4 qp = make_float4(CUDART_NAN_F, 0.f, 0.f, 0.f);
+    int cx = 0, cy = 0, cz = 0;
+    if (active) {
+        qp = __ldg(s_pos + q);
+        const uint32_t key = __ldg(skey + q);
+        const uint32_t t = key / (uint32_t)dimx;
+        cx = (int)(key - t * (uint32_t)dimx);
+        cz = (int)(t / (uint32_t)dimy);
+        cy = (int)(t - (uint32_t)cz * (uint32_t)dimy);
+    }
+    const uint64_t QY = pack2(qp.y, qp.y), QZ = pack2(qp.z, qp.z);
+    float accu[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    int cnt_nb = 0;
+    const float* sx31 = sx + 31;
+
+    unsigned remaining = __ballot_sync(0xFFFFFFFFu, active);
+    while (remaining) {
+        const int leader = __ffs(remaining) - 1;
+        const int minx = __shfl_sync(0xFFFFFFFFu, cx, leader);
+        const int gy0 = __shfl_sync(0xFFFFFFFFu, cy, leader), gz0 = __shfl_sync(0xFFFFFFFFu, cz, leader);
+        const bool member = active && ((remaining >> lane) & 1u) && cy == gy0 && cz == gz0 && (unsigned)(cx - minx) <= (unsigned)P.span;
+        remaining &= ~__ballot_sync(0xFFFFFFFFu, member);
+        const int maxx = __reduce_max_sync(0xFFFFFFFFu, member ? cx : minx);
+        const float px = member ? qp.x : CUDART_NAN_F;
+        const uint64_t QX = pack2(px, px);
+        const int y0 = max(gy0 - P.reach, 0), y1 = min(gy0 + P.reach, dimy - 1);
+        const int z0 = max(gz0 - P.reach, 0), z1 = min(gz0 + P.reach, dimz - 1);
+        const int ny = y1 - y0 + 1, nrows = ny * (z1 - z0 + 1);
+
+        int rb = 0, nr = 0, l = 0, row_s = 0, row_e = 0, cur = 0, end = 0;
+        auto next_tile = [&](int& tb, int& te) -> bool {
+            while (cur >= end) {
+                if (l >= nr) {
+                    if (rb >= nrows) return false;
+                    row_s = 0; row_e = 0;
+                    const int r = rb + lane;
+                    if (r < nrows) {
+                        const int zz = z0 + r / ny, yy = y0 + r % ny;
+                        const int gy = max(abs(yy - gy0) - 1, 0), gz = max(abs(zz - gz0) - 1, 0);
+                        const float gap2 = (float)(gy * gy + gz * gz) * P.cellf * P.cellf;
+                        if (gap2 < P.rcull2) {
+                            int rx = (int)(sqrtf(P.rcull2 - gap2) / P.cellf) + 1;
+                            rx = min(rx, P.reach);
+                            const int xa = max(minx - rx, 0), xb = min(maxx + rx, dimx - 1);
+                            const int64_t base = ((int64_t)zz * dimy + yy) * dimx;
+                            row_s = __ldg(cell_start + base + xa);
+                            row_e = __ldg(cell_start + base + xb + 1);
+                        }
+                    }
+                    nr = min(32, nrows - rb);
+                    rb += 32;
+                    l = 0;
+                }
+                cur = __shfl_sync(0xFFFFFFFFu, row_s, l);
+                end = __shfl_sync(0xFFFFFFFFu, row_e, l);
+                ++l;
+            }
+            tb = cur; te = end;
+            cur += 32;
+            return true;
+        };
+
+        int tb = 0, te = 0;
+        bool have = next_tile(tb, te);
+        float4 cp = make_float4(CUDART_NAN_F, 0.f, 0.f, 0.f);
+        if (have && tb + lane < te) cp = __ldg(s_pos + tb + lane);
+        while (have) {
+            __syncwarp();
+            sx[lane] = cp.x; sy[lane] = cp.y; sz[lane] = cp.z;
+            const int cnt = min(32, te - tb);
+            have = next_tile(tb, te);
+            cp = make_float4(CUDART_NAN_F, 0.f, 0.f, 0.f);
+            if (have && tb + lane < te) cp = __ldg(s_pos + tb + lane);
+            __syncwarp();
+            uint32_t mask = 0;
+#pragma unroll
+            for (int k0 = 0; k0 < 32; k0 += 8) {
+                if (k0 < cnt) {
+#pragma unroll
+                    for (int u = 0; u < 8; u += 4) {
+                        const ulonglong2 X = *reinterpret_cast<const ulonglong2*>(sx + k0 + u);
+                        const ulonglong2 Y = *reinterpret_cast<const ulonglong2*>(sy + k0 + u);
+                        const ulonglong2 Z = *reinterpret_cast<const ulonglong2*>(sz + k0 + u);
+                        float d0, d1, d2, d3;
+                        unpack2(dist2_x2(QX, QY, QZ, X.x, Y.x, Z.x, P.one2), d0, d1);
+                        unpack2(dist2_x2(QX, QY, QZ, X.y, Y.y, Z.y, P.one2), d2, d3);
+                        if (d0 < P.r2) mask |= 0x80000000u >> (k0 + u);
+                        if (d1 < P.r2) mask |= 0x80000000u >> (k0 + u + 1);
+                        if (d2 < P.r2) mask |= 0x80000000u >> (k0 + u + 2);
+                        if (d3 < P.r2) mask |= 0x80000000u >> (k0 + u + 3);
+                    }
+                }
+            }
+            cnt_nb += __popc(mask);
+            while (mask) {
+                const int m = 31 - __clz(mask);
+                mask ^= 1u << m;
+                const float* t = sx31 - m;
+                const float x = t[0], y = t[32], z = t[64];
+                accu[0] = __fadd_rn(accu[0], __fmul_rn(x, x));
+                accu[1] = __fadd_rn(accu[1], __fmul_rn(x, y));
+                accu[2] = __fadd_rn(accu[2], __fmul_rn(x, z));
+                accu[3] = __fadd_rn(accu[3], __fmul_rn(y, y));
+                accu[4] = __fadd_rn(accu[4], __fmul_rn(y, z));
+                accu[5] = __fadd_rn(accu[5], __fmul_rn(z, z));
+                accu[6] = __fadd_rn(accu[6], x);
+                accu[7] = __fadd_rn(accu[7], y);
+                accu[8] = __fadd_rn(accu[8], z);
+            }
+        }
+    }
+    if (active) s_nrm[q] = normal_from_moments(accu, cnt_nb, qp.x, qp.y, qp.z, P.vpx, P.vpy, P.vpz);
+}
+
+cudaError_t launch_normals_radius(kpl_ctx* c, int64_t n)
+{
+    const kpl_params& U = c->params;
+    NormRadParams P;
+    const double r = (double)U.radius_features;
+    P.n = (int)n; P.reach = c->grid.reach_feat; P.span = (U.cells_per_radius + 1) / 2;
+    P.r2 = (float)(r * r);                         // static_cast<float>(radius*radius), KdTreeFLANN::radiusSearch
+    P.cellf = (float)c->grid.cell;
+    P.rcull2 = (float)(r * r * (1.0 + 1e-5));
+    P.vpx = U.viewpoint[0]; P.vpy = U.viewpoint[1]; P.vpz = U.viewpoint[2];
+    P.one2 = 0x3F8000003F800000ull;
+    normals_radius_kernel<<<(unsigned)((n + 31) / 32), 32, 0, c->stream>>>(c->s_pos.p, c->key_b.p, c->cell_start.p,
+                                                                          c->grid.dim[0], c->grid.dim[1], c->grid.dim[2], P, c->s_nrm.p);
+    c->launches++;
+    return cudaGetLastError();
+}
 
 }  // namespace kpl

@@ -502,26 +502,58 @@ KPLO_API int kplo_knn_indices(const float* xyz, int64_t n, int k, double cell, i
 }
 
 /* F2': include/impl/KeypointLearning.hpp:130-137, NormalEstimation.setRadiusSearch(search_radius_):
- * PCA over the whole ball, neighbours in the sorted-search order (d2, index). */
-KPLO_API int kplo_normals_radius(const float* xyz, int64_t n, double radius, const float vp[3], float* normals4)
+ * PCA over the whole ball (query included).  PCL accumulates the un-centred FP32 moments in the order its
+ * sorted search returns, ascending (d2, index): order 0.  Sorting ~2500 neighbours per point is not
+ * something a GPU should do, so the device path accumulates in the canonical (cell key, index) order it
+ * already uses for the histograms: order 1 (cpr = cells per radius of the canonical grid).  The two differ
+ * only by FP32 re-association of the moment sums (tests/test_oracle.py bounds the angle between them). */
+KPLO_API int kplo_canon_grid(const float* xyz, int64_t n, double r_feat, int cpr, double org[3], double* cell, int32_t dims[3]);
+KPLO_API void kplo_canon_keys(const float* xyz, int64_t n, const double org[3], double cell, const int32_t dims[3], int64_t* keys);
+typedef struct { int64_t key; nb_t nb; } knb_t;
+static int cmp_key_idx(const void* a, const void* b)
+{
+    const knb_t *x = (const knb_t*)a, *y = (const knb_t*)b;
+    if (x->key != y->key) return (x->key > y->key) - (x->key < y->key);
+    return (x->nb.idx > y->nb.idx) - (x->nb.idx < y->nb.idx);
+}
+KPLO_API int kplo_normals_radius_ordered(const float* xyz, int64_t n, double radius, const float vp[3], int order, int cpr, float* normals4)
 {
     ogrid g; int rc = ogrid_build(&g, xyz, n, radius / 2.0);
     if (rc) return rc;
+    int64_t* ckey = NULL;
+    if (order == 1) {
+        double org[3], cell; int32_t dims[3];
+        kplo_canon_grid(xyz, n, radius, cpr, org, &cell, dims);
+        ckey = (int64_t*)malloc((size_t)n * sizeof(int64_t));
+        if (!ckey) { ogrid_free(&g); return -3; }
+        kplo_canon_keys(xyz, n, org, cell, dims, ckey);
+    }
     float r2 = (float)(radius * radius);
     int err = 0;
 #pragma omp parallel
     {
         nbvec nb = { 0, 0, 0 };
+        knb_t* kb = NULL; int64_t kcap = 0;
 #pragma omp for schedule(dynamic, 64)
         for (int64_t i = 0; i < n; ++i) {
             if (ogrid_radius(&g, i, radius, r2, &nb)) { err = 1; continue; }
-            qsort(nb.v, (size_t)nb.n, sizeof(nb_t), cmp_d2_idx);
+            if (order == 1) {
+                if (nb.n > kcap) { free(kb); kcap = nb.n * 2; kb = (knb_t*)malloc((size_t)kcap * sizeof(knb_t)); }
+                if (!kb) { err = 1; kcap = 0; continue; }
+                for (int64_t t = 0; t < nb.n; ++t) { kb[t].key = ckey[nb.v[t].idx]; kb[t].nb = nb.v[t]; }
+                qsort(kb, (size_t)nb.n, sizeof(knb_t), cmp_key_idx);
+                for (int64_t t = 0; t < nb.n; ++t) nb.v[t] = kb[t].nb;
+            } else qsort(nb.v, (size_t)nb.n, sizeof(nb_t), cmp_d2_idx);
             point_normal(xyz, nb.v, (int)nb.n, xyz + 3 * i, vp, normals4 + 4 * i);
         }
-        free(nb.v);
+        free(nb.v); free(kb);
     }
-    ogrid_free(&g);
+    free(ckey); ogrid_free(&g);
     return err ? -3 : 0;
+}
+KPLO_API int kplo_normals_radius(const float* xyz, int64_t n, double radius, const float vp[3], float* normals4)
+{
+    return kplo_normals_radius_ordered(xyz, n, radius, vp, 0, 4, normals4);
 }
 
 /* ------------------------------------------------------------------------------------------ */
@@ -554,13 +586,6 @@ KPLO_API void kplo_canon_keys(const float* xyz, int64_t n, const double org[3], 
     }
 }
 
-typedef struct { int64_t key; nb_t nb; } knb_t;
-static int cmp_key_idx(const void* a, const void* b)
-{
-    const knb_t *x = (const knb_t*)a, *y = (const knb_t*)b;
-    if (x->key != y->key) return (x->key > y->key) - (x->key < y->key);
-    return (x->nb.idx > y->nb.idx) - (x->nb.idx < y->nb.idx);
-}
 
 /* ------------------------------------------------------------------------------------------ */
 /* F4: include/impl/KeypointLearning.hpp:321-376.  normals4 = (nx,ny,nz,*).  The query's own     */
@@ -769,7 +794,7 @@ KPLO_API int64_t kplo_detect(const float* xyz, float* normals4, int64_t n, int n
     double t0 = now_ms(), t1;
     int rc = 0;
     if (normals_mode == 1) rc = kplo_normals_knn(xyz, n, k, vp, 0.0, normals4);
-    else if (normals_mode == 2) rc = kplo_normals_radius(xyz, n, r_feat, vp, normals4);
+    else if (normals_mode == 2) rc = kplo_normals_radius_ordered(xyz, n, r_feat, vp, order == 1 ? 1 : 0, cpr, normals4);
     if (rc) return rc;
     if (flip && normals_mode != 0) for (int64_t i = 0; i < n; ++i) { normals4[4 * i] *= -1; normals4[4 * i + 1] *= -1; normals4[4 * i + 2] *= -1; }
     t1 = now_ms(); if (stage_ms) stage_ms[0] = t1 - t0;

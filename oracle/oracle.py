@@ -43,6 +43,7 @@ def lib():
         L.kplo_normals_knn.argtypes = [f32p, C.c_int64, C.c_int, f32p, C.c_double, f32p]
         L.kplo_knn_indices.argtypes = [f32p, C.c_int64, C.c_int, C.c_double, i32p, f32p]
         L.kplo_normals_radius.argtypes = [f32p, C.c_int64, C.c_double, f32p, f32p]
+        L.kplo_normals_radius_ordered.argtypes = [f32p, C.c_int64, C.c_double, f32p, C.c_int, C.c_int, f32p]
         L.kplo_canon_grid.argtypes = [f32p, C.c_int64, C.c_double, C.c_int, f64p, f64p, i32p]
         L.kplo_canon_keys.argtypes = [f32p, C.c_int64, f64p, C.c_double, i32p, i64p]
         L.kplo_features.argtypes = [f32p, f32p, C.c_int64, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int,
@@ -148,11 +149,12 @@ def knn_indices(xyz, k=10, cell=0.0):
     return idx, d2
 
 
-def normals_radius(xyz, radius, viewpoint=(0.0, 0.0, 0.0)):
+def normals_radius(xyz, radius, viewpoint=(0.0, 0.0, 0.0), order=0, cpr=4):
+    """order 0: PCL's sorted-search order (d2, index); order 1: canonical (cell key, index), the device order."""
     xyz = _xyz(xyz)
     vp = np.asarray(viewpoint, np.float32)
     out = np.empty((len(xyz), 4), np.float32)
-    rc = lib().kplo_normals_radius(_p(xyz, C.c_float), len(xyz), float(radius), _p(vp, C.c_float), _p(out, C.c_float))
+    rc = lib().kplo_normals_radius_ordered(_p(xyz, C.c_float), len(xyz), float(radius), _p(vp, C.c_float), int(order), int(cpr), _p(out, C.c_float))
     assert rc == 0, rc
     return out
 

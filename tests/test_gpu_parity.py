@@ -106,6 +106,31 @@ def test_knn_normals_other_k_and_viewpoint(det, views, oracle):
     det.setNormalsMode(1, k=10)
 
 
+def test_radius_normals_bit_exact_and_pipeline(kpl, views, oracle, main_forest):
+    """F2' (hpp:130-137): PCA normals over the r_feat ball when setNormals() was not called.  The device
+    adds the moments in canonical (cell, index) order = oracle order 1; the whole pipeline on top of those
+    normals must then reproduce the oracle's scores and keypoints exactly."""
+    xyz = np.ascontiguousarray(views["cheff001"][:30000])
+    d = make_detector(kpl)
+    for r, vp, flip in ((20.0, (0.0, 0.0, 0.0), False), (7.5, (5.0, -3.0, 400.0), True)):
+        d.setRadiusSearch(r)
+        d.setNormalsMode(2, viewpoint=vp, flip=flip)
+        n_gpu = d.computeNormals(xyz)
+        n_cpu = oracle.normals_radius(xyz, r, vp, order=1)
+        if flip:
+            n_cpu[:, :3] *= -1
+        same = (n_gpu.view(np.uint32) == n_cpu.view(np.uint32)) | (np.isnan(n_gpu) & np.isnan(n_cpu))
+        assert same.all(), np.argwhere(~same)[:5]
+    d.setRadiusSearch(R_FEAT)
+    d.setNormalsMode(2)
+    d.setInputCloud(xyz); d.setNormals(None)
+    _, idx = d.compute()
+    ref = oracle.detect(xyz, main_forest, R_FEAT, R_NMS, TH, 5, 10, normals_mode=2, order=1)
+    assert np.array_equal(d.getResponse().view(np.uint32), ref["scores"].view(np.uint32))
+    assert np.array_equal(idx, ref["keypoints"])
+    d.close()
+
+
 # ---------------------------------------------------------------------------------------------
 # features
 # ---------------------------------------------------------------------------------------------

@@ -175,6 +175,20 @@ def test_normals_radius_mode_runs(oracle, views):
     assert np.allclose(np.linalg.norm(nrm[ok, :3], axis=1), 1.0, atol=1e-5)
 
 
+def test_normals_radius_order_deviation_is_small(oracle, views):
+    """Canonical (cell, index) accumulation order (what the device uses) against PCL's sorted (d2, index)
+    order: the same un-centred FP32 moment sums re-associated.  On the model-centred bundled view the two
+    normals agree to a small fraction of a degree."""
+    xyz = np.ascontiguousarray(views["cheff001"][:6000])
+    a = oracle.normals_radius(xyz, 10.0, order=0)
+    b = oracle.normals_radius(xyz, 10.0, order=1)
+    ok = np.isfinite(a).all(axis=1) & np.isfinite(b).all(axis=1)
+    assert np.array_equal(np.isfinite(a).all(axis=1), np.isfinite(b).all(axis=1))
+    cosang = np.clip(np.abs(np.sum(a[ok, :3] * b[ok, :3], axis=1)), 0.0, 1.0)
+    ang = np.degrees(np.arccos(cosang))
+    assert np.median(ang) < 0.05 and np.quantile(ang, 0.99) < 1.0, (np.median(ang), np.quantile(ang, 0.99))
+
+
 # ---------------------------------------------------------------------------------------------
 # features
 # ---------------------------------------------------------------------------------------------
