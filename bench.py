@@ -215,6 +215,13 @@ def run_b200(args):
     ms_per_step = ms / args.steps
     value = n_total / (ms_per_step * 1e-3)
     st = det.stats()
+    per_rank = None
+    if world > 1:
+        # device time, slab size and pair count of every rank for the last step: shows the load balance
+        mine = torch.tensor([stage["total_ms"], float(job.last_slab_points), float(st["feature_pairs"])], device=dev, dtype=torch.float64)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = [{"device_ms": round(float(t[0]), 3), "slab_points": int(t[1]), "pairs": int(t[2])} for t in allr]
 
     # ---- e2e: host buffers through the public host API (H2D + compute + D2H every step) ----------
     e2e = None
@@ -288,7 +295,7 @@ def run_b200(args):
                            "parallelism": "slab%d+halo" % world if world > 1 else "single",
                            "l2": "inputs and intermediates (%.0f MB) exceed the 126 MB L2; no flush needed" % (n_total * (16 + 16 + 16 + 200 + 16) / 1e6)},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
-                "keypoints": int(nkp), "n_points": n_total, "points_per_rank": n_local}
+                "keypoints": int(nkp), "n_points": n_total, "points_per_rank": n_local, "per_rank": per_rank}
         print(json.dumps(line), flush=True)
     det.close()
     if world > 1:

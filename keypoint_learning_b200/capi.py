@@ -186,7 +186,12 @@ class KeypointLearningDetector:
             self._p.grid_origin[i] = float(origin[i]); self._p.grid_dims[i] = int(dims[i]); self._p.grid_offset[i] = int(offset[i])
 
     def setStream(self, cuda_stream_ptr):
-        self._check(self._L.kpl_set_stream(self._h, C.c_void_p(cuda_stream_ptr or 0)))
+        """Run on a caller-owned cudaStream_t.  0 is the legacy default stream (what torch.cuda.current_stream()
+        reports unless a side stream is active): it is passed as cudaStreamLegacy (1), because a NULL handle
+        means "the context's own non-blocking stream" to kpl_set_stream, which would not be ordered after
+        work the caller enqueued on the default stream.  None resets to the context stream."""
+        ptr = None if cuda_stream_ptr is None else (int(cuda_stream_ptr) or 1)
+        self._check(self._L.kpl_set_stream(self._h, C.c_void_p(ptr)))
 
     def setForestArrays(self, forest):
         f = forest

@@ -57,16 +57,48 @@ def plan_slabs(xyz: np.ndarray, r_feat: float, r_nms: float, cpr: int, world: in
     hi = xyz.max(axis=0).astype(np.float64)
     dims = (np.floor((hi - lo) / cell) + 1).astype(np.int32)
     cx = cell_coords(xyz, lo, cell, 0)
-    hist = np.bincount(cx, minlength=int(dims[0]))
-    cum = np.concatenate([[0], np.cumsum(hist)])
-    cuts = [0]
-    for r in range(1, world):
-        target = len(xyz) * r / world
-        c = int(np.searchsorted(cum, target, side="left"))
-        cuts.append(min(max(c, cuts[-1] + 1), int(dims[0]) - (world - r)))
-    cuts.append(int(dims[0]))
+    hist = np.bincount(cx, minlength=int(dims[0])).astype(np.float64)
     rn, rf = reach(r_nms, cell), reach(r_feat, cell)
-    plan = SlabPlan(lo, cell, dims, np.asarray(cuts, np.int64), rn + rf + normal_support_cells, rn, rf)
+    halo = rn + rf + normal_support_cells
+    nx = int(dims[0])
+    cum = np.concatenate([[0.0], np.cumsum(hist)])
+
+    def pts(a, b):                                   # points in columns [a, b), clipped to the grid
+        return cum[min(max(b, 0), nx)] - cum[min(max(a, 0), nx)]
+
+    def cost(c0, c1):
+        # what a rank owning [c0, c1) computes: features + forest for its columns and the reach_nms margin
+        # (cost ~ 1 per point, the neighbour count is set by the sampling density, not by the slab), normals
+        # and grid for everything including the halo (~7 % of a scored point each)
+        return pts(c0 - rn, c1 + rn) + 0.07 * pts(c0 - halo, c1 + halo)
+
+    def greedy(limit):
+        cuts, c0 = [0], 0
+        while c0 < nx and len(cuts) <= world:
+            c1 = c0 + 1
+            while c1 < nx and cost(c0, c1 + 1) <= limit:
+                c1 += 1
+            cuts.append(c1)
+            c0 = c1
+        return cuts if cuts[-1] == nx and len(cuts) - 1 <= world else None
+
+    lo_t, hi_t = 0.0, cost(0, nx)
+    for _ in range(50):                               # smallest per-rank cost bound that needs <= world slabs
+        mid = 0.5 * (lo_t + hi_t)
+        if greedy(mid) is None:
+            lo_t = mid
+        else:
+            hi_t = mid
+    cuts = greedy(hi_t)
+    while len(cuts) - 1 < world:                      # fewer slabs than ranks: split the widest
+        w = np.diff(cuts)
+        k = int(np.argmax(w))
+        if w[k] < 2:
+            break
+        cuts.insert(k + 1, cuts[k] + int(w[k]) // 2)
+    if len(cuts) - 1 != world:
+        raise ValueError("cannot cut %d cell columns into %d slabs" % (nx, world))
+    plan = SlabPlan(lo, cell, dims, np.asarray(cuts, np.int64), halo, rn, rf)
     widths = np.diff(plan.cuts)
     if world > 1 and widths.min() < plan.halo:
         raise ValueError("slabs (%s cells) are thinner than the halo (%d cells): use fewer ranks" % (widths.tolist(), plan.halo))
@@ -129,8 +161,8 @@ class SlabJob:
 
     # ---- step pieces (kept separate so the CPU tests can put the oracle in the middle) --------------
     def exchange_halo(self):
-        """Neighbour P2P: send my boundary strips, receive theirs.  Returns (left, right) tuples of
-        (xyz4, gidx, cx) or None at the ends."""
+        """Send my boundary strips to the two neighbours, receive theirs (NCCL all_to_all over NVLink; gloo on
+        CPU).  Returns the (left, right) received buffers, None at the ends."""
         p, r, w = self.plan, self.rank, self.world
         left_sel = torch.nonzero(self.cx < self.c0 + p.halo).flatten() if r > 0 else None
         right_sel = torch.nonzero(self.cx >= self.c1 - p.halo).flatten() if r < w - 1 else None
@@ -146,29 +178,26 @@ class SlabJob:
 
         send_l = pack(left_sel) if left_sel is not None else None
         send_r = pack(right_sel) if right_sel is not None else None
-        # sizes first (tiny), then payloads
-        n_from_l = torch.zeros(1, dtype=torch.int64, device=self.device)
-        n_from_r = torch.zeros(1, dtype=torch.int64, device=self.device)
-        ops = []
+        # strip sizes of every rank (one tiny all_gather), then ONE all_to_all whose only non-empty
+        # splits are the two neighbours: the same collective sequence on every rank, whatever its position.
+        mine = torch.tensor([len(send_l) if send_l is not None else 0, len(send_r) if send_r is not None else 0],
+                            dtype=torch.int64, device=self.device)
+        sizes = [torch.zeros(2, dtype=torch.int64, device=self.device) for _ in range(w)]
+        dist.all_gather(sizes, mine)
+        sizes = torch.stack(sizes).cpu()
+        in_split = [0] * w
+        out_split = [0] * w
         if r > 0:
-            ops += [dist.P2POp(dist.isend, torch.tensor([len(send_l)], dtype=torch.int64, device=self.device), r - 1),
-                    dist.P2POp(dist.irecv, n_from_l, r - 1)]
+            in_split[r - 1] = int(sizes[r, 0]); out_split[r - 1] = int(sizes[r - 1, 1])
         if r < w - 1:
-            ops += [dist.P2POp(dist.isend, torch.tensor([len(send_r)], dtype=torch.int64, device=self.device), r + 1),
-                    dist.P2POp(dist.irecv, n_from_r, r + 1)]
-        if ops:
-            for q in dist.batch_isend_irecv(ops):
-                q.wait()
-        recv_l = torch.empty((int(n_from_l.item()), 7), dtype=torch.float32, device=self.device) if r > 0 else None
-        recv_r = torch.empty((int(n_from_r.item()), 7), dtype=torch.float32, device=self.device) if r < w - 1 else None
-        ops = []
-        if r > 0:
-            ops += [dist.P2POp(dist.isend, send_l, r - 1), dist.P2POp(dist.irecv, recv_l, r - 1)]
-        if r < w - 1:
-            ops += [dist.P2POp(dist.isend, send_r, r + 1), dist.P2POp(dist.irecv, recv_r, r + 1)]
-        if ops:
-            for q in dist.batch_isend_irecv(ops):
-                q.wait()
+            in_split[r + 1] = int(sizes[r, 1]); out_split[r + 1] = int(sizes[r + 1, 0])
+        send = torch.cat([t for t in (send_l, send_r) if t is not None]) if (send_l is not None or send_r is not None) \
+            else torch.empty((0, 7), dtype=torch.float32, device=self.device)
+        recv = torch.empty((sum(out_split), 7), dtype=torch.float32, device=self.device)
+        dist.all_to_all_single(recv, send.contiguous(), output_split_sizes=out_split, input_split_sizes=in_split)
+        n_l = out_split[r - 1] if r > 0 else 0
+        recv_l = recv[:n_l] if r > 0 else None
+        recv_r = recv[n_l:] if r < w - 1 else None
         self.halo_bytes = sum(int(t.numel()) * 4 for t in (send_l, send_r) if t is not None)
         return recv_l, recv_r
 
@@ -212,14 +241,15 @@ class SlabJob:
         cnt = torch.tensor([len(mine)], dtype=torch.int64, device=self.device)
         cnts = [torch.zeros(1, dtype=torch.int64, device=self.device) for _ in range(self.world)]
         dist.all_gather(cnts, cnt)
-        mx = int(max(int(c.item()) for c in cnts))
+        cnts = torch.cat(cnts).cpu().tolist()               # one host sync for all ranks' counts
+        mx = max(cnts)
         pad = torch.full((max(mx, 1),), -1, dtype=torch.int64, device=self.device)
         pad[:len(mine)] = mine
         allp = [torch.empty_like(pad) for _ in range(self.world)]
         dist.all_gather(allp, pad)
         if self.rank != 0:
             return None
-        out = torch.cat([a[:int(c.item())] for a, c in zip(allp, cnts)])
+        out = torch.cat([a[:c] for a, c in zip(allp, cnts)])
         return torch.sort(out).values
 
     # ---- the GPU step --------------------------------------------------------------------------------
@@ -231,6 +261,9 @@ class SlabJob:
             self._kp = torch.empty(n + n // 8, dtype=torch.int32, device=self.device)
             self._scores = torch.empty(n + n // 8, dtype=torch.float32, device=self.device)
         det.setForcedGrid(self.plan.origin, self.local_dims, self.offset)
+        if self.device.type == "cuda":
+            # the slab was assembled by torch ops on the current stream: run the detection on that stream too
+            det.setStream(torch.cuda.current_stream(self.device).cuda_stream)
         nkp = det.detectDevice(xyz4.data_ptr(), n, d_role=role.data_ptr(), d_scores=self._scores.data_ptr(), d_kp_idx=self._kp.data_ptr())
         glob = self.finish(self._kp[:nkp])
         self.last_global_keypoints = glob

@@ -1,5 +1,5 @@
 """Multi-rank host logic of the slab sharding on CPU: world_size-2/3 `gloo` process groups exchange the
-halos for real (torch.distributed P2P); the CPU oracle stands in for the CUDA detection call, so the
+halos for real (torch.distributed all_gather + all_to_all); the CPU oracle stands in for the CUDA detection call, so the
 test proves that (a) every rank assembles exactly the slab it needs and (b) the union of the slabs'
 owned results equals the unsharded result bit for bit (forced global grid => same canonical order)."""
 import os
