@@ -47,8 +47,13 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+VIEW_W, VIEW_H = 560, 360            # BASELINE.json configs[4]: ~200 k-point 2.5D views
+
+
 def make_workload(name, n_points):
     from keypoint_learning_b200 import synth
+    if name == "views":
+        raise ValueError("the views workload is built per rank (make_views)")
     if name == "view1m":
         xyz, vp = synth.view_25d(1250, 800, seed=1234)
         desc = "synthetic 1M-point 2.5D view (1250x800 range image, pitch 0.64 mm)"
@@ -56,6 +61,17 @@ def make_workload(name, n_points):
         xyz, vp = synth.scene_closed_surfaces(n_points, seed=4321)
         desc = "synthetic %d-point scene (32 closed surfaces, 2x2x1 m, ~0.64 mm spacing)" % len(xyz)
     return xyz, vp, desc
+
+
+def make_views(rank, distinct):
+    """`distinct` different 560x360 views for this rank (seeds rank*distinct + i), as (n,4) float32."""
+    from keypoint_learning_b200 import synth
+    out, vp = [], None
+    for i in range(distinct):
+        xyz, vp = synth.view_25d(VIEW_W, VIEW_H, seed=rank * distinct + i)
+        x4 = np.ones((len(xyz), 4), np.float32); x4[:, :3] = xyz
+        out.append(x4)
+    return out, vp
 
 
 class ClockSampler:
@@ -120,7 +136,12 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    xyz, vp, desc = make_workload(args.workload, args.points)
+    if args.workload == "views":
+        hv, vp = make_views(0, 1)
+        xyz = hv[0][:, :3].copy()
+        desc = "batch of synthetic 2.5D views (%dx%d px, %d points each)" % (VIEW_W, VIEW_H, len(xyz))
+    else:
+        xyz, vp, desc = make_workload(args.workload, args.points)
     vals = []
     last = None
     for s in range(args.warmup + args.steps):
@@ -155,8 +176,18 @@ def run_b200(args):
     dev = torch.device("cuda", local)
     peak_gbs, peak_src = measured_peaks()
 
-    xyz, vp, desc = make_workload(args.workload, args.points)
-    n_total = len(xyz)
+    views = args.workload == "views"
+    if views:
+        host_views, vp = make_views(rank, args.distinct_views)
+        pts_view = len(host_views[0])
+        n_total = pts_view * args.views_per_gpu * world          # points scored per step by the whole job
+        desc = ("batch of synthetic 2.5D views (%dx%d px, %d points each): %d views per GPU per step, %d distinct per GPU, "
+                "independent units round-robin over the GPUs, no communication (the full config is 4096 views)"
+                % (VIEW_W, VIEW_H, pts_view, args.views_per_gpu, args.distinct_views))
+        xyz = None
+    else:
+        xyz, vp, desc = make_workload(args.workload, args.points)
+        n_total = len(xyz)
 
     det = K.KeypointLearningDetector(device=local)
     det.setNAnnulus(A); det.setNBins(B); det.setNonMaxima(True); det.setNonMaxRadius(R_NMS); det.setNonMaximaDrawsRemove(False)
@@ -168,10 +199,72 @@ def run_b200(args):
     stream = torch.cuda.current_stream(dev)
     det.setStream(stream.cuda_stream)
 
-    if world > 1:
+    acc = {"feat_ms": 0.0, "pairs": 0, "scored": 0, "cand": 0, "launches": 0, "stage": None}
+
+    def account(d_=None):
+        d_ = d_ or det
+        t = d_.timings(); st_ = d_.stats()
+        acc["feat_ms"] += t["features_ms"]; acc["pairs"] += st_["feature_pairs"]; acc["scored"] += st_["n_scored"]
+        acc["cand"] += st_["candidate_pairs"]; acc["launches"] += st_["kernel_launches"]
+        if acc["stage"] is None:
+            acc["stage"] = dict(t)
+        else:
+            for k_ in t:
+                acc["stage"][k_] += t[k_]
+
+    if views:
+        pinned = [torch.from_numpy(v).pin_memory() for v in host_views]
+        d_views = [p_.to(dev, non_blocking=True) for p_ in pinned]
+        d_scores = torch.empty(pts_view, dtype=torch.float32, device=dev)
+        d_kp = torch.empty(pts_view, dtype=torch.int32, device=dev)
+        torch.cuda.synchronize(dev)
+
+        # One 200 k-point view is ~1.5 waves of the feature kernel: a lone view leaves SMs idle in its tail.
+        # Views are independent, so S detector contexts on S streams (one host thread each) keep S views in
+        # flight; kernels of different views then fill each other's tails.  Context 0 is `det`.
+        S = max(1, args.view_streams)
+        dets = [det]
+        for _ in range(1, S):
+            d2_ = K.KeypointLearningDetector(device=local)
+            d2_.setNAnnulus(A); d2_.setNBins(B); d2_.setNonMaxima(True); d2_.setNonMaxRadius(R_NMS); d2_.setNonMaximaDrawsRemove(False)
+            d2_.setPredictionThreshold(float(np.float32(TH))); d2_.setRadiusSearch(R_FEAT)
+            d2_.setNormalsMode(1, k=K_NORMALS, viewpoint=vp); d2_.setCellsPerRadius(args.cpr)
+            assert d2_.loadForest(FOREST)
+            dets.append(d2_)
+        if S > 1:
+            for d_ in dets:
+                d_.setStream(None)                  # each context on its own non-blocking stream
+        outs = [(torch.empty(pts_view, dtype=torch.float32, device=dev), torch.empty(pts_view, dtype=torch.int32, device=dev)) for _ in range(S)]
+        torch.cuda.synchronize(dev)
+        acc_lock = threading.Lock()
+
+        def run_views(t, res):
+            d_, (sc_, kp_) = dets[t], outs[t]
+            nk = 0
+            for v in range(t, args.views_per_gpu, S):
+                nk += d_.detectDevice(d_views[v % len(d_views)].data_ptr(), pts_view, d_scores=sc_.data_ptr(), d_kp_idx=kp_.data_ptr())
+                with acc_lock:
+                    account(d_)
+            res[t] = nk
+
+        def step_fn():
+            res = [0] * S
+            if S == 1:
+                run_views(0, res)
+            else:
+                th = [threading.Thread(target=run_views, args=(t, res)) for t in range(S)]
+                for x in th:
+                    x.start()
+                for x in th:
+                    x.join()
+            return sum(res)
+        n_local = pts_view * args.views_per_gpu
+    elif world > 1:
         from keypoint_learning_b200 import shard
         job = shard.SlabJob(xyz, R_FEAT, R_NMS, args.cpr, rank, world, dev)
-        step_fn = lambda: job.step(det)            # noqa: E731
+
+        def step_fn():
+            nk = job.step(det); account(); return nk
         n_local = job.n_owned
     else:
         xyz4 = np.ones((n_total, 4), np.float32); xyz4[:, :3] = xyz
@@ -180,7 +273,9 @@ def run_b200(args):
         d_scores = torch.empty(n_total, dtype=torch.float32, device=dev)
         d_kp = torch.empty(n_total, dtype=torch.int32, device=dev)
         torch.cuda.synchronize(dev)
-        step_fn = lambda: det.detectDevice(d_xyz4.data_ptr(), n_total, d_scores=d_scores.data_ptr(), d_kp_idx=d_kp.data_ptr())  # noqa: E731
+
+        def step_fn():
+            nk = det.detectDevice(d_xyz4.data_ptr(), n_total, d_scores=d_scores.data_ptr(), d_kp_idx=d_kp.data_ptr()); account(); return nk
         n_local = n_total
 
     def barrier():
@@ -192,8 +287,9 @@ def run_b200(args):
     for _ in range(args.warmup):
         step_fn()
     sampler = ClockSampler(local)
-    feat_ms, stage = [], None
-    launches = 0
+    for k_ in ("feat_ms", "pairs", "scored", "cand", "launches"):
+        acc[k_] = 0
+    acc["stage"] = None
     barrier()
     if rank == 0:
         sampler.start()
@@ -202,8 +298,6 @@ def run_b200(args):
     nkp = 0
     for _ in range(args.steps):
         nkp = step_fn()
-        t = det.timings(); feat_ms.append(t["features_ms"]); stage = t
-        launches += det.stats()["kernel_launches"]
     ev1.record(stream)
     barrier()
     ms = ev0.elapsed_time(ev1)
@@ -215,8 +309,11 @@ def run_b200(args):
     ms_per_step = ms / args.steps
     value = n_total / (ms_per_step * 1e-3)
     st = det.stats()
+    launches = acc["launches"]
+    stage = {k_: v_ / args.steps for k_, v_ in acc["stage"].items()}          # per step (summed over the step's calls)
+    snap = dict(acc)                                                          # the e2e leg below keeps accounting
     per_rank = None
-    if world > 1:
+    if world > 1 and not views:
         # device time, slab size and pair count of every rank for the last step: shows the load balance
         mine = torch.tensor([stage["total_ms"], float(job.last_slab_points), float(st["feature_pairs"])], device=dev, dtype=torch.float64)
         allr = [torch.zeros_like(mine) for _ in range(world)]
@@ -225,7 +322,43 @@ def run_b200(args):
 
     # ---- e2e: host buffers through the public host API (H2D + compute + D2H every step) ----------
     e2e = None
-    if world == 1:
+    if views:
+        # every view: H2D from pinned host memory, detection, scores + keypoint indices back to the host (kpl_detect)
+        steps_e2e = max(1, min(args.steps, 3))
+        host_np = [p_.numpy() for p_ in pinned]
+        for d_ in dets:
+            d_.setInputCloud(host_np[0]); d_.setNormals(None); d_.compute()      # warm the staging buffers
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record(stream)
+        nkb = [0] * len(dets)
+
+        def e2e_views(t):
+            for v in range(t, args.views_per_gpu, len(dets)):
+                dets[t].setInputCloud(host_np[v % len(host_np)])
+                _, idx = dets[t].compute()
+                nkb[t] += len(idx) * 4
+
+        for _ in range(steps_e2e):
+            th = [threading.Thread(target=e2e_views, args=(t,)) for t in range(len(dets))]
+            for x in th:
+                x.start()
+            for x in th:
+                x.join()
+        nk_bytes = sum(nkb)
+        e1.record(stream)
+        barrier()
+        wall = (time.perf_counter() - t0) / steps_e2e
+        e2e_ms = max(e0.elapsed_time(e1) / steps_e2e, wall * 1e3)
+        if world > 1:
+            tms = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+            e2e_ms = float(tms.item())
+        e2e = {"value": n_total / (e2e_ms * 1e-3), "unit": "points/s", "h2d_bytes_per_step": int(n_total * 16),
+               "d2h_bytes_per_step": int(n_total * 4 + world * nk_bytes // steps_e2e), "ms_per_step": e2e_ms,
+               "api": "kpl_detect per view (host xyz, pinned; normals estimated on device; scores + keypoint indices copied back)"}
+    elif world == 1:
         sc_host = torch.empty(n_total, dtype=torch.float32).pin_memory().numpy()
         host_np = host_xyz4.numpy()
         det.setInputCloud(host_np); det.setNormals(None)
@@ -267,36 +400,43 @@ def run_b200(args):
                "api": "SlabJob.step: owned slab H2D from pinned host, NCCL halo exchange, kpl_detect_device, global keypoint list to host"}
 
     # ---- roofline of the dominant kernel (feature_kernel), algorithmic bytes per SURVEY.md 8d -------
-    pairs_self = st["feature_pairs"] + st["n_scored"]            # K_f with the query itself included
+    # per launch = per kpl_detect call; this rank's launches of the timed region
+    calls = args.steps * (args.views_per_gpu if views else 1)
+    pairs_self = (snap["pairs"] + snap["scored"]) / calls        # K_f with the query itself included, per launch
     feat_bytes = 32.0 * pairs_self
-    feat_s = float(np.mean(feat_ms)) * 1e-3
+    feat_s = snap["feat_ms"] / calls * 1e-3
     achieved = feat_bytes / feat_s / 1e9
-    pipe_bytes = 32.0 * pairs_self + 16.0 * K_NORMALS * st["n_points"] + 200.0 * st["n_points"]  # + 20*K_n*[above th], added below
+    pts_launch = snap["scored"] / calls
+    pipe_bytes = (32.0 * pairs_self + 16.0 * K_NORMALS * pts_launch + 200.0 * pts_launch) * (args.views_per_gpu if views else 1)
     roofline = {"bound": "hbm", "kernel": "feature_kernel", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
                 "traffic": (measured_traffic(args.workload) or {}).get("dram_bytes_per_launch") if world == 1 else None,
                 "traffic_source": (measured_traffic(args.workload) or {}).get("source") if world == 1 else None,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": feat_bytes,
-                "kernel_ms": feat_s * 1e3, "pairs_per_s": st["feature_pairs"] / feat_s,
-                "candidate_tests_per_s": st["candidate_pairs"] / feat_s,
-                "acceptance": st["feature_pairs"] / max(1, st["candidate_pairs"]),
+                "kernel_ms": feat_s * 1e3, "launches_per_step": calls // args.steps, "pairs_per_s": snap["pairs"] / calls / feat_s,
+                "candidate_tests_per_s": snap["cand"] / calls / feat_s,
+                "acceptance": snap["pairs"] / max(1, snap["cand"]),
                 "pipeline_frac_rank0": (pipe_bytes / (ms_per_step * 1e-3) / 1e9) / peak_gbs if world == 1 else None,
                 "stage_ms": stage, "fast_math_selftest_passed": bool(st["fast_math"])}
 
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu:
-            c = cpu_baseline_run(xyz, vp, args.cpu_sample)
+            c = cpu_baseline_run(host_views[0][:, :3].copy() if views else xyz, vp, args.cpu_sample)
             cpu = {"value": c["value"], "unit": "points/s", "cores": c["cores"], "kind": "port", "sample": c["sample"], "stage_ms": c["stage_ms"]}
         line = {"metric": "points scored/sec (search+normals+features+RF+NMS)", "value": value, "unit": "points/s", "n_gpus": world,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak" if views else "strong",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": desc, "radiusFeatures": R_FEAT, "radiusNMS": R_NMS, "threshold": TH, "annuli": A, "bins": B,
                            "forest": os.path.basename(FOREST), "normals": "kNN-%d on device" % K_NORMALS, "cells_per_radius": args.cpr,
-                           "parallelism": "slab%d+halo" % world if world > 1 else "single",
-                           "l2": "inputs and intermediates (%.0f MB) exceed the 126 MB L2; no flush needed" % (n_total * (16 + 16 + 16 + 200 + 16) / 1e6)},
+                           "view_streams": args.view_streams if views else None,
+                           "parallelism": ("views-dp%d" % world) if views else ("slab%d+halo" % world if world > 1 else "single"),
+                           "l2": "inputs and intermediates of a step (%.0f MB) exceed the 126 MB L2; no flush needed" % (n_total / world * (16 + 16 + 16 + 16 + 16) / 1e6)},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
                 "keypoints": int(nkp), "n_points": n_total, "points_per_rank": n_local, "per_rank": per_rank}
         print(json.dumps(line), flush=True)
+    if views:
+        for d_ in dets[1:]:
+            d_.close()
     det.close()
     if world > 1:
         dist.destroy_process_group()
@@ -308,7 +448,10 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="scene10m", choices=["scene10m", "view1m"])
+    ap.add_argument("--workload", default="scene10m", choices=["scene10m", "view1m", "views"])
+    ap.add_argument("--views-per-gpu", type=int, default=32, help="views workload: detections per GPU per step")
+    ap.add_argument("--distinct-views", type=int, default=8, help="views workload: different views resident per GPU")
+    ap.add_argument("--view-streams", type=int, default=3, help="views workload: detector contexts / streams per GPU")
     ap.add_argument("--points", type=int, default=10_000_000)
     ap.add_argument("--cpr", type=int, default=4, help="grid cells per radiusFeatures")
     ap.add_argument("--cpu-sample", type=int, default=1_500_000, help="points of the workload crop the CPU legs run on (~10-20 s of host work)")
