@@ -99,7 +99,7 @@ void kpl_destroy(kpl_ctx* ctx)
     release(ctx->in_xyz); release(ctx->in_nrm); release(ctx->in_role); release(ctx->s_role);
     release(ctx->key_a); release(ctx->key_b); release(ctx->idx_a); release(ctx->idx_b); release(ctx->cub_tmp);
     release(ctx->cell_start); release(ctx->s_pos); release(ctx->s_nrm); release(ctx->feat);
-    release(ctx->s_score); release(ctx->score); release(ctx->flag); release(ctx->kp_idx);
+    release(ctx->s_score); release(ctx->score); release(ctx->flag); release(ctx->s_state); release(ctx->kp_idx);
     release(ctx->scratch_f); release(ctx->scratch_i); release(ctx->counters);
     if (ctx->d_bbox) cudaFree(ctx->d_bbox);
     if (ctx->forest.d_nodes) cudaFree(ctx->forest.d_nodes);
@@ -275,7 +275,8 @@ static int run_detect(kpl_ctx* ctx, const float4* d_xyz, const float4* d_nrm, co
     if (n_kp_out) *n_kp_out = 0;
     if (n < 0 || n > 2147483000ll) return fail(ctx, KPL_E_INVALID, "point count out of range");
     if (ctx->forest.ntrees < 1) return fail(ctx, KPL_E_FOREST, "no forest loaded");
-    if (P.draws_remove && P.non_maxima) return fail(ctx, KPL_E_UNSUPPORTED, "non_maxima_draws_remove is not implemented (off in TestDetector)");
+    if (P.draws_remove && P.non_maxima && d_role)
+        return fail(ctx, KPL_E_UNSUPPORTED, "draws-remove NMS walks the whole cloud in index order (hpp:233-250): not available for slab-sharded calls");
     const int F = P.n_annulus * P.n_bins;
     if (ctx->forest.var_count > 0 && ctx->forest.var_count != F) return fail(ctx, KPL_E_VARCOUNT, "annuli*bins does not match the forest's var_count");
     ctx->stats.n_points = n;
@@ -298,7 +299,8 @@ static int run_detect(kpl_ctx* ctx, const float4* d_xyz, const float4* d_nrm, co
     KPL_CUDA(cudaEventRecord(ctx->ev[3], ctx->stream));
     if (!fuse) KPL_CUDA(launch_forest(ctx, n, d_role != nullptr));
     KPL_CUDA(cudaEventRecord(ctx->ev[4], ctx->stream));
-    if (P.non_maxima) KPL_CUDA(launch_nms(ctx, n, d_role != nullptr));
+    if (P.non_maxima && P.draws_remove) KPL_CUDA(launch_nms_draws(ctx, n, d_role != nullptr));
+    else if (P.non_maxima) KPL_CUDA(launch_nms(ctx, n, d_role != nullptr));
     else KPL_CUDA(launch_all_flags(ctx, n));
     KPL_CUDA(launch_compact(ctx, n, d_kp_out));
     if (d_scores_out) KPL_CUDA(cudaMemcpyAsync(d_scores_out, ctx->score.p, (size_t)n * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));

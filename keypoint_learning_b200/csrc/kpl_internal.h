@@ -77,6 +77,7 @@ struct kpl_ctx {
     kpl::DevBuf<float> feat;                     // n x F, sorted order
     kpl::DevBuf<float> s_score, score;           // sorted order / original order
     kpl::DevBuf<uint8_t> flag;                   // keypoint flag, original order
+    kpl::DevBuf<uint8_t> s_state;                // draws-remove NMS state, sorted order
     kpl::DevBuf<int32_t> kp_idx;
     kpl::DevBuf<float> scratch_f;                // fetch / reorder scratch
     kpl::DevBuf<int32_t> scratch_i;
@@ -104,6 +105,7 @@ cudaError_t launch_check_normals(kpl_ctx* c, int64_t n);
 cudaError_t launch_features(kpl_ctx* c, int64_t n, bool use_role, bool fuse_forest, bool store_rows);
 cudaError_t launch_forest(kpl_ctx* c, int64_t n, bool use_role);
 cudaError_t launch_nms(kpl_ctx* c, int64_t n, bool use_role);
+cudaError_t launch_nms_draws(kpl_ctx* c, int64_t n, bool use_role);
 cudaError_t launch_compact(kpl_ctx* c, int64_t n, int32_t* d_kp_idx_out);
 cudaError_t launch_radius_stats(kpl_ctx* c, int64_t n, double radius, int32_t* d_counts, unsigned long long* d_hash);
 cudaError_t launch_radius_lists(kpl_ctx* c, int64_t n, double radius, const int32_t* d_queries, int64_t m,

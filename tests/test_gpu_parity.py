@@ -287,6 +287,28 @@ def test_nms_semantics(kpl, oracle):
         d.close()
 
 
+def test_nms_draws_remove_branch(kpl, views, oracle):
+    """hpp:233-250 (setNonMaximaDrawsRemove(true), the class default): sequential skip-list semantics of the
+    reference, resolved on the device in dependency rounds.  Scores are k/ntrees, so ties are everywhere."""
+    xyz = views["cheff002"]
+    nrm = oracle.normals_knn(xyz, 10)
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_cheff002.npz"))
+    total = 0
+    for r_nms, th, dthr in ((4.0, 0.85, 2.0), (4.0, 0.5, 1.0), (8.0, 0.3, 8.0), (2.0, 0.0, 0.7), (4.0, 0.85, 0.0)):
+        d = make_detector(kpl, r_nms=r_nms, th=th)
+        d.setNonMaximaDrawsRemove(True); d.setNonMaximaDrawsThreshold(dthr)
+        d.setInputCloud(xyz); d.setNormals(nrm)
+        _, idx = d.compute()
+        assert np.array_equal(d.getResponse().view(np.uint32), g["scores"].view(np.uint32))
+        ref = oracle.nms(xyz, g["scores"], r_nms, th, draws_remove=True, draws_thr=dthr)
+        assert np.array_equal(idx, ref), (r_nms, th, dthr, len(idx), len(ref))
+        plain = oracle.nms(xyz, g["scores"], r_nms, th)
+        assert set(idx.tolist()) <= set(plain.tolist())        # the branch only ever removes keypoints
+        total += len(plain) - len(idx)
+        d.close()
+    assert total > 0                                            # the cases really exercise the branch
+
+
 def test_non_maxima_off_returns_every_point(kpl, views, oracle):
     xyz = np.ascontiguousarray(views["cheff001"][:5000])
     d = make_detector(kpl)
