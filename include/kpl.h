@@ -135,6 +135,12 @@ KPL_API int kpl_detect(kpl_ctx* ctx, const float* xyz, int32_t xyz_stride, const
  * normals_out = n x (nx, ny, nz, curvature). Mode / k / viewpoint / flip come from the params. */
 KPL_API int kpl_normals(kpl_ctx* ctx, const float* xyz, int32_t xyz_stride, int64_t n, float* normals_out);
 
+/* pcl::UniformSampling as TestDetector's --subSampling uses it (main_test_detector.cpp:145-157): one point
+ * per leaf-sized voxel, the one closest to the voxel centre (ties: lower index).  idx_out (capacity n)
+ * receives the ascending original indices of the survivors, *m_out their number. */
+KPL_API int kpl_uniform_sample(kpl_ctx* ctx, const float* xyz, int32_t xyz_stride, int64_t n, float leaf,
+                               int32_t* idx_out, int64_t* m_out);
+
 /* computePointsForTrainingFeatures (impl/KeypointLearning.hpp:299-318): rows of A*B floats for the
  * m given point indices (NULL: all points, m == n). */
 KPL_API int kpl_features(kpl_ctx* ctx, const float* xyz, int32_t xyz_stride, const float* normals, int32_t normals_stride,

@@ -500,6 +500,40 @@ int kpl_radius_neighbors(kpl_ctx* ctx, const float* xyz, int32_t xyz_stride, int
     return KPL_OK;
 }
 
+int kpl_uniform_sample(kpl_ctx* ctx, const float* xyz, int32_t xyz_stride, int64_t n, float leaf, int32_t* idx_out, int64_t* m_out)
+{
+    if (!ctx || !m_out || (n > 0 && !idx_out)) return KPL_E_INVALID;
+    begin_call(ctx);
+    *m_out = 0;
+    if (!(leaf > 0.f) || !std::isfinite(leaf)) return fail(ctx, KPL_E_INVALID, "leaf must be > 0");
+    if (n < 0 || n > 2147483000ll) return fail(ctx, KPL_E_INVALID, "point count out of range");
+    if (n == 0) return KPL_OK;
+    int rc = upload_inputs(ctx, xyz, xyz_stride, nullptr, 0, nullptr, n);
+    if (rc) return rc;
+    KPL_CUDA(launch_bbox(ctx, ctx->in_xyz.p, n, ctx->d_bbox));
+    uint32_t hb[8];
+    KPL_CUDA(cudaMemcpyAsync(hb, ctx->d_bbox, sizeof hb, cudaMemcpyDeviceToHost, ctx->stream));
+    KPL_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (hb[6]) return fail(ctx, KPL_E_NONFINITE, "input cloud holds non-finite points");
+    float mn[3], mx[3];
+    for (int a = 0; a < 3; ++a) { mn[a] = dec_float(hb[a]); mx[a] = dec_float(hb[3 + a]); }
+    KPL_CUDA(ensure(ctx->kp_idx, (size_t)n));
+    KPL_CUDA(cudaMemsetAsync(ctx->counters.p, 0, 8 * sizeof(unsigned long long), ctx->stream));
+    std::string err;
+    cudaError_t e = uniform_sample(ctx, ctx->in_xyz.p, n, leaf, mn, mx, ctx->kp_idx.p, err);
+    if (e == cudaErrorInvalidValue && !err.empty()) return fail(ctx, KPL_E_GRID, err);
+    KPL_CUDA(e);
+    unsigned long long hc[8];
+    KPL_CUDA(cudaMemcpyAsync(hc, ctx->counters.p, sizeof hc, cudaMemcpyDeviceToHost, ctx->stream));
+    KPL_CUDA(cudaStreamSynchronize(ctx->stream));
+    const int64_t m = (int64_t)(hc[3] & 0xFFFFFFFFull);
+    if (m > 0) KPL_CUDA(cudaMemcpyAsync(idx_out, ctx->kp_idx.p, (size_t)m * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    KPL_CUDA(cudaStreamSynchronize(ctx->stream));
+    *m_out = m;
+    ctx->stats.n_points = n; ctx->stats.kernel_launches = ctx->launches;
+    return KPL_OK;
+}
+
 int kpl_get_timings(const kpl_ctx* ctx, kpl_timings* t)
 {
     if (!ctx || !t) return KPL_E_INVALID;

@@ -24,6 +24,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include "kpl_internal.h"
 #include "kpl_math.cuh"
 #include "forest.cuh"
@@ -492,9 +493,13 @@ feature_kernel(const float4* __restrict__ s_pos, const float4* __restrict__ s_nr
 static cudaError_t fast_math_verdict(kpl_ctx* c, const FeatParams& P, bool& fast)
 {
     struct Verdict { float adim, bdim; int device; bool fast; };
-    static std::vector<Verdict> cache;
-    for (const Verdict& v : cache)
-        if (v.adim == P.adim && v.bdim == P.bdim && v.device == c->device) { fast = v.fast; return cudaSuccess; }
+    static std::vector<Verdict> cache;          // process-wide: contexts on several host threads share it
+    static std::mutex cache_mutex;
+    {
+        std::lock_guard<std::mutex> lock(cache_mutex);
+        for (const Verdict& v : cache)
+            if (v.adim == P.adim && v.bdim == P.bdim && v.device == c->device) { fast = v.fast && P.r2 <= FAST_SQRT_HI; return cudaSuccess; }
+    }
     unsigned* d_res = reinterpret_cast<unsigned*>(c->counters.p + 6);   // counters[6..7] are scratch
     cudaError_t e;
     if ((e = cudaMemsetAsync(d_res, 0, 4 * sizeof(unsigned), c->stream))) return e;
@@ -504,8 +509,12 @@ static cudaError_t fast_math_verdict(kpl_ctx* c, const FeatParams& P, bool& fast
     if ((e = cudaStreamSynchronize(c->stream))) return e;
     if ((e = cudaMemsetAsync(d_res, 0, 4 * sizeof(unsigned), c->stream))) return e;
     if (h[3] != 0) return cudaErrorAssert;   // packed FP32 is not IEEE RN on this device: no exact path exists
-    fast = (h[0] == 0 && h[1] == 0 && h[2] == 0) && P.r2 <= FAST_SQRT_HI;
-    cache.push_back({P.adim, P.bdim, c->device, fast});
+    fast = (h[0] == 0 && h[1] == 0 && h[2] == 0);
+    {
+        std::lock_guard<std::mutex> lock(cache_mutex);
+        cache.push_back({P.adim, P.bdim, c->device, fast});
+    }
+    fast = fast && P.r2 <= FAST_SQRT_HI;         // the fast sqrt is only proven below 2^40
     c->launches++;
     return cudaGetLastError();
 }
@@ -546,12 +555,9 @@ cudaError_t launch_features(kpl_ctx* c, int64_t n, bool use_role, bool fuse_fore
     if (const char* e = getenv("KPL_FEAT_WARPS")) wpb = std::max(1, std::min(FEAT_WARPS, atoi(e)));   // tuning experiments only
     size_t smem = (size_t)wpb * (P.F * 32 + 192) * sizeof(float);
     if (smem > 227 * 1024) return cudaErrorInvalidValue;
-    static size_t configured[2] = {0, 0};
     auto kern = fast ? feature_kernel<true> : feature_kernel<false>;
-    if (smem > 48 * 1024 && smem > configured[fast]) {
-        if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return e;
-        configured[fast] = smem;
-    }
+    // per device and per process state of the runtime: set it on every launch that needs it (a host-side call)
+    if (smem > 48 * 1024 && (e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return e;
     int warps = (int)((n + 31) / 32);
     int blocks = (warps + wpb - 1) / wpb;
     kern<<<blocks, wpb * 32, smem, c->stream>>>(c->s_pos.p, c->s_nrm.p, c->key_b.p, c->cell_start.p,

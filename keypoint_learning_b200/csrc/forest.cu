@@ -54,11 +54,7 @@ cudaError_t launch_forest(kpl_ctx* c, int64_t n, bool use_role)
     if ((e = ensure(c->s_score, n)) || (e = ensure(c->score, n))) return e;
     size_t smem = (size_t)F * FOREST_THREADS * sizeof(float);
     if (smem > 227 * 1024) return cudaErrorInvalidValue;
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        if ((e = cudaFuncSetAttribute(forest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return e;
-        configured = smem;
-    }
+    if (smem > 48 * 1024 && (e = cudaFuncSetAttribute(forest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return e;
     int blocks = (int)((n + FOREST_THREADS - 1) / FOREST_THREADS);
     forest_kernel<<<blocks, FOREST_THREADS, smem, c->stream>>>(c->feat.p, c->forest.d_nodes, c->forest.d_roots, c->forest.ntrees, F, (int)n,
                                                                use_role ? c->s_role.p : nullptr, c->s_pos.p, c->s_nrm.p, c->s_score.p, c->score.p,

@@ -17,6 +17,7 @@
 #include <cub/device/device_select.cuh>
 #include <thrust/iterator/reverse_iterator.h>
 #include <thrust/iterator/counting_iterator.h>
+#include <cmath>
 #include "kpl_internal.h"
 
 namespace kpl {
@@ -161,6 +162,87 @@ cudaError_t launch_compact(kpl_ctx* c, int64_t n, int32_t* d_kp_idx_out)
     bytes = c->cub_tmp.cap;
     if ((e = cub::DeviceSelect::Flagged(c->cub_tmp.p, bytes, it, c->flag.p, d_kp_idx_out, d_cnt, (int)n, c->stream))) return e;
     c->launches += 2;
+    return cudaGetLastError();
+}
+
+// ---- pcl::UniformSampling (src/main_test_detector.cpp:145-157) ----------------------------------
+// One survivor per leaf-sized voxel: the point closest to the voxel centre (PCL 1.8 filters/uniform_sampling:
+// ijk = floor(p * (1/leaf)) in FP32, centre = (ijk + 0.5) * leaf), ties to the lower index; survivors are
+// reported in ascending original index (PCL emits them in unordered_map order, which is platform dependent).
+// Same machinery as the neighbour grid: voxel keys, a stable radix sort, one scan of each run of equal keys.
+__global__ void __launch_bounds__(256) voxel_key_kernel(const float4* __restrict__ xyz, int64_t n, float inv_leaf, float leaf,
+                                                        int mbx, int mby, int mbz, unsigned long long dx, unsigned long long dy,
+                                                        unsigned long long* __restrict__ keys, uint32_t* __restrict__ idx, float* __restrict__ dist)
+{
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 p = __ldg(xyz + i);
+    const float fx = floorf(__fmul_rn(p.x, inv_leaf)), fy = floorf(__fmul_rn(p.y, inv_leaf)), fz = floorf(__fmul_rn(p.z, inv_leaf));
+    const unsigned long long ix = (unsigned long long)((long long)fx - mbx), iy = (unsigned long long)((long long)fy - mby),
+                             iz = (unsigned long long)((long long)fz - mbz);
+    keys[i] = (iz * dy + iy) * dx + ix;
+    idx[i] = (uint32_t)i;
+    const float cx = __fmul_rn(__fadd_rn(fx, 0.5f), leaf), cy = __fmul_rn(__fadd_rn(fy, 0.5f), leaf), cz = __fmul_rn(__fadd_rn(fz, 0.5f), leaf);
+    const float ex = __fsub_rn(cx, p.x), ey = __fsub_rn(cy, p.y), ez = __fsub_rn(cz, p.z);
+    dist[i] = __fadd_rn(__fmul_rn(ex, ex), __fadd_rn(__fmul_rn(ey, ey), __fmul_rn(ez, ez)));
+}
+
+__global__ void __launch_bounds__(256) voxel_pick_kernel(const unsigned long long* __restrict__ skeys, const uint32_t* __restrict__ sidx,
+                                                         const float* __restrict__ dist, int64_t n, uint8_t* __restrict__ flag)
+{
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long k = skeys[i];
+    if (i > 0 && skeys[i - 1] == k) return;                 // not the head of its run
+    uint32_t best = sidx[i];
+    float bd = dist[best];
+    for (int64_t j = i + 1; j < n && skeys[j] == k; ++j) {  // the sort is stable: ascending original index inside a run
+        const uint32_t o = sidx[j];
+        const float d = dist[o];
+        if (d < bd) { bd = d; best = o; }
+    }
+    flag[best] = 1;
+}
+
+cudaError_t uniform_sample(kpl_ctx* c, const float4* xyz, int64_t n, float leaf, const float mn[3], const float mx[3],
+                           int32_t* d_idx_out, std::string& err)
+{
+    const float inv_leaf = 1.0f / leaf;
+    long long mb[3], db[3];
+    for (int a = 0; a < 3; ++a) {
+        mb[a] = (long long)floorf(mn[a] * inv_leaf);
+        db[a] = (long long)floorf(mx[a] * inv_leaf) - mb[a] + 1;
+        if (mb[a] < -2000000000ll || mb[a] > 2000000000ll || db[a] < 1) { err = "leaf size too small for this cloud"; return cudaErrorInvalidValue; }
+    }
+    if ((double)db[0] * (double)db[1] * (double)db[2] > 1.8e19) { err = "leaf size too small for this cloud (more than 2^64 voxels)"; return cudaErrorInvalidValue; }
+    cudaError_t e;
+    DevBuf<uint8_t>& tmp = c->cub_tmp;
+    // scratch: keys a/b (u64), idx a/b (u32), dist (f32), flags (u8) carved from scratch buffers
+    if ((e = ensure(c->scratch_f, (size_t)n * 5 + 16)) || (e = ensure(c->scratch_i, (size_t)n * 2 + 16)) || (e = ensure(c->flag, (size_t)n))) return e;
+    unsigned long long* key_a = reinterpret_cast<unsigned long long*>(c->scratch_f.p);
+    unsigned long long* key_b = key_a + n;
+    float* dist = c->scratch_f.p + 4 * (size_t)n + 8;
+    uint32_t* idx_a = reinterpret_cast<uint32_t*>(c->scratch_i.p);
+    uint32_t* idx_b = idx_a + n;
+    int end_bit = 1;
+    const double nvox = (double)db[0] * (double)db[1] * (double)db[2];
+    while (end_bit < 64 && std::ldexp(1.0, end_bit) < nvox) end_bit++;
+    size_t sort_bytes = 0, sel_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, key_a, key_b, idx_a, idx_b, (int)n, 0, end_bit, c->stream);
+    thrust::counting_iterator<int32_t> it(0);
+    int32_t* d_cnt = (int32_t*)(c->counters.p + 3);
+    cub::DeviceSelect::Flagged(nullptr, sel_bytes, it, c->flag.p, d_idx_out, d_cnt, (int)n, c->stream);
+    if ((e = ensure(tmp, std::max(sort_bytes, sel_bytes)))) return e;
+    const unsigned blocks = (unsigned)((n + 255) / 256);
+    voxel_key_kernel<<<blocks, 256, 0, c->stream>>>(xyz, n, inv_leaf, leaf, (int)mb[0], (int)mb[1], (int)mb[2],
+                                                    (unsigned long long)db[0], (unsigned long long)db[1], key_a, idx_a, dist);
+    size_t bytes = tmp.cap;
+    if ((e = cub::DeviceRadixSort::SortPairs(tmp.p, bytes, key_a, key_b, idx_a, idx_b, (int)n, 0, end_bit, c->stream))) return e;
+    if ((e = cudaMemsetAsync(c->flag.p, 0, (size_t)n, c->stream))) return e;
+    voxel_pick_kernel<<<blocks, 256, 0, c->stream>>>(key_b, idx_b, dist, n, c->flag.p);
+    bytes = tmp.cap;
+    if ((e = cub::DeviceSelect::Flagged(tmp.p, bytes, it, c->flag.p, d_idx_out, d_cnt, (int)n, c->stream))) return e;
+    c->launches += 4 + (end_bit + 7) / 8 + 1;
     return cudaGetLastError();
 }
 

@@ -107,6 +107,8 @@ cudaError_t launch_forest(kpl_ctx* c, int64_t n, bool use_role);
 cudaError_t launch_nms(kpl_ctx* c, int64_t n, bool use_role);
 cudaError_t launch_nms_draws(kpl_ctx* c, int64_t n, bool use_role);
 cudaError_t launch_compact(kpl_ctx* c, int64_t n, int32_t* d_kp_idx_out);
+cudaError_t uniform_sample(kpl_ctx* c, const float4* xyz, int64_t n, float leaf, const float mn[3], const float mx[3],
+                           int32_t* d_idx_out, std::string& err);
 cudaError_t launch_radius_stats(kpl_ctx* c, int64_t n, double radius, int32_t* d_counts, unsigned long long* d_hash);
 cudaError_t launch_radius_lists(kpl_ctx* c, int64_t n, double radius, const int32_t* d_queries, int64_t m,
                                 const int64_t* d_offsets, int32_t* d_indices);

@@ -1,4 +1,4 @@
-// pcl_shim.cpp -- PCD v0.7 IO, NormalEstimation and UniformSampling stand-ins (see pcl_shim.h).
+// pcl_shim.cpp -- PCD v0.7 IO; NormalEstimation and UniformSampling forward to the C ABI (see pcl_shim.h).
 #include "pcl_shim.h"
 
 #include <algorithm>
@@ -259,37 +259,28 @@ bool NormalEstimation<PointInT, NormalT>::compute(PointCloud<NormalT>& out, std:
 }
 template class NormalEstimation<PointXYZ, Normal>;
 
-// ---- UniformSampling ----------------------------------------------------------------------------
+// ---- UniformSampling -> kpl_uniform_sample ---------------------------------------------------------
 template <typename PointT>
 void UniformSampling<PointT>::filter(PointCloud<PointT>& out)
 {
     typename PointCloud<PointT>::ConstPtr in = input_;
     std::vector<PointT> kept;
     if (in && leaf_ > 0 && !in->points.empty()) {
-        float mn[3] = {in->points[0].x, in->points[0].y, in->points[0].z};
-        for (const PointT& p : in->points) if (isFinite(p)) { mn[0] = std::min(mn[0], p.x); mn[1] = std::min(mn[1], p.y); mn[2] = std::min(mn[2], p.z); }
-        const double inv = 1.0 / leaf_;
-        // PCL: min_b = floor(min * inverse_leaf); ijk = floor(p * inverse_leaf) - min_b; keep the point closest to the voxel centre
-        long minb[3] = {(long)std::floor(mn[0] * inv), (long)std::floor(mn[1] * inv), (long)std::floor(mn[2] * inv)};
-        struct Best { size_t idx; double d; };
-        std::map<std::tuple<long, long, long>, Best> leaves;
-        for (size_t i = 0; i < in->points.size(); ++i) {
-            const PointT& p = in->points[i];
-            if (!isFinite(p)) continue;
-            long ijk[3] = {(long)std::floor(p.x * inv) - minb[0], (long)std::floor(p.y * inv) - minb[1], (long)std::floor(p.z * inv) - minb[2]};
-            double c[3] = {(ijk[0] + minb[0] + 0.5) * leaf_, (ijk[1] + minb[1] + 0.5) * leaf_, (ijk[2] + minb[2] + 0.5) * leaf_};
-            double d = (p.x - c[0]) * (p.x - c[0]) + (p.y - c[1]) * (p.y - c[1]) + (p.z - c[2]) * (p.z - c[2]);
-            auto key = std::make_tuple(ijk[0], ijk[1], ijk[2]);
-            auto it = leaves.find(key);
-            if (it == leaves.end()) leaves.emplace(key, Best{i, d});
-            else if (d < it->second.d) it->second = Best{i, d};
+        kpl_ctx* ctx = nullptr;
+        if (kpl_create(0, &ctx) != KPL_OK) {
+            std::fprintf(stderr, "[pcl::UniformSampling::filter] no usable sm_100 device; there is no CPU path\n");
+        } else {
+            const int64_t n = (int64_t)in->points.size();
+            std::vector<int32_t> idx((size_t)n);
+            int64_t m = 0;
+            if (kpl_uniform_sample(ctx, reinterpret_cast<const float*>(in->points.data()), (int32_t)sizeof(PointT), n, (float)leaf_, idx.data(), &m) != KPL_OK)
+                std::fprintf(stderr, "[pcl::UniformSampling::filter] %s\n", kpl_last_error(ctx));
+            else {
+                kept.reserve((size_t)m);
+                for (int64_t k = 0; k < m; ++k) kept.push_back(in->points[(size_t)idx[(size_t)k]]);
+            }
+            kpl_destroy(ctx);
         }
-        std::vector<size_t> idx;
-        idx.reserve(leaves.size());
-        for (auto& kv : leaves) idx.push_back(kv.second.idx);
-        std::sort(idx.begin(), idx.end());
-        kept.reserve(idx.size());
-        for (size_t i : idx) kept.push_back(in->points[i]);
     }
     out.points.swap(kept);          // `out` may alias the input cloud (main_test_detector.cpp:156)
     out.width = (uint32_t)out.points.size(); out.height = 1; out.is_dense = true;

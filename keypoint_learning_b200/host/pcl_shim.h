@@ -114,8 +114,8 @@ private:
 };
 
 // pcl::UniformSampling (main_test_detector.cpp:145-157): one point per leaf-sized voxel, the one
-// closest to the voxel centre.  PCL emits them in hash-map order (platform dependent); here the
-// survivors keep their original relative order, which is deterministic.
+// closest to the voxel centre, computed on the device (kpl_uniform_sample).  PCL emits the survivors in
+// hash-map order (platform dependent); here they keep their original relative order.
 template <typename PointT>
 class UniformSampling {
 public:

@@ -159,6 +159,26 @@ def normals_radius(xyz, radius, viewpoint=(0.0, 0.0, 0.0), order=0, cpr=4):
     return out
 
 
+def uniform_sample(xyz, leaf):
+    """pcl::UniformSampling (PCL 1.8 filters/uniform_sampling, call site src/main_test_detector.cpp:145-157),
+    restated in FP32 numpy: ijk = floor(p * (1/leaf)), centre = (ijk + 0.5) * leaf, keep the point closest to
+    the centre (squared distance dx^2 + (dy^2 + dz^2)), ties to the lower index; ascending indices."""
+    x = _xyz(xyz)
+    leaf = np.float32(leaf)
+    inv = np.float32(1.0) / leaf
+    f = np.floor(x * inv)
+    mb = np.floor(x.min(axis=0) * inv)
+    db = (np.floor(x.max(axis=0) * inv) - mb + 1).astype(np.int64)
+    ijk = (f - mb).astype(np.int64)
+    key = (ijk[:, 2] * db[1] + ijk[:, 1]) * db[0] + ijk[:, 0]
+    e = (f + np.float32(0.5)) * leaf - x
+    d = e[:, 0] * e[:, 0] + (e[:, 1] * e[:, 1] + e[:, 2] * e[:, 2])
+    order = np.lexsort((np.arange(len(x)), d, key))
+    first = np.ones(len(x), bool)
+    first[1:] = key[order][1:] != key[order][:-1]
+    return np.sort(order[first]).astype(np.int32)
+
+
 def canon_grid(xyz, r_feat, cpr=4):
     xyz = _xyz(xyz)
     org = np.empty(3, np.float64); cell = C.c_double(); dims = np.empty(3, np.int32)

@@ -309,6 +309,23 @@ def test_nms_draws_remove_branch(kpl, views, oracle):
     assert total > 0                                            # the cases really exercise the branch
 
 
+def test_uniform_sampling_matches_restatement(kpl, views, oracle):
+    """--subSampling (main_test_detector.cpp:145-157): one survivor per voxel, closest to the centre."""
+    d = kpl.KeypointLearningDetector()
+    for view, leaf in (("cheff001", 2.0), ("cheff001", 0.5), ("cheff002", 7.5), ("cheff000", 500.0)):
+        xyz = views[view]
+        keep = d.uniformSample(xyz, leaf)
+        ref = oracle.uniform_sample(xyz, leaf)
+        assert np.array_equal(keep, ref), (view, leaf, len(keep), len(ref))
+        vox = np.floor(xyz[keep] * (np.float32(1.0) / np.float32(leaf)))
+        assert len(np.unique(vox, axis=0)) == len(keep)                  # one survivor per voxel
+    assert len(d.uniformSample(views["cheff000"], 500.0)) <= 8
+    assert len(d.uniformSample(np.zeros((0, 3), np.float32), 1.0)) == 0
+    with pytest.raises(kpl.KplError):
+        d.uniformSample(views["cheff000"], 0.0)
+    d.close()
+
+
 def test_non_maxima_off_returns_every_point(kpl, views, oracle):
     xyz = np.ascontiguousarray(views["cheff001"][:5000])
     d = make_detector(kpl)

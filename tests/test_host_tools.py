@@ -96,26 +96,19 @@ def test_pcd_nan_and_writers(tools, tmp_path, views):
     assert subprocess.call([tools.PCD_TOOL, "dump", str(tmp_path / "missing.pcd")], stderr=subprocess.DEVNULL) == 1
 
 
-def test_uniform_sampling_stand_in(tools, tmp_path, views):
+@pytest.mark.gpu
+def test_uniform_sampling_through_the_shim(tools, tmp_path, views, oracle):
+    """pcl::UniformSampling in the shim forwards to kpl_uniform_sample (device); checked against the FP32
+    numpy restatement of PCL's filter."""
     xyz = views["cheff000"][:8000]
     p, o = str(tmp_path / "c.pcd"), str(tmp_path / "s.pcd")
     write_pcd(p, xyz, "binary")
     leaf = 2.0
     assert subprocess.call([tools.PCD_TOOL, "subsample", str(leaf), p, o]) == 0
     _, _, pts = dump(tools, o)
-    # reference semantics (pcl::UniformSampling): one point per leaf-sized voxel, the closest to its centre
-    inv = 1.0 / leaf
-    minb = np.floor(xyz.min(axis=0).astype(np.float64) * inv)
-    ijk = np.floor(xyz.astype(np.float64) * inv) - minb
-    ctr = (ijk + minb + 0.5) * leaf
-    d = ((xyz.astype(np.float64) - ctr) ** 2).sum(axis=1)
-    best = {}
-    for i, (k, di) in enumerate(zip(map(tuple, ijk), d)):
-        if k not in best or di < best[k][1]:
-            best[k] = (i, di)
-    keep = np.sort([v[0] for v in best.values()])
+    keep = oracle.uniform_sample(xyz, leaf)
     assert len(pts) == len(keep)
-    assert np.allclose(pts, xyz[keep], rtol=1e-7)
+    assert np.array_equal(pts.view(np.uint32), np.ascontiguousarray(xyz[keep]).view(np.uint32))
 
 
 def test_cli_argument_handling(tools, tmp_path):
