@@ -359,17 +359,18 @@ def run_b200(args):
                "d2h_bytes_per_step": int(n_total * 4 + world * nk_bytes // steps_e2e), "ms_per_step": e2e_ms,
                "api": "kpl_detect per view (host xyz, pinned; normals estimated on device; scores + keypoint indices copied back)"}
     elif world == 1:
-        sc_host = torch.empty(n_total, dtype=torch.float32).pin_memory().numpy()
+        sc_host = torch.empty(n_total, dtype=torch.float32).pin_memory().numpy()     # pinned result buffers, as for the input
+        kp_host = torch.empty(n_total, dtype=torch.int32).pin_memory().numpy()
         host_np = host_xyz4.numpy()
         det.setInputCloud(host_np); det.setNormals(None)
-        det.compute()                                   # warm the staging buffers
+        det.compute(scores_out=sc_host, kp_out=kp_host)   # warm the staging buffers
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize(dev)
         t0 = time.perf_counter()
         e0.record(stream)
         steps_e2e = max(1, min(args.steps, 3))
         for _ in range(steps_e2e):
-            _, idx = det.compute()
+            _, idx = det.compute(scores_out=sc_host, kp_out=kp_host)
         e1.record(stream)
         torch.cuda.synchronize(dev)
         wall = (time.perf_counter() - t0) / steps_e2e
@@ -377,7 +378,7 @@ def run_b200(args):
         e2e = {"value": n_total / (e2e_ms * 1e-3), "unit": "points/s", "h2d_bytes_per_step": int(n_total * 16),
                "d2h_bytes_per_step": int(n_total * 4 + len(idx) * 4 + 64), "ms_per_step": e2e_ms,
                "api": "kpl_detect (host xyz, pinned; normals estimated on device; scores + keypoint indices copied back)"}
-        del sc_host
+        del sc_host, kp_host
     else:
         # every step: owned slab H2D from pinned host memory, halo exchange + detection, keypoints D2H on rank 0
         steps_e2e = max(1, min(args.steps, 3))

@@ -207,7 +207,7 @@ class KeypointLearningDetector:
         return dict(ntrees=v[0].value, nnodes=v[1].value, var_count=v[2].value, max_depth=v[3].value)
 
     # ---- the hot path
-    def compute(self, role=None):
+    def compute(self, role=None, scores_out=None, kp_out=None):
         """detector->compute(*keypoint): returns (keypoints (n_kp,4) float32, indices (n_kp,) int32)."""
         if self._cloud is None:
             raise KplError(1, "no input cloud")
@@ -219,8 +219,11 @@ class KeypointLearningDetector:
             if nrm.shape[0] != n:
                 raise KplError(3, "normals given, but the number of normals does not match the number of input points")
         self._push()
-        scores = np.empty(n, np.float32)
-        kp = np.empty(max(n, 1), np.int32)
+        # caller-provided result buffers (e.g. pinned host memory) are used as they are
+        scores = np.empty(n, np.float32) if scores_out is None else scores_out
+        kp = np.empty(max(n, 1), np.int32) if kp_out is None else kp_out
+        if scores.dtype != np.float32 or scores.size < n or kp.dtype != np.int32 or kp.size < max(n, 1):
+            raise KplError(1, "scores_out / kp_out must be float32[n] / int32[n]")
         nkp = C.c_int64(0)
         r = None if role is None else np.ascontiguousarray(role, np.uint8)
         self._check(self._L.kpl_detect(self._h, _ptr(xyz, C.c_float), xs, _ptr(nrm, C.c_float), ns or 0, _ptr(r, C.c_uint8), n,

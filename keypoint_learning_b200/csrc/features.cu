@@ -28,6 +28,7 @@
 #include "kpl_internal.h"
 #include "kpl_math.cuh"
 #include "forest.cuh"
+#include <cub/device/device_scan.cuh>
 
 namespace kpl {
 
@@ -246,7 +247,7 @@ __device__ __forceinline__ void vote4(unsigned hb, unsigned row_bytes, int a, in
 template <bool FAST>
 __global__ void __launch_bounds__(FEAT_WARPS * 32)
 feature_kernel(const float4* __restrict__ s_pos, const float4* __restrict__ s_nrm, const uint32_t* __restrict__ skey,
-               const int32_t* __restrict__ cell_start, const uint8_t* __restrict__ s_role,
+               const int32_t* __restrict__ cell_start, const uint8_t* __restrict__ s_role, const int2* __restrict__ work, int nwarps,
                int dimx, int dimy, int dimz, FeatParams P, FusedForest FF, float* __restrict__ feat,
                unsigned long long* __restrict__ counters)
 {
@@ -257,16 +258,18 @@ feature_kernel(const float4* __restrict__ s_pos, const float4* __restrict__ s_nr
     float* sx = hist + P.F * 32;                                  // SoA candidate tile: x, y, z, nx, ny, nz
     float* sy = sx + 32; float* sz = sy + 32; float* snx = sz + 32; float* sny = snx + 32; float* snz = sny + 32;
 
-    const int q0 = (blockIdx.x * (blockDim.x >> 5) + warp) * 32;
-    if (q0 >= P.n) return;
+    const int w = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (w >= nwarps) return;
+    const int2 item = __ldg(work + w);                       // up to 32 consecutive sorted points of one run
+    const int q0 = item.x, nvalid = item.y;
     const int q = q0 + lane;
-    bool active = q < P.n;
+    const bool valid = lane < nvalid;
+    bool active = valid;
     if (active && s_role) active = (s_role[q] & 1) != 0;
     if (!__any_sync(0xFFFFFFFFu, active)) {
-        const int nvalid = min(32, P.n - q0);
         if (feat)
             for (int e = lane; e < nvalid * P.F; e += 32) feat[(int64_t)q0 * P.F + e] = 0.0f;
-        if (FF.nodes && q < P.n) {
+        if (FF.nodes && valid) {
             FF.s_score[q] = CUDART_NAN_F;
             FF.score[__float_as_uint(__ldg(&s_pos[q].w))] = CUDART_NAN_F;
         }
@@ -467,14 +470,13 @@ feature_kernel(const float4* __restrict__ s_pos, const float4* __restrict__ s_nr
     // fused forest: score = 1 - sum/ntrees (hpp:281-287); unscored points (halo role, no finite normal) get NaN
     if (FF.nodes) {
         const float sc = active ? forest_score(hist + lane, 32, FF.nodes, FF.roots, FF.ntrees) : CUDART_NAN_F;
-        if (q < P.n) {
+        if (valid) {
             FF.s_score[q] = sc;
             FF.score[__float_as_uint(__ldg(&s_pos[q].w))] = sc;
         }
     }
     // coalesced store of the warp's 32 rows (row-major, sorted order)
     if (feat) {
-        const int nvalid = min(32, P.n - q0);
         const int total = nvalid * P.F;
         float* dst = feat + (int64_t)q0 * P.F;
         for (int e = lane; e < total; e += 32) {
@@ -487,6 +489,70 @@ feature_kernel(const float4* __restrict__ s_pos, const float4* __restrict__ s_nr
         atomicAdd(counters + 0, (unsigned long long)npairs);
         atomicAdd(counters + 1, (unsigned long long)ncand * 32ull);
     }
+}
+
+// ---- warp work list --------------------------------------------------------------------------------
+// A warp works best when its 32 queries share one cell row and span few cells in x: then they form ONE
+// group and no lane idles while another group is processed.  Consecutive sorted points do not have that
+// property (a closed surface crosses a cell row in several separate places), so the queries are cut into
+// runs -- maximal stretches of one row spanning at most span + 1 cells -- and every warp gets up to 32
+// consecutive points of one run: work[w] = (first sorted position, count).  One thread walks one row.
+template <bool FILL>
+__global__ void __launch_bounds__(128) run_list_kernel(const int32_t* __restrict__ cell_start, int dimx, int64_t nrows, int span,
+                                                       int32_t* __restrict__ row_warps, const int32_t* __restrict__ row_offset,
+                                                       int2* __restrict__ work)
+{
+    const int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (row >= nrows) return;
+    const int32_t* cs = cell_start + row * dimx;
+    int warps = 0;
+    int out = FILL ? row_offset[row] : 0;
+    int run_x = -1, run_s = 0, run_e = 0;
+    auto close_run = [&]() {
+        for (int s = run_s; s < run_e; s += 32) {
+            if (FILL) work[out++] = make_int2(s, min(32, run_e - s));
+            ++warps;
+        }
+    };
+    int prev = __ldg(cs);
+    for (int x = 0; x < dimx; ++x) {
+        const int next = __ldg(cs + x + 1);
+        if (next > prev) {                                   // cell x holds points [prev, next)
+            if (run_x < 0 || x - run_x > span) {
+                if (run_x >= 0) close_run();
+                run_x = x; run_s = prev;
+            }
+            run_e = next;
+        }
+        prev = next;
+    }
+    if (run_x >= 0) close_run();
+    if (!FILL) row_warps[row] = warps;
+}
+
+// Builds c->work (device) for the current grid and returns the number of warps.
+static cudaError_t build_work_list(kpl_ctx* c, int span, int& nwarps)
+{
+    const GridDesc& g = c->grid;
+    const int64_t nrows = (int64_t)g.dim[1] * g.dim[2];
+    cudaError_t e;
+    if ((e = ensure(c->row_warps, (size_t)nrows + 1)) || (e = ensure(c->row_offset, (size_t)nrows + 1))) return e;
+    const unsigned blocks = (unsigned)((nrows + 127) / 128);
+    run_list_kernel<false><<<blocks, 128, 0, c->stream>>>(c->cell_start.p, g.dim[0], nrows, span, c->row_warps.p, nullptr, nullptr);
+    size_t bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, bytes, c->row_warps.p, c->row_offset.p, (int)nrows + 1, c->stream);
+    if ((e = ensure(c->cub_tmp, bytes))) return e;
+    bytes = c->cub_tmp.cap;
+    if ((e = cudaMemsetAsync(c->row_warps.p + nrows, 0, sizeof(int32_t), c->stream))) return e;
+    if ((e = cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, bytes, c->row_warps.p, c->row_offset.p, (int)nrows + 1, c->stream))) return e;
+    int32_t total = 0;
+    if ((e = cudaMemcpyAsync(&total, c->row_offset.p + nrows, sizeof total, cudaMemcpyDeviceToHost, c->stream))) return e;
+    if ((e = cudaStreamSynchronize(c->stream))) return e;
+    if ((e = ensure(c->work, (size_t)total + 1))) return e;
+    run_list_kernel<true><<<blocks, 128, 0, c->stream>>>(c->cell_start.p, g.dim[0], nrows, span, nullptr, c->row_offset.p, c->work.p);
+    c->launches += 4;
+    nwarps = total;
+    return cudaGetLastError();
 }
 
 // Runs the exhaustive self-test once per (adim, bdim) pair and caches the verdict.
@@ -524,7 +590,7 @@ cudaError_t launch_features(kpl_ctx* c, int64_t n, bool use_role, bool fuse_fore
     const kpl_params& U = c->params;
     FeatParams P;
     P.n = (int)n; P.A = U.n_annulus; P.B = U.n_bins; P.F = P.A * P.B; P.reach = c->grid.reach_feat;
-    P.span = (U.cells_per_radius + 1) / 2;      // measured on the 1 M-point view: 2 at 4 cells per radius (gpurun_out/sweep1.log)
+    P.span = U.cells_per_radius;                // cells a warp's run may span in x beyond its first: 1/2/3/4 measured 197/192/190/189 ms (10 M points)
     if (const char* e = getenv("KPL_FEAT_SPAN")) P.span = atoi(e);   // tuning experiments only
     const double r = (double)U.radius_features;
     P.r2 = (float)(r * r);                       // static_cast<float>(radius*radius), KdTreeFLANN::radiusSearch
@@ -558,10 +624,12 @@ cudaError_t launch_features(kpl_ctx* c, int64_t n, bool use_role, bool fuse_fore
     auto kern = fast ? feature_kernel<true> : feature_kernel<false>;
     // per device and per process state of the runtime: set it on every launch that needs it (a host-side call)
     if (smem > 48 * 1024 && (e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return e;
-    int warps = (int)((n + 31) / 32);
+    int warps = 0;
+    if ((e = build_work_list(c, P.span, warps))) return e;
+    if (warps == 0) return cudaSuccess;
     int blocks = (warps + wpb - 1) / wpb;
     kern<<<blocks, wpb * 32, smem, c->stream>>>(c->s_pos.p, c->s_nrm.p, c->key_b.p, c->cell_start.p,
-                                                       use_role ? c->s_role.p : nullptr,
+                                                       use_role ? c->s_role.p : nullptr, c->work.p, warps,
                                                        c->grid.dim[0], c->grid.dim[1], c->grid.dim[2], P, FF,
                                                        store_rows ? c->feat.p : nullptr, c->counters.p);
     c->launches++;

@@ -73,6 +73,8 @@ struct kpl_ctx {
     kpl::DevBuf<uint32_t> key_a, key_b, idx_a, idx_b;
     kpl::DevBuf<uint8_t> cub_tmp;
     kpl::DevBuf<int32_t> cell_start;
+    kpl::DevBuf<int32_t> row_warps, row_offset;   // feature-kernel work list: warps per cell row and their prefix sum
+    kpl::DevBuf<int2> work;                       // (first sorted position, count <= 32) per warp
     kpl::DevBuf<float4> s_pos, s_nrm;            // cell-sorted positions (w = original index bits) / normals
     kpl::DevBuf<float> feat;                     // n x F, sorted order
     kpl::DevBuf<float> s_score, score;           // sorted order / original order
