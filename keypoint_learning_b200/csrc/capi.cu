@@ -98,7 +98,7 @@ void kpl_destroy(kpl_ctx* ctx)
     if (ctx->own_stream) cudaStreamSynchronize(ctx->own_stream);
     release(ctx->in_xyz); release(ctx->in_nrm); release(ctx->in_role); release(ctx->s_role);
     release(ctx->key_a); release(ctx->key_b); release(ctx->idx_a); release(ctx->idx_b); release(ctx->cub_tmp);
-    release(ctx->cell_start); release(ctx->row_warps); release(ctx->row_offset); release(ctx->work); release(ctx->s_pos); release(ctx->s_nrm); release(ctx->feat);
+    release(ctx->cell_start); release(ctx->row_warps); release(ctx->row_offset); release(ctx->work); release(ctx->work_n); release(ctx->s_pos); release(ctx->s_nrm); release(ctx->feat);
     release(ctx->s_score); release(ctx->score); release(ctx->flag); release(ctx->s_state); release(ctx->kp_idx);
     release(ctx->scratch_f); release(ctx->scratch_i); release(ctx->counters);
     if (ctx->d_bbox) cudaFree(ctx->d_bbox);

@@ -28,7 +28,6 @@
 #include "kpl_internal.h"
 #include "kpl_math.cuh"
 #include "forest.cuh"
-#include <cub/device/device_scan.cuh>
 
 namespace kpl {
 
@@ -491,70 +490,6 @@ feature_kernel(const float4* __restrict__ s_pos, const float4* __restrict__ s_nr
     }
 }
 
-// ---- warp work list --------------------------------------------------------------------------------
-// A warp works best when its 32 queries share one cell row and span few cells in x: then they form ONE
-// group and no lane idles while another group is processed.  Consecutive sorted points do not have that
-// property (a closed surface crosses a cell row in several separate places), so the queries are cut into
-// runs -- maximal stretches of one row spanning at most span + 1 cells -- and every warp gets up to 32
-// consecutive points of one run: work[w] = (first sorted position, count).  One thread walks one row.
-template <bool FILL>
-__global__ void __launch_bounds__(128) run_list_kernel(const int32_t* __restrict__ cell_start, int dimx, int64_t nrows, int span,
-                                                       int32_t* __restrict__ row_warps, const int32_t* __restrict__ row_offset,
-                                                       int2* __restrict__ work)
-{
-    const int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (row >= nrows) return;
-    const int32_t* cs = cell_start + row * dimx;
-    int warps = 0;
-    int out = FILL ? row_offset[row] : 0;
-    int run_x = -1, run_s = 0, run_e = 0;
-    auto close_run = [&]() {
-        for (int s = run_s; s < run_e; s += 32) {
-            if (FILL) work[out++] = make_int2(s, min(32, run_e - s));
-            ++warps;
-        }
-    };
-    int prev = __ldg(cs);
-    for (int x = 0; x < dimx; ++x) {
-        const int next = __ldg(cs + x + 1);
-        if (next > prev) {                                   // cell x holds points [prev, next)
-            if (run_x < 0 || x - run_x > span) {
-                if (run_x >= 0) close_run();
-                run_x = x; run_s = prev;
-            }
-            run_e = next;
-        }
-        prev = next;
-    }
-    if (run_x >= 0) close_run();
-    if (!FILL) row_warps[row] = warps;
-}
-
-// Builds c->work (device) for the current grid and returns the number of warps.
-static cudaError_t build_work_list(kpl_ctx* c, int span, int& nwarps)
-{
-    const GridDesc& g = c->grid;
-    const int64_t nrows = (int64_t)g.dim[1] * g.dim[2];
-    cudaError_t e;
-    if ((e = ensure(c->row_warps, (size_t)nrows + 1)) || (e = ensure(c->row_offset, (size_t)nrows + 1))) return e;
-    const unsigned blocks = (unsigned)((nrows + 127) / 128);
-    run_list_kernel<false><<<blocks, 128, 0, c->stream>>>(c->cell_start.p, g.dim[0], nrows, span, c->row_warps.p, nullptr, nullptr);
-    size_t bytes = 0;
-    cub::DeviceScan::ExclusiveSum(nullptr, bytes, c->row_warps.p, c->row_offset.p, (int)nrows + 1, c->stream);
-    if ((e = ensure(c->cub_tmp, bytes))) return e;
-    bytes = c->cub_tmp.cap;
-    if ((e = cudaMemsetAsync(c->row_warps.p + nrows, 0, sizeof(int32_t), c->stream))) return e;
-    if ((e = cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, bytes, c->row_warps.p, c->row_offset.p, (int)nrows + 1, c->stream))) return e;
-    int32_t total = 0;
-    if ((e = cudaMemcpyAsync(&total, c->row_offset.p + nrows, sizeof total, cudaMemcpyDeviceToHost, c->stream))) return e;
-    if ((e = cudaStreamSynchronize(c->stream))) return e;
-    if ((e = ensure(c->work, (size_t)total + 1))) return e;
-    run_list_kernel<true><<<blocks, 128, 0, c->stream>>>(c->cell_start.p, g.dim[0], nrows, span, nullptr, c->row_offset.p, c->work.p);
-    c->launches += 4;
-    nwarps = total;
-    return cudaGetLastError();
-}
-
 // Runs the exhaustive self-test once per (adim, bdim) pair and caches the verdict.
 static cudaError_t fast_math_verdict(kpl_ctx* c, const FeatParams& P, bool& fast)
 {
@@ -625,7 +560,7 @@ cudaError_t launch_features(kpl_ctx* c, int64_t n, bool use_role, bool fuse_fore
     // per device and per process state of the runtime: set it on every launch that needs it (a host-side call)
     if (smem > 48 * 1024 && (e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return e;
     int warps = 0;
-    if ((e = build_work_list(c, P.span, warps))) return e;
+    if ((e = build_work_list(c, P.span, c->work, warps))) return e;
     if (warps == 0) return cudaSuccess;
     int blocks = (warps + wpb - 1) / wpb;
     kern<<<blocks, wpb * 32, smem, c->stream>>>(c->s_pos.p, c->s_nrm.p, c->key_b.p, c->cell_start.p,

@@ -74,7 +74,7 @@ struct kpl_ctx {
     kpl::DevBuf<uint8_t> cub_tmp;
     kpl::DevBuf<int32_t> cell_start;
     kpl::DevBuf<int32_t> row_warps, row_offset;   // feature-kernel work list: warps per cell row and their prefix sum
-    kpl::DevBuf<int2> work;                       // (first sorted position, count <= 32) per warp
+    kpl::DevBuf<int2> work, work_n;               // (first sorted position, count <= 32) per warp: feature / normal kernels
     kpl::DevBuf<float4> s_pos, s_nrm;            // cell-sorted positions (w = original index bits) / normals
     kpl::DevBuf<float> feat;                     // n x F, sorted order
     kpl::DevBuf<float> s_score, score;           // sorted order / original order
@@ -109,6 +109,7 @@ cudaError_t launch_forest(kpl_ctx* c, int64_t n, bool use_role);
 cudaError_t launch_nms(kpl_ctx* c, int64_t n, bool use_role);
 cudaError_t launch_nms_draws(kpl_ctx* c, int64_t n, bool use_role);
 cudaError_t launch_compact(kpl_ctx* c, int64_t n, int32_t* d_kp_idx_out);
+cudaError_t build_work_list(kpl_ctx* c, int span, DevBuf<int2>& work, int& nwarps);
 cudaError_t uniform_sample(kpl_ctx* c, const float4* xyz, int64_t n, float leaf, const float mn[3], const float mx[3],
                            int32_t* d_idx_out, std::string& err);
 cudaError_t launch_radius_stats(kpl_ctx* c, int64_t n, double radius, int32_t* d_counts, unsigned long long* d_hash);

@@ -172,17 +172,16 @@ __global__ void __launch_bounds__(128) normals_knn_kernel(const float4* __restri
 template <int K>
 __global__ void __launch_bounds__(32) normals_knn_coop_kernel(const float4* __restrict__ s_pos, const uint32_t* __restrict__ skey,
                                                               const int32_t* __restrict__ cell_start, const float4* __restrict__ xyz,
-                                                              GridDesc g, int n, uint64_t one2, float vpx, float vpy, float vpz,
-                                                              float4* __restrict__ s_nrm)
+                                                              GridDesc g, const int2* __restrict__ work, uint64_t one2,
+                                                              float vpx, float vpy, float vpz, float4* __restrict__ s_nrm)
 {
     __shared__ __align__(16) float tile[128];
     float* sx = tile; float* sy = tile + 32; float* sz = tile + 64;
     uint32_t* si = reinterpret_cast<uint32_t*>(tile + 96);
     const int lane = threadIdx.x;
-    const int q0 = blockIdx.x * 32;
-    if (q0 >= n) return;
-    const int q = q0 + lane;
-    const bool active = q < n;
+    const int2 item = __ldg(work + blockIdx.x);              // up to 32 consecutive sorted points of one run (grid.cu)
+    const int q = item.x + lane;
+    const bool active = lane < item.y;
     float4 p = make_float4(CUDART_NAN_F, 0.f, 0.f, 0.f);
     int cx = 0, cy = 0, cz = 0;
     if (active) { p = __ldg(s_pos + q); key_to_cell(__ldg(skey + q), g, cx, cy, cz); }
@@ -345,10 +344,15 @@ cudaError_t launch_normals_knn(kpl_ctx* c, int64_t n)
     const kpl_params& P = c->params;
     int blocks = (int)((n + 127) / 128);
     const float4* xyz = c->cur_xyz;
-    if (P.k_normals == 10 && !getenv("KPL_NORMALS_PER_THREAD"))
-        normals_knn_coop_kernel<10><<<(unsigned)((n + 31) / 32), 32, 0, c->stream>>>(c->s_pos.p, c->key_b.p, c->cell_start.p, xyz, c->grid, (int)n,
-                                                                                      0x3F8000003F800000ull, P.viewpoint[0], P.viewpoint[1],
-                                                                                      P.viewpoint[2], c->s_nrm.p);
+    if (P.k_normals == 10 && !getenv("KPL_NORMALS_PER_THREAD")) {
+        int warps = 0;
+        cudaError_t e = build_work_list(c, 1, c->work_n, warps);      // runs of at most two cells: one group per warp
+        if (e) return e;
+        if (warps > 0)
+            normals_knn_coop_kernel<10><<<(unsigned)warps, 32, 0, c->stream>>>(c->s_pos.p, c->key_b.p, c->cell_start.p, xyz, c->grid, c->work_n.p,
+                                                                                0x3F8000003F800000ull, P.viewpoint[0], P.viewpoint[1],
+                                                                                P.viewpoint[2], c->s_nrm.p);
+    }
     else if (P.k_normals == 10)
         normals_knn_kernel<10><<<blocks, 128, 0, c->stream>>>(c->s_pos.p, c->key_b.p, c->cell_start.p, xyz, c->grid, (int)n, 10,
                                                                P.viewpoint[0], P.viewpoint[1], P.viewpoint[2], c->s_nrm.p);
@@ -415,15 +419,14 @@ struct NormRadParams {
 
 __global__ void __launch_bounds__(32)
 normals_radius_kernel(const float4* __restrict__ s_pos, const uint32_t* __restrict__ skey, const int32_t* __restrict__ cell_start,
-                      int dimx, int dimy, int dimz, NormRadParams P, float4* __restrict__ s_nrm)
+                      const int2* __restrict__ work, int dimx, int dimy, int dimz, NormRadParams P, float4* __restrict__ s_nrm)
 {
     __shared__ __align__(16) float tile[96];
     float* sx = tile; float* sy = tile + 32; float* sz = tile + 64;
     const int lane = threadIdx.x;
-    const int q0 = blockIdx.x * 32;
-    if (q0 >= P.n) return;
-    const int q = q0 + lane;
-    const bool active = q < P.n;
+    const int2 item = __ldg(work + blockIdx.x);              // up to 32 consecutive sorted points of one run (grid.cu)
+    const int q = item.x + lane;
+    const bool active = lane < item.y;
     float4 qp = make_float4(CUDART_NAN_F, 0.f, 0.f, 0.f);
     int cx = 0, cy = 0, cz = 0;
     if (active) {
@@ -543,14 +546,18 @@ cudaError_t launch_normals_radius(kpl_ctx* c, int64_t n)
     const kpl_params& U = c->params;
     NormRadParams P;
     const double r = (double)U.radius_features;
-    P.n = (int)n; P.reach = c->grid.reach_feat; P.span = (U.cells_per_radius + 1) / 2;
+    P.n = (int)n; P.reach = c->grid.reach_feat; P.span = U.cells_per_radius;
     P.r2 = (float)(r * r);                         // static_cast<float>(radius*radius), KdTreeFLANN::radiusSearch
     P.cellf = (float)c->grid.cell;
     P.rcull2 = (float)(r * r * (1.0 + 1e-5));
     P.vpx = U.viewpoint[0]; P.vpy = U.viewpoint[1]; P.vpz = U.viewpoint[2];
     P.one2 = 0x3F8000003F800000ull;
-    normals_radius_kernel<<<(unsigned)((n + 31) / 32), 32, 0, c->stream>>>(c->s_pos.p, c->key_b.p, c->cell_start.p,
-                                                                          c->grid.dim[0], c->grid.dim[1], c->grid.dim[2], P, c->s_nrm.p);
+    int warps = 0;
+    cudaError_t e = build_work_list(c, P.span, c->work_n, warps);
+    if (e) return e;
+    if (warps > 0)
+        normals_radius_kernel<<<(unsigned)warps, 32, 0, c->stream>>>(c->s_pos.p, c->key_b.p, c->cell_start.p, c->work_n.p,
+                                                                    c->grid.dim[0], c->grid.dim[1], c->grid.dim[2], P, c->s_nrm.p);
     c->launches++;
     return cudaGetLastError();
 }
