@@ -161,6 +161,24 @@ __global__ void __launch_bounds__(128) normals_knn_kernel(const float4* __restri
     s_nrm[i] = normal_from_moments(accu, cnt, p.x, p.y, p.z, vpx, vpy, vpz);
 }
 
+// Branch-free insertion into a list kept sorted by the 64-bit key (d2 bits, index): for d2 >= 0 the IEEE bit
+// pattern orders like the value, so the unsigned key order IS the (d2, index) order of the sorted search.
+// Every slot is rewritten with selects; a candidate that is not smaller than the last slot changes nothing.
+template <int K>
+__device__ __forceinline__ void knn_insert(uint32_t (&hi)[K], uint32_t (&lo)[K], uint32_t chi, uint32_t clo)
+{
+    bool lt_prev = false;
+    uint32_t phi = 0u, plo = 0u;
+#pragma unroll
+    for (int t = 0; t < K; ++t) {
+        const uint32_t ohi = hi[t], olo = lo[t];
+        const bool lt = chi < ohi || (chi == ohi && clo < olo);
+        hi[t] = lt_prev ? phi : (lt ? chi : ohi);
+        lo[t] = lt_prev ? plo : (lt ? clo : olo);
+        lt_prev = lt; phi = ohi; plo = olo;
+    }
+}
+
 // Warp-cooperative form of the k = 10 search (the TestDetector setting).  The per-thread kernel above spends
 // most of its issue slots on idle lanes (ncu: 7.75 of 32 threads active per instruction) because every
 // lane walks its own cell ranges.  Here a warp owns 32 consecutive sorted points; lanes that share a cell
@@ -185,10 +203,10 @@ __global__ void __launch_bounds__(32) normals_knn_coop_kernel(const float4* __re
     float4 p = make_float4(CUDART_NAN_F, 0.f, 0.f, 0.f);
     int cx = 0, cy = 0, cz = 0;
     if (active) { p = __ldg(s_pos + q); key_to_cell(__ldg(skey + q), g, cx, cy, cz); }
-    float bd2[K];
+    uint32_t bd2[K];          // bit patterns of the k smallest squared distances, ascending by (d2, index)
     uint32_t bi[K];
 #pragma unroll
-    for (int t = 0; t < K; ++t) { bd2[t] = CUDART_INF_F; bi[t] = 0xFFFFFFFFu; }
+    for (int t = 0; t < K; ++t) { bd2[t] = 0x7F800000u; bi[t] = 0xFFFFFFFFu; }   // +inf, no index
     const uint64_t QY = pack2(p.y, p.y), QZ = pack2(p.z, p.z);
 
     // squared lower bounds on the distance to the neighbouring cell layer on the low / high side of y and z
@@ -225,7 +243,7 @@ __global__ void __launch_bounds__(32) normals_knn_coop_kernel(const float4* __re
             const int y = gy0 + dy, z = gz0 + dz;
             if (y < 0 || y >= g.dim[1] || z < 0 || z >= g.dim[2]) continue;
             const float gap2 = (dy < 0 ? lo2[1] : (dy > 0 ? hi2[1] : 0.0f)) + (dz < 0 ? lo2[2] : (dz > 0 ? hi2[2] : 0.0f));
-            if (!__any_sync(0xFFFFFFFFu, member && gap2 <= bd2[K - 1])) continue;     // no member can use this row
+            if (!__any_sync(0xFFFFFFFFu, member && gap2 <= __uint_as_float(bd2[K - 1]))) continue;     // no member can use this row
             const int64_t base = ((int64_t)z * g.dim[1] + y) * g.dim[0];
             const int rs = __ldg(cell_start + base + xa), re = __ldg(cell_start + base + xb + 1);
             for (int tb = rs; tb < re; tb += 32) {
@@ -235,7 +253,7 @@ __global__ void __launch_bounds__(32) normals_knn_coop_kernel(const float4* __re
                 sx[lane] = c.x; sy[lane] = c.y; sz[lane] = c.z; si[lane] = __float_as_uint(c.w);
                 __syncwarp();
                 const int cnt = min(32, re - tb);
-                const float worst = bd2[K - 1];
+                const float worst = __uint_as_float(bd2[K - 1]);
                 uint32_t mask = 0;
 #pragma unroll
                 for (int k0 = 0; k0 < 32; k0 += 8) {
@@ -260,16 +278,7 @@ __global__ void __launch_bounds__(32) normals_knn_coop_kernel(const float4* __re
                     mask ^= 1u << m;
                     const int k = 31 - m;
                     const float d2 = dist2(p.x, p.y, p.z, sx[k], sy[k], sz[k]);
-                    const uint32_t oi = si[k];
-                    if (less_d2_idx(d2, oi, bd2[K - 1], bi[K - 1])) {
-#pragma unroll
-                        for (int t = K - 1; t >= 0; --t) {
-                            const float pd = (t > 0) ? bd2[t > 0 ? t - 1 : 0] : -CUDART_INF_F;
-                            const uint32_t pi = (t > 0) ? bi[t > 0 ? t - 1 : 0] : 0u;
-                            if (less_d2_idx(d2, oi, pd, pi)) { bd2[t] = pd; bi[t] = pi; }
-                            else if (less_d2_idx(d2, oi, bd2[t], bi[t])) { bd2[t] = d2; bi[t] = oi; }
-                        }
-                    }
+                    knn_insert<K>(bd2, bi, __float_as_uint(d2), si[k]);
                 }
             }
         }
@@ -280,7 +289,7 @@ __global__ void __launch_bounds__(32) normals_knn_coop_kernel(const float4* __re
         const bool all1 = (cz - 1 <= 0 && cy - 1 <= 0 && cx - 1 <= 0 && cz + 1 >= g.dim[2] - 1 && cy + 1 >= g.dim[1] - 1 && cx + 1 >= g.dim[0] - 1);
         double guard = g.cell;
         guard = guard * guard * (1.0 - 1e-6);
-        const bool exact = all1 || (bd2[K - 1] < CUDART_INF_F && (double)bd2[K - 1] < guard);
+        const bool exact = all1 || (bd2[K - 1] < 0x7F800000u && (double)__uint_as_float(bd2[K - 1]) < guard);
         if (!exact) {
             const int maxdim = max(g.dim[0], max(g.dim[1], g.dim[2]));
             for (int R = 2; R <= maxdim; ++R) {
@@ -288,7 +297,7 @@ __global__ void __launch_bounds__(32) normals_knn_coop_kernel(const float4* __re
                 const int y0 = max(cy - R, 0), y1 = min(cy + R, g.dim[1] - 1);
                 const int x0 = max(cx - R, 0), x1 = min(cx + R, g.dim[0] - 1);
 #pragma unroll
-                for (int t = 0; t < K; ++t) { bd2[t] = CUDART_INF_F; bi[t] = 0xFFFFFFFFu; }
+                for (int t = 0; t < K; ++t) { bd2[t] = 0x7F800000u; bi[t] = 0xFFFFFFFFu; }
                 for (int z = z0; z <= z1; ++z)
                     for (int y = y0; y <= y1; ++y) {
                         const int64_t base = ((int64_t)z * g.dim[1] + y) * g.dim[0];
@@ -296,23 +305,14 @@ __global__ void __launch_bounds__(32) normals_knn_coop_kernel(const float4* __re
                         for (int j = s; j < e; ++j) {
                             const float4 c = __ldg(s_pos + j);
                             const float d2 = dist2(p.x, p.y, p.z, c.x, c.y, c.z);
-                            const uint32_t oi = __float_as_uint(c.w);
-                            if (less_d2_idx(d2, oi, bd2[K - 1], bi[K - 1])) {
-#pragma unroll
-                                for (int t = K - 1; t >= 0; --t) {
-                                    const float pd = (t > 0) ? bd2[t > 0 ? t - 1 : 0] : -CUDART_INF_F;
-                                    const uint32_t pi = (t > 0) ? bi[t > 0 ? t - 1 : 0] : 0u;
-                                    if (less_d2_idx(d2, oi, pd, pi)) { bd2[t] = pd; bi[t] = pi; }
-                                    else if (less_d2_idx(d2, oi, bd2[t], bi[t])) { bd2[t] = d2; bi[t] = oi; }
-                                }
-                            }
+                            if (d2 <= __uint_as_float(bd2[K - 1])) knn_insert<K>(bd2, bi, __float_as_uint(d2), __float_as_uint(c.w));
                         }
                     }
                 if (z0 == 0 && y0 == 0 && x0 == 0 && z1 == g.dim[2] - 1 && y1 == g.dim[1] - 1 && x1 == g.dim[0] - 1) break;
-                if (bd2[K - 1] < CUDART_INF_F) {
+                if (bd2[K - 1] < 0x7F800000u) {
                     double gr = (double)R * g.cell;
                     gr = gr * gr * (1.0 - 1e-6);
-                    if ((double)bd2[K - 1] < gr) break;
+                    if ((double)__uint_as_float(bd2[K - 1]) < gr) break;
                 }
             }
         }
