@@ -433,7 +433,7 @@ def run_b200(args):
                            "parallelism": ("views-dp%d" % world) if views else ("slab%d+halo" % world if world > 1 else "single"),
                            "l2": "inputs and intermediates of a step (%.0f MB) exceed the 126 MB L2; no flush needed" % (n_total / world * (16 + 16 + 16 + 16 + 16) / 1e6)},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
-                "keypoints": int(nkp), "n_points": n_total, "points_per_rank": n_local, "per_rank": per_rank}
+                "keypoints": int(nkp), "near_threshold_points": int(st["n_near_threshold"]), "n_points": n_total, "points_per_rank": n_local, "per_rank": per_rank}
         print(json.dumps(line), flush=True)
     if views:
         for d_ in dets[1:]:

@@ -97,6 +97,8 @@ typedef struct kpl_stats {
     int32_t fast_math;        /* 1: the self-tested FMA-corrected sqrt/div sequences were used (bit-identical) */
     int32_t reserved;
     int64_t n_unscored;       /* points without a finite normal: score NaN, never a keypoint (hpp:277)        */
+    int64_t n_near_threshold; /* scored points with |score - threshold| <= 1e-5: the decisions a 1e-5 score
+                                 difference against another implementation could flip                         */
 } kpl_stats;
 
 /* ---- lifetime ------------------------------------------------------------------------------- */

@@ -320,6 +320,7 @@ static int run_detect(kpl_ctx* ctx, const float4* d_xyz, const float4* d_nrm, co
     kpl_stats& S = ctx->stats;
     S.feature_pairs = (int64_t)hc[0]; S.candidate_pairs = (int64_t)hc[1]; S.n_above_threshold = (int64_t)hc[2];
     S.n_keypoints = nkp; S.kernel_launches = ctx->launches; S.n_scored = n; S.n_unscored = (int64_t)hc[4]; S.fast_math = ctx->fast_math ? 1 : 0;
+    S.n_near_threshold = (int64_t)hc[7];
     return KPL_OK;
 }
 

@@ -83,7 +83,7 @@ struct kpl_ctx {
     kpl::DevBuf<int32_t> kp_idx;
     kpl::DevBuf<float> scratch_f;                // fetch / reorder scratch
     kpl::DevBuf<int32_t> scratch_i;
-    kpl::DevBuf<unsigned long long> counters;    // [0] feature pairs [1] candidate pairs [2] above th [3] n_kp [4] nonfinite flag [5] scored
+    kpl::DevBuf<unsigned long long> counters;    // [0] feature pairs [1] candidate pairs [2] above th [3] n_kp [4] unscored [5] scored [6] scratch [7] near threshold
     const float4* cur_xyz = nullptr;             // original-order inputs of the call in flight (device)
     const float4* cur_nrm = nullptr;
     float* d_bbox = nullptr;                     // 6 ordered-int encoded floats + flags

@@ -24,13 +24,14 @@ nms_kernel(const float4* __restrict__ s_pos, const float* __restrict__ s_score, 
            int n, float rn2, int reach, double th, uint8_t* __restrict__ flag, unsigned long long* __restrict__ counters)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    bool above = false;
+    bool above = false, near = false;
     if (i < n) {
         const float4 p = __ldg(s_pos + i);
         const uint32_t orig = __float_as_uint(p.w);
         const float my = __ldg(s_score + i);
         const bool owned = !s_role || ((s_role[i] & 3) == 3);
         above = owned && isfinite(my) && !((double)my < th);
+        near = owned && isfinite(my) && fabs((double)my - th) <= 1e-5;
         bool is_max = above;
         if (above) {
             int cx, cy, cz;
@@ -52,6 +53,8 @@ nms_kernel(const float4* __restrict__ s_pos, const float* __restrict__ s_score, 
     }
     unsigned m = __ballot_sync(0xFFFFFFFFu, above);
     if ((threadIdx.x & 31) == 0 && m) atomicAdd(counters + 2, (unsigned long long)__popc(m));
+    m = __ballot_sync(0xFFFFFFFFu, near);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(counters + 7, (unsigned long long)__popc(m));
 }
 
 cudaError_t launch_nms(kpl_ctx* c, int64_t n, bool use_role)
@@ -97,7 +100,7 @@ nms_draws_kernel(const float4* __restrict__ s_pos, const float* __restrict__ s_s
                  unsigned long long* __restrict__ counters)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    bool above = false;
+    bool above = false, near = false;
     if (i < n) {
         const float4 p = __ldg(s_pos + i);
         const uint32_t orig = __float_as_uint(p.w);
@@ -105,6 +108,7 @@ nms_draws_kernel(const float4* __restrict__ s_pos, const float* __restrict__ s_s
         if (PASS == 0) {
             const bool owned = !s_role || ((s_role[i] & 3) == 3);
             above = owned && isfinite(my) && !((double)my < th);
+            near = owned && isfinite(my) && fabs((double)my - th) <= 1e-5;
         }
         const bool work = PASS == 0 ? above : (s_state[i] == 2);
         if (work) {
@@ -147,6 +151,8 @@ nms_draws_kernel(const float4* __restrict__ s_pos, const float* __restrict__ s_s
     if (PASS == 0) {
         unsigned m = __ballot_sync(0xFFFFFFFFu, above);
         if ((threadIdx.x & 31) == 0 && m) atomicAdd(counters + 2, (unsigned long long)__popc(m));
+        m = __ballot_sync(0xFFFFFFFFu, near);
+        if ((threadIdx.x & 31) == 0 && m) atomicAdd(counters + 7, (unsigned long long)__popc(m));
     }
 }
 

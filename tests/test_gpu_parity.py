@@ -284,6 +284,11 @@ def test_nms_semantics(kpl, oracle):
         d.setInputCloud(xyz); d.setNormals(nrm)
         _, idx = d.compute()
         assert np.array_equal(idx, oracle.nms(xyz, g["scores"], r_nms, th)), (r_nms, th)
+        # decisions within 1e-5 of the threshold are reported separately (north star): with T = 100 trees the
+        # score k/100 sits exactly on 0.85 / 0.5 / 0.9 for many points
+        thd = float(np.float32(th))
+        near = int(np.sum(np.abs(g["scores"].astype(np.float64) - thd) <= 1e-5))
+        assert d.stats()["n_near_threshold"] == near, (th, d.stats()["n_near_threshold"], near)
         d.close()
 
 
