@@ -163,7 +163,7 @@ static int install_forest(kpl_ctx* ctx, const HostForestArrays& H)
     KPL_CUDA(cudaMalloc((void**)&F.d_roots, roots.size() * sizeof(int32_t)));
     KPL_CUDA(cudaMemcpy(F.d_nodes, nodes.data(), nodes.size() * sizeof(PackedNode), cudaMemcpyHostToDevice));
     KPL_CUDA(cudaMemcpy(F.d_roots, roots.data(), roots.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
-    F.ntrees = (int32_t)roots.size(); F.nnodes = (int32_t)nodes.size(); F.var_count = H.var_count; F.max_depth = max_depth;
+    F.ntrees = (int32_t)roots.size(); F.nnodes = (int32_t)H.var.size(); F.var_count = H.var_count; F.max_depth = max_depth;
     F.roots = roots;
     return KPL_OK;
 }

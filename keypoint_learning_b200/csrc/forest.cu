@@ -1,8 +1,8 @@
 // forest.cu -- random-forest evaluation: replaces cv::ml::RTrees::predict(feat, result, PREDICT_SUM)
 // and the score line of KeypointLearningDetector::runForest (impl/KeypointLearning.hpp:281-287).
 //
-// Nodes are re-laid out on the host in pre-order, 8 bytes each (PackedNode): the left child is the
-// next node, the right child is node + right_offset, so a visit is one 8-byte load.  One thread
+// Nodes are re-laid out on the host in 32-byte blocks {node, left child, right child} (pack_forest below),
+// so one sector fetched from L2 serves two levels of a walk.  One thread
 // evaluates one point; its feature row sits in shared memory as sf[var][thread] (bank == lane, no
 // conflicts for the data-dependent var), and four trees are walked concurrently per thread so four
 // independent node loads are in flight (the node arrays live in L2 / L1).
@@ -63,39 +63,51 @@ cudaError_t launch_forest(kpl_ctx* c, int64_t n, bool use_role)
     return cudaGetLastError();
 }
 
-// Host side: arbitrary (roots,var,thr,left,right,value) arrays -> pre-order PackedNode array.
+// Host side: arbitrary (roots,var,thr,left,right,value) arrays -> 32-byte BLOCKS of four PackedNodes
+// {P, L, R, unused}: a node P of even depth together with its two children.  One 32-byte sector -- the unit
+// the L2 delivers -- therefore carries two levels of a walk, where a flat node array spends a sector per
+// level (8 useful bytes of 32).  `roots` and the child offsets count blocks:
+//   P.packed = var                      (1023: P is a leaf, thr holds its value; L and R are unused)
+//   L.packed = var | (offset << 10)     block of L's left child = this block + offset, L's right child the next block
+//   R.packed likewise for R's children; a leaf child has var 1023 and its value in thr.
+// `nodes` is the flat array of 4 * nblocks PackedNodes.
 int pack_forest(const HostForestArrays& in, std::vector<PackedNode>& nodes, std::vector<int32_t>& roots, int& max_depth, std::string& err)
 {
     const int32_t nn = (int32_t)in.var.size();
     nodes.clear(); roots.clear(); max_depth = 0;
-    nodes.reserve(nn);
-    std::vector<std::pair<int32_t, int32_t>> stack;   // (source node, packed index of parent waiting for its right child or -1)
-    std::vector<int32_t> depth_stack;
+    struct Item { int32_t src, block, depth; };
+    std::vector<Item> queue;
+    const PackedNode empty = {0.f, KPL_LEAF_VAR};
+    auto bad = [&](int32_t i) { return i < 0 || i >= nn; };
     for (size_t t = 0; t < in.roots.size(); ++t) {
-        roots.push_back((int32_t)nodes.size());
-        stack.clear(); depth_stack.clear();
-        stack.push_back({in.roots[t], -1}); depth_stack.push_back(0);
-        while (!stack.empty()) {
-            auto [src, parent] = stack.back(); stack.pop_back();
-            int d = depth_stack.back(); depth_stack.pop_back();
-            if (src < 0 || src >= nn) { err = "forest: node index out of range"; return KPL_E_FOREST; }
-            if ((int64_t)nodes.size() > (int64_t)nn) { err = "forest: cyclic node graph"; return KPL_E_FOREST; }
-            int32_t me = (int32_t)nodes.size();
-            if (parent >= 0) {
-                int64_t off = (int64_t)me - parent;
-                if (off >= (1 << 22)) { err = "forest: subtree larger than 2^22 nodes"; return KPL_E_FOREST; }
-                nodes[parent].packed |= (uint32_t)off << 10;
-            }
-            max_depth = std::max(max_depth, d);
-            PackedNode pn;
-            if (in.var[src] < 0) { pn.thr = in.value[src]; pn.packed = KPL_LEAF_VAR; nodes.push_back(pn); }
-            else {
-                if (in.var[src] >= (int32_t)KPL_LEAF_VAR) { err = "forest: variable index >= 1023"; return KPL_E_FOREST; }
-                pn.thr = in.thr[src]; pn.packed = (uint32_t)in.var[src];
-                nodes.push_back(pn);
-                // right is pushed first so that the left subtree is emitted immediately after `me`
-                stack.push_back({in.right[src], me}); depth_stack.push_back(d + 1);
-                stack.push_back({in.left[src], -1}); depth_stack.push_back(d + 1);
+        queue.clear();
+        const int32_t root_block = (int32_t)(nodes.size() / 4);
+        roots.push_back(root_block);
+        nodes.insert(nodes.end(), 4, empty);
+        queue.push_back({in.roots[t], root_block, 0});
+        for (size_t h = 0; h < queue.size(); ++h) {
+            const Item it = queue[h];
+            if (bad(it.src)) { err = "forest: node index out of range"; return KPL_E_FOREST; }
+            if ((int64_t)nodes.size() > 16ll * nn + 16) { err = "forest: cyclic node graph"; return KPL_E_FOREST; }
+            max_depth = std::max(max_depth, it.depth);
+            const size_t b = (size_t)it.block * 4;
+            if (in.var[it.src] < 0) { nodes[b] = PackedNode{in.value[it.src], KPL_LEAF_VAR}; continue; }
+            if (in.var[it.src] >= (int32_t)KPL_LEAF_VAR) { err = "forest: variable index >= 1023"; return KPL_E_FOREST; }
+            nodes[b] = PackedNode{in.thr[it.src], (uint32_t)in.var[it.src]};
+            const int32_t kids[2] = {in.left[it.src], in.right[it.src]};
+            for (int side = 0; side < 2; ++side) {
+                const int32_t c = kids[side];
+                if (bad(c)) { err = "forest: node index out of range"; return KPL_E_FOREST; }
+                max_depth = std::max(max_depth, it.depth + 1);
+                if (in.var[c] < 0) { nodes[b + 1 + side] = PackedNode{in.value[c], KPL_LEAF_VAR}; continue; }
+                if (in.var[c] >= (int32_t)KPL_LEAF_VAR) { err = "forest: variable index >= 1023"; return KPL_E_FOREST; }
+                const int32_t first = (int32_t)(nodes.size() / 4);
+                const int64_t off = (int64_t)first - it.block;
+                if (off >= (1 << 22)) { err = "forest: tree larger than 2^22 blocks"; return KPL_E_FOREST; }
+                nodes[b + 1 + side] = PackedNode{in.thr[c], (uint32_t)in.var[c] | ((uint32_t)off << 10)};
+                nodes.insert(nodes.end(), 8, empty);
+                queue.push_back({in.left[c], first, it.depth + 2});
+                queue.push_back({in.right[c], first + 1, it.depth + 2});
             }
         }
     }

@@ -15,7 +15,7 @@ static constexpr int TREES_IN_FLIGHT = KPL_TREES_IN_FLIGHT;
 
 // x[var * stride] is feature `var` of this thread's point (a shared-memory column: bank == lane for
 // stride 32 / 128, so the data-dependent var never conflicts).  Four trees are walked concurrently so
-// four independent 8-byte node loads (L1 / L2 resident) are in flight per thread.
+// four independent block loads (L2 resident) are in flight per thread; nd[] counts 32-byte blocks.
 __device__ __forceinline__ float forest_score(const float* x, int stride, const PackedNode* __restrict__ nodes,
                                               const int32_t* __restrict__ roots, int ntrees)
 {
@@ -36,13 +36,22 @@ __device__ __forceinline__ float forest_score(const float* x, int stride, const 
 #pragma unroll
             for (int u = 0; u < TREES_IN_FLIGHT; ++u) {
                 if (live[u]) {
-                    const uint2 raw = __ldg(reinterpret_cast<const uint2*>(nodes + nd[u]));
-                    const float thr = __uint_as_float(raw.x);
-                    const uint32_t var = raw.y & 1023u;
-                    if (var == KPL_LEAF_VAR) { val[u] = thr; live[u] = false; }
+                    // one 32-byte block: the node, its left child, its right child (pack_forest): two levels per sector
+                    const uint4* blk = reinterpret_cast<const uint4*>(nodes) + 2 * (size_t)nd[u];
+                    const uint4 pl = __ldg(blk);
+                    const uint2 r = __ldg(reinterpret_cast<const uint2*>(blk + 1));
+                    const uint32_t pvar = pl.y & 1023u;
+                    if (pvar == KPL_LEAF_VAR) { val[u] = __uint_as_float(pl.x); live[u] = false; }
                     else {
-                        nd[u] = (x[var * stride] <= thr) ? nd[u] + 1 : nd[u] + (int)(raw.y >> 10);
-                        any = true;
+                        // DTreesImpl::predictTrees: go left iff value <= split.c
+                        const bool left = x[pvar * stride] <= __uint_as_float(pl.x);
+                        const uint32_t cthr = left ? pl.z : r.x, cpk = left ? pl.w : r.y;
+                        const uint32_t cvar = cpk & 1023u;
+                        if (cvar == KPL_LEAF_VAR) { val[u] = __uint_as_float(cthr); live[u] = false; }
+                        else {
+                            nd[u] += (int)(cpk >> 10) + ((x[cvar * stride] <= __uint_as_float(cthr)) ? 0 : 1);
+                            any = true;
+                        }
                     }
                 }
             }

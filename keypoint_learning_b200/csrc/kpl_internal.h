@@ -23,8 +23,8 @@ struct GridDesc {
     int64_t ncells;
 };
 
-// One forest node, 8 bytes: thr_or_value + packed(right_offset << 10 | var); var == 1023 => leaf.
-// The left child of node i is i+1 (pre-order), the right child is i + right_offset.
+// One forest node, 8 bytes: thr_or_value + packed(child_block_offset << 10 | var); var == 1023 => leaf.
+// Nodes are grouped in 32-byte blocks {node, left child, right child, unused}: see pack_forest (forest.cu).
 struct __align__(8) PackedNode {
     float thr;
     uint32_t packed;
@@ -33,7 +33,7 @@ static constexpr uint32_t KPL_LEAF_VAR = 1023u;
 
 struct Forest {
     int32_t ntrees = 0, nnodes = 0, var_count = 0, max_depth = 0;
-    std::vector<int32_t> roots;           // host copy (pre-order node index of each root)
+    std::vector<int32_t> roots;           // host copy (block index of each root)
     PackedNode* d_nodes = nullptr;
     int32_t* d_roots = nullptr;
 };
