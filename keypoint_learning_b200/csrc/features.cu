@@ -3,19 +3,22 @@
 // its helpers findAnnulusPair / findBinPair (src/KeypointLearning.cpp:41-92) and the FLANN radius
 // search behind searchForNeighbors (hpp:334).
 //
-// Mapping: one warp owns 32 consecutive cell-sorted query points, one lane per query.  The warp
-// walks the cell rows that can hold neighbours of any of its queries; each row is ONE contiguous
-// range of the sorted arrays (grid.cu), staged 32 candidates at a time into a per-warp shared
-// tile with coalesced float4 loads (the next tile's loads are in flight while the current one is
-// consumed).  A tile is consumed in two phases:
-//   1. membership: every lane tests all 32 candidates (shared-memory broadcast reads, 12
-//      instructions each) and records the exact FLANN predicate d2 < r2 in a 32-bit mask;
-//   2. votes: every lane walks the set bits of ITS mask in ascending order, so the expensive vote
-//      arithmetic runs only for real neighbours instead of for every (lane, candidate) pair.
+// Mapping: one warp (= one block) owns up to 32 consecutive cell-sorted query points of ONE run of the
+// work list (grid.cu: a stretch of one cell row spanning at most span + 1 cells), one lane per query, so
+// the warp's queries share a tight candidate box.  The warp walks the cell rows that can hold neighbours
+// of any of its queries; each row is ONE contiguous range of the sorted arrays, staged 32 candidates at a
+// time into a shared SoA tile with coalesced float4 loads (the next tile's loads are in flight while the
+// current one is consumed).  A tile is consumed in two phases:
+//   1. membership: every lane evaluates the exact FLANN predicate d2 < r2 for all 32 candidates --
+//      broadcast 128-bit shared loads, four candidates per step in packed FP32 (FADD2/FMUL2/FFMA2) --
+//      into a 32-bit mask;
+//   2. votes: every lane walks the set bits of ITS mask in ascending order, two neighbours per iteration
+//      with the FP32 arithmetic of both packed, so the expensive vote runs only for real neighbours.
 // Each query therefore sees its neighbours in ascending sorted position = canonical
 // (cell key, index) order and accumulates its votes sequentially in FP32 into a lane-private
 // histogram column hist[cell][lane] (bank == lane: conflict-free, no atomics).  That fixed order
-// is what makes the histogram bit-identical to the oracle.
+// is what makes the histogram bit-identical to the oracle.  The tail normalises the row per annulus and,
+// in kpl_detect*, evaluates the forest straight out of the histogram column (forest.cuh).
 //
 // Arithmetic: IEEE binary32 RN without contraction, as the reference evaluates it.  The FAST
 // variant replaces the IEEE square root and the divisions by the two run constants (annulus and
