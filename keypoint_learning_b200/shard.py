@@ -158,14 +158,16 @@ class SlabJob:
         self.offset = np.array([self.x0, 0, 0], np.int32)
         self._scores = None
         self._kp = None
+        # which of my points the neighbours need: a property of the resident slab, not of a step
+        self._left_sel = torch.nonzero(self.cx < self.c0 + p.halo).flatten() if rank > 0 else None
+        self._right_sel = torch.nonzero(self.cx >= self.c1 - p.halo).flatten() if rank < world - 1 else None
 
     # ---- step pieces (kept separate so the CPU tests can put the oracle in the middle) --------------
     def exchange_halo(self):
         """Send my boundary strips to the two neighbours, receive theirs (NCCL all_to_all over NVLink; gloo on
         CPU).  Returns the (left, right) received buffers, None at the ends."""
         p, r, w = self.plan, self.rank, self.world
-        left_sel = torch.nonzero(self.cx < self.c0 + p.halo).flatten() if r > 0 else None
-        right_sel = torch.nonzero(self.cx >= self.c1 - p.halo).flatten() if r < w - 1 else None
+        left_sel, right_sel = self._left_sel, self._right_sel
 
         def pack(sel):
             # one message per neighbour: xyz4 | gidx (as 2 x int32 bit patterns) | cx  -> float32 [m, 7]

@@ -121,6 +121,16 @@ KPLO_API void kplo_find_bin_pair(int n_bins, float cosine, int* bin_index, int* 
     *bin_index = b; *bin_index_pair = p; *bin_weight = fabsf(w);
 }
 
+/* whole arrays at once (tests sweep millions of inputs against oracle/_ref) */
+KPLO_API void kplo_annulus_sweep(int n_annulus, float support, const float* distance, int64_t n, int* index, int* pair, float* weight)
+{
+    for (int64_t i = 0; i < n; ++i) kplo_find_annulus_pair(n_annulus, distance[i], support, index + i, pair + i, weight + i);
+}
+KPLO_API void kplo_bin_sweep(int n_bins, const float* cosine, int64_t n, int* index, int* pair, float* weight)
+{
+    for (int64_t i = 0; i < n; ++i) kplo_find_bin_pair(n_bins, cosine[i], index + i, pair + i, weight + i);
+}
+
 /* FLANN L2_Simple<float>: result += diff*diff over x,y,z, FP32, no FMA */
 static inline float dist2(const float* a, const float* b)
 {

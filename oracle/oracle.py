@@ -27,6 +27,52 @@ def build(force: bool = False) -> str:
     return so
 
 
+REFERENCE = os.environ.get("KPL_REFERENCE", "/root/reference")
+_REF = None
+
+
+def build_ref(force: bool = False):
+    """oracle/_ref/libkpl_ref_helpers.so: the reference's OWN src/KeypointLearning.cpp (findAnnulusPair /
+    findBinPair) compiled from the mounted reference tree (oracle/Makefile, target `ref`).  Returns the path,
+    or None where the reference tree is not mounted and no prebuilt library travelled with the repository."""
+    so = os.path.join(_HERE, "_ref", "libkpl_ref_helpers.so")
+    src = os.path.join(REFERENCE, "src", "KeypointLearning.cpp")
+    if os.path.exists(src) and (force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(os.path.join(_HERE, "ref_wrap.cpp"))):
+        subprocess.check_call(["make", "-C", _HERE, "-s", "ref", "REFERENCE=" + REFERENCE] + (["-B"] if force else []))
+    return so if os.path.exists(so) else None
+
+
+def ref_lib():
+    """ctypes handle of oracle/_ref (the reference's own binning helpers), or None when it was never built."""
+    global _REF
+    if _REF is None:
+        so = build_ref()
+        if so is None:
+            return None
+        L = C.CDLL(so)
+        f32p, ip = C.POINTER(C.c_float), C.POINTER(C.c_int)
+        L.kplref_find_annulus_pair.argtypes = [C.c_int, C.c_float, C.c_float, ip, ip, f32p]
+        L.kplref_find_bin_pair.argtypes = [C.c_int, C.c_float, ip, ip, f32p]
+        L.kplref_annulus_sweep.argtypes = [C.c_int, C.c_float, f32p, C.c_long, ip, ip, f32p]
+        L.kplref_bin_sweep.argtypes = [C.c_int, f32p, C.c_long, ip, ip, f32p]
+        _REF = L
+    return _REF
+
+
+def ref_annulus_sweep(n_annulus, support, distances):
+    d = np.ascontiguousarray(distances, np.float32)
+    i = np.empty(len(d), np.int32); p = np.empty(len(d), np.int32); w = np.empty(len(d), np.float32)
+    ref_lib().kplref_annulus_sweep(int(n_annulus), np.float32(support), _p(d, C.c_float), len(d), _p(i, C.c_int), _p(p, C.c_int), _p(w, C.c_float))
+    return i, p, w
+
+
+def ref_bin_sweep(n_bins, cosines):
+    c = np.ascontiguousarray(cosines, np.float32)
+    i = np.empty(len(c), np.int32); p = np.empty(len(c), np.int32); w = np.empty(len(c), np.float32)
+    ref_lib().kplref_bin_sweep(int(n_bins), _p(c, C.c_float), len(c), _p(i, C.c_int), _p(p, C.c_int), _p(w, C.c_float))
+    return i, p, w
+
+
 def lib():
     global _LIB
     if _LIB is None:
@@ -79,6 +125,24 @@ def _xyz(a):
 # ---------------------------------------------------------------------------------------------
 # scalar helpers
 # ---------------------------------------------------------------------------------------------
+def annulus_sweep(n_annulus, support, distances):
+    d = np.ascontiguousarray(distances, np.float32)
+    i = np.empty(len(d), np.int32); p = np.empty(len(d), np.int32); w = np.empty(len(d), np.float32)
+    L = lib()
+    L.kplo_annulus_sweep.argtypes = [C.c_int, C.c_float, C.POINTER(C.c_float), C.c_int64, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_float)]
+    L.kplo_annulus_sweep(int(n_annulus), np.float32(support), _p(d, C.c_float), len(d), _p(i, C.c_int), _p(p, C.c_int), _p(w, C.c_float))
+    return i, p, w
+
+
+def bin_sweep(n_bins, cosines):
+    c = np.ascontiguousarray(cosines, np.float32)
+    i = np.empty(len(c), np.int32); p = np.empty(len(c), np.int32); w = np.empty(len(c), np.float32)
+    L = lib()
+    L.kplo_bin_sweep.argtypes = [C.c_int, C.POINTER(C.c_float), C.c_int64, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_float)]
+    L.kplo_bin_sweep(int(n_bins), _p(c, C.c_float), len(c), _p(i, C.c_int), _p(p, C.c_int), _p(w, C.c_float))
+    return i, p, w
+
+
 def find_annulus_pair(n_annulus, distance, support):
     i, p, w = C.c_int(), C.c_int(), C.c_float()
     lib().kplo_find_annulus_pair(n_annulus, np.float32(distance), np.float32(support), C.byref(i), C.byref(p), C.byref(w))

@@ -175,6 +175,42 @@ def test_normals_radius_mode_runs(oracle, views):
     assert np.allclose(np.linalg.norm(nrm[ok, :3], axis=1), 1.0, atol=1e-5)
 
 
+def test_binning_helpers_match_the_reference_build(oracle):
+    """oracle/_ref: the reference's OWN src/KeypointLearning.cpp compiled from the mounted tree.  The oracle's
+    restatement of findAnnulusPair / findBinPair must agree with it bit for bit on a dense sweep that includes
+    every bin boundary +- a few ulps, the clamps and the centre-of-bin cases."""
+    if oracle.ref_lib() is None:
+        pytest.skip("oracle/_ref was not built (reference tree not mounted)")
+    rng = np.random.default_rng(5)
+
+    def around(values, span=3):
+        out = []
+        for v in values:
+            x = np.float32(v)
+            lo = hi = x
+            out.append(x)
+            for _ in range(span):
+                lo = np.nextafter(lo, np.float32(-np.inf)); hi = np.nextafter(hi, np.float32(np.inf))
+                out += [lo, hi]
+        return np.asarray(out, np.float32)
+
+    for A, support in ((5, 20.0), (4, 7.5), (8, 40.0), (10, 13.37), (1, 2.0), (16, 20.0)):
+        dim = np.float32(support) / np.float32(A)
+        edges = around(np.arange(0, 2 * A + 1, dtype=np.float32) * dim / np.float32(2))        # boundaries and centres
+        d = np.concatenate([edges[(edges >= 0) & (edges <= np.float32(support))],
+                            rng.uniform(0, support, 200_000).astype(np.float32), np.float32([0.0, support])])
+        got, ref = oracle.annulus_sweep(A, support, d), oracle.ref_annulus_sweep(A, support, d)
+        for g, r in zip(got, ref):
+            assert np.array_equal(g.view(np.uint32), r.view(np.uint32)), (A, support)
+    for B in (10, 5, 8, 16, 1, 3):
+        dim = np.float32(2) / np.float32(B)
+        edges = around(np.arange(0, 2 * B + 1, dtype=np.float32) * dim / np.float32(2))
+        c = np.concatenate([edges, rng.uniform(-0.5, 2.5, 200_000).astype(np.float32), np.float32([-1.0, 0.0, 2.0, 3.0, -0.0])])
+        got, ref = oracle.bin_sweep(B, c), oracle.ref_bin_sweep(B, c)
+        for g, r in zip(got, ref):
+            assert np.array_equal(g.view(np.uint32), r.view(np.uint32)), B
+
+
 def test_normals_radius_order_deviation_is_small(oracle, views):
     """Canonical (cell, index) accumulation order (what the device uses) against PCL's sorted (d2, index)
     order: the same un-centred FP32 moment sums re-associated.  On the model-centred bundled view the two
