@@ -5,21 +5,25 @@
  * and bench.py's cpu_baseline / --impl reference legs may load this library.  The product
  * (keypoint_learning_b200/csrc) never includes, links or calls anything in this file.
  *
- * PARITY UNPINNED: the reference (CVLAB-Unibo/Keypoint-Learning) ships no tests, no golden
- * outputs and its trained forests are absent from the checkout; PCL 1.8.0 / FLANN / Eigen /
- * OpenCV 3.2 C++ are not installed, so the reference binary cannot be built here.  This file
- * is a plain-C restatement of the reference's arithmetic, following
+ * PARITY PIN: the reference (CVLAB-Unibo/Keypoint-Learning) ships no tests, no golden outputs and its
+ * trained forests are absent from the checkout, and it cannot be built as a whole here (PCL 1.8.0 / FLANN /
+ * Eigen / OpenCV 3.2 C++ are not installed).  Its OWN code on this path can be: oracle/_ref compiles
+ * src/KeypointLearning.cpp (findAnnulusPair / findBinPair) and the detector templates of
+ * include/KeypointLearning.h + include/impl/KeypointLearning.hpp from the mounted reference tree against a
+ * stand-in environment (oracle/ref_stubs/kplref_env.h), and tests/test_oracle.py holds this file to it BIT FOR
+ * BIT: the binning helpers over millions of inputs, computePointFeatures rows, runForest scores, the
+ * threshold + local-maximum NMS and the draws-remove branch on crops of the bundled views.
+ * What is NOT the reference's own code -- and therefore restated here from the upstream versions the
+ * reference pins (README.md:66-67), their sources not being in the container -- is third-party:
+ * PCL 1.8.0 NormalEstimation / computeMeanAndCovarianceMatrix / eigen33 / computeRoots, FLANN L2_Simple +
+ * strict radius test, OpenCV DTreesImpl::predictTrees with PREDICT_SUM, Eigen's small reductions.  Those are
+ * pinned independently in tests/: cv2.ml.RTrees (the real OpenCV) for the forest stage, scipy cKDTree for
+ * neighbour sets, float64 PCA for normals.  This file follows
  *   include/impl/KeypointLearning.hpp:179-263  (detectKeypoints: threshold + local-max NMS)
  *   include/impl/KeypointLearning.hpp:267-296  (runForest: score = 1 - sum/ntrees)
  *   include/impl/KeypointLearning.hpp:321-376  (computePointFeatures: annuli x bins histogram)
  *   src/KeypointLearning.cpp:41-65, 68-92      (findAnnulusPair, findBinPair)
  *   src/main_test_detector.cpp:162-169         (k-NN(10) PCA normals, viewpoint 0,0,0)
- * and the third-party semantics those lines call into (PCL 1.8.0 NormalEstimation /
- * computeMeanAndCovarianceMatrix / eigen33 / computeRoots, FLANN L2_Simple + strict radius test,
- * OpenCV DTreesImpl::predictTrees with PREDICT_SUM), recalled from the pinned upstream versions
- * (README.md:66-67 of the reference) because their sources are not in the container.
- * What CAN be pinned is pinned in tests/: cv2.ml.RTrees for the forest stage, scipy cKDTree for
- * neighbour sets, float64 PCA for normals, hand-derived known answers for the binning helpers.
  *
  * Arithmetic contract (shared with the CUDA kernels, which implement it independently):
  *   - all per-pair math in IEEE binary32, round-to-nearest, NO fused multiply-add

@@ -32,29 +32,36 @@ _REF = None
 
 
 def build_ref(force: bool = False):
-    """oracle/_ref/libkpl_ref_helpers.so: the reference's OWN src/KeypointLearning.cpp (findAnnulusPair /
-    findBinPair) compiled from the mounted reference tree (oracle/Makefile, target `ref`).  Returns the path,
-    or None where the reference tree is not mounted and no prebuilt library travelled with the repository."""
-    so = os.path.join(_HERE, "_ref", "libkpl_ref_helpers.so")
+    """oracle/_ref/libkpl_ref.so: the reference's OWN code on the detection path -- src/KeypointLearning.cpp and
+    the detector templates of include/KeypointLearning.h + impl/KeypointLearning.hpp -- compiled from the mounted
+    reference tree against the stand-in environment oracle/ref_stubs/ (oracle/Makefile, target `ref`).  Returns
+    the path, or None where the reference tree is not mounted and no prebuilt library travelled with the repo."""
+    so = os.path.join(_HERE, "_ref", "libkpl_ref.so")
     src = os.path.join(REFERENCE, "src", "KeypointLearning.cpp")
-    if os.path.exists(src) and (force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(os.path.join(_HERE, "ref_wrap.cpp"))):
+    deps = [os.path.join(_HERE, "ref_wrap.cpp"), os.path.join(_HERE, "ref_stubs", "kplref_env.h")]
+    if os.path.exists(src) and (force or not os.path.exists(so) or any(os.path.getmtime(so) < os.path.getmtime(d) for d in deps)):
         subprocess.check_call(["make", "-C", _HERE, "-s", "ref", "REFERENCE=" + REFERENCE] + (["-B"] if force else []))
     return so if os.path.exists(so) else None
 
 
 def ref_lib():
-    """ctypes handle of oracle/_ref (the reference's own binning helpers), or None when it was never built."""
+    """ctypes handle of oracle/_ref (the reference's own code), or None when it was never built."""
     global _REF
     if _REF is None:
         so = build_ref()
         if so is None:
             return None
         L = C.CDLL(so)
-        f32p, ip = C.POINTER(C.c_float), C.POINTER(C.c_int)
+        f32p, ip, i32p, i64p = C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_int32), C.POINTER(C.c_int64)
         L.kplref_find_annulus_pair.argtypes = [C.c_int, C.c_float, C.c_float, ip, ip, f32p]
         L.kplref_find_bin_pair.argtypes = [C.c_int, C.c_float, ip, ip, f32p]
         L.kplref_annulus_sweep.argtypes = [C.c_int, C.c_float, f32p, C.c_long, ip, ip, f32p]
         L.kplref_bin_sweep.argtypes = [C.c_int, f32p, C.c_long, ip, ip, f32p]
+        L.kplref_set_neighbours.argtypes = [C.c_double, i64p, i32p, C.c_double, i64p, i32p]
+        L.kplref_set_forest.argtypes = [C.c_int, i32p, i32p, f32p, i32p, i32p, f32p]
+        L.kplref_features.argtypes = [f32p, f32p, C.c_int64, C.c_double, C.c_int, C.c_int, i32p, C.c_int64, f32p]
+        L.kplref_detect.argtypes = [f32p, f32p, C.c_int64, C.c_double, C.c_double, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, i32p, f32p]
+        L.kplref_detect.restype = C.c_int64
         _REF = L
     return _REF
 
@@ -71,6 +78,59 @@ def ref_bin_sweep(n_bins, cosines):
     i = np.empty(len(c), np.int32); p = np.empty(len(c), np.int32); w = np.empty(len(c), np.float32)
     ref_lib().kplref_bin_sweep(int(n_bins), _p(c, C.c_float), len(c), _p(i, C.c_int), _p(p, C.c_int), _p(w, C.c_float))
     return i, p, w
+
+
+def ref_neighbour_lists(xyz, radius, order, r_feat=None, cpr=4):
+    """CSR neighbour lists for the stand-in pcl::search::KdTree of oracle/_ref: every point's radius neighbours
+    (d2 < (float)(r*r), FLANN's FP32 expression) with the query itself FIRST -- slot 0 of a sorted search, the
+    slot computePointFeatures skips -- and the others in `order`: 0 ascending point index, 1 canonical
+    (cell key, index) of the grid built for r_feat, 2 ascending (d2, index) like a sorted kd-tree."""
+    xyz = _xyz(xyz)
+    n = len(xyz)
+    off, idx = radius_neighbors(xyz, radius, np.arange(n, dtype=np.int32))
+    q = np.repeat(np.arange(n, dtype=np.int64), np.diff(off))
+    not_self = (idx != q).astype(np.int8)
+    if order == 1:
+        org, cell, dims = canon_grid(xyz, radius if r_feat is None else r_feat, cpr)
+        sec = canon_keys(xyz, org, cell, dims)[idx]
+    elif order == 2:
+        d = xyz[q] - xyz[idx]
+        sec = ((d[:, 0] * d[:, 0]) + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2]
+    else:
+        sec = np.zeros(len(idx), np.int8)
+    perm = np.lexsort((idx, sec, not_self, q))
+    return np.ascontiguousarray(off, np.int64), np.ascontiguousarray(idx[perm], np.int32)
+
+
+def ref_features(xyz, normals4, r_feat, A, B, lists, qidx=None):
+    """The reference's computePointsForTrainingFeatures / computePointFeatures (hpp:299-376) through oracle/_ref."""
+    xyz = _xyz(xyz); nrm = np.ascontiguousarray(normals4, np.float32)
+    q = np.arange(len(xyz), dtype=np.int32) if qidx is None else np.ascontiguousarray(qidx, np.int32)
+    off, idx = lists
+    L = ref_lib()
+    L.kplref_set_neighbours(float(r_feat), _p(off, C.c_int64), _p(idx, C.c_int32), -1.0, None, None)
+    out = np.empty((len(q), A * B), np.float32)
+    rc = L.kplref_features(_p(xyz, C.c_float), _p(nrm, C.c_float), len(xyz), float(r_feat), A, B, _p(q, C.c_int32), len(q), _p(out, C.c_float))
+    assert rc == 0, rc
+    return out
+
+
+def ref_detect(xyz, normals4, forest, r_feat, r_nms, th, A, B, lists_feat, lists_nms, non_maxima=True, draws_remove=False, draws_thr=0.0):
+    """The reference's compute() -> detectKeypoints -> runForest (hpp:179-296) through oracle/_ref.
+    Returns (keypoint indices, their scores); with non_maxima=False every point and its response."""
+    xyz = _xyz(xyz); nrm = np.ascontiguousarray(normals4, np.float32)
+    L = ref_lib()
+    L.kplref_set_forest(forest["ntrees"], _p(forest["roots"], C.c_int32), _p(forest["var"], C.c_int32), _p(forest["thr"], C.c_float),
+                        _p(forest["left"], C.c_int32), _p(forest["right"], C.c_int32), _p(forest["value"], C.c_float))
+    of, xf = lists_feat
+    on, xn = lists_nms if lists_nms is not None else (None, None)
+    L.kplref_set_neighbours(float(r_feat), _p(of, C.c_int64), _p(xf, C.c_int32), float(r_nms),
+                            _p(on, C.c_int64) if on is not None else None, _p(xn, C.c_int32) if xn is not None else None)
+    kp = np.empty(len(xyz), np.int32); sc = np.empty(len(xyz), np.float32)
+    cnt = L.kplref_detect(_p(xyz, C.c_float), _p(nrm, C.c_float), len(xyz), float(r_feat), float(r_nms), np.float32(th), A, B,
+                          int(non_maxima), int(draws_remove), np.float32(draws_thr), _p(kp, C.c_int32), _p(sc, C.c_float))
+    assert cnt >= 0, cnt
+    return kp[:cnt].copy(), sc[:cnt].copy()
 
 
 def lib():

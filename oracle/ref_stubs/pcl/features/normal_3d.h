@@ -1,0 +1,3 @@
+// Stand-in for <pcl/features/normal_3d.h> (not installed): everything the reference needs is in kplref_env.h.
+#pragma once
+#include "kplref_env.h"

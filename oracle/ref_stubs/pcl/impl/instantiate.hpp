@@ -1,3 +1,3 @@
-// Stand-in for <pcl/impl/instantiate.hpp> (PCL is not installed): the reference translation unit
-// src/KeypointLearning.cpp only needs it for a commented-out PCL_INSTANTIATE line.
+// Stand-in for <pcl/impl/instantiate.hpp> (not installed): everything the reference needs is in kplref_env.h.
 #pragma once
+#include "kplref_env.h"

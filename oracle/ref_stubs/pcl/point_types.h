@@ -1,2 +1,3 @@
-// Stand-in for <pcl/point_types.h>: nothing of it is used by findAnnulusPair / findBinPair.
+// Stand-in for <pcl/point_types.h> (not installed): everything the reference needs is in kplref_env.h.
 #pragma once
+#include "kplref_env.h"

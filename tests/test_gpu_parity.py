@@ -331,6 +331,34 @@ def test_uniform_sampling_matches_restatement(kpl, views, oracle):
     d.close()
 
 
+def test_cuda_path_against_the_reference_templates(kpl, views, oracle):
+    """The CUDA path against oracle/_ref DIRECTLY: the reference's own computePointFeatures / runForest /
+    detectKeypoints templates (compiled from the mounted tree; the prebuilt library travels with the repo),
+    fed with the canonical neighbour order the device uses."""
+    if oracle.ref_lib() is None:
+        pytest.skip("oracle/_ref was not built (reference tree not mounted)")
+    xyz = np.ascontiguousarray(views["cheff002"][:3000])
+    nrm = oracle.normals_knn(xyz, 10)
+    forest = oracle.load_forest_yaml(forest_path("synthetic-SHOT-like-T50-D10"))
+    lf = oracle.ref_neighbour_lists(xyz, R_FEAT, 1)
+    ln = oracle.ref_neighbour_lists(xyz, R_NMS, 0)
+    d = make_detector(kpl, forest=forest_path("synthetic-SHOT-like-T50-D10"), th=0.5)
+    d.keepIntermediates(True)
+    d.setInputCloud(xyz); d.setNormals(nrm)
+    _, idx = d.compute()
+    f_ref = oracle.ref_features(xyz, nrm, R_FEAT, 5, 10, lf)
+    assert np.array_equal(d.fetch("features", len(xyz), 50).view(np.uint32), f_ref.view(np.uint32))
+    all_idx, sc_ref = oracle.ref_detect(xyz, nrm, forest, R_FEAT, R_NMS, 0.5, 5, 10, lf, None, non_maxima=False)
+    assert np.array_equal(d.getResponse().view(np.uint32), sc_ref.view(np.uint32))
+    kp_ref, _ = oracle.ref_detect(xyz, nrm, forest, R_FEAT, R_NMS, 0.5, 5, 10, lf, ln)
+    assert np.array_equal(idx, kp_ref)
+    d.setNonMaximaDrawsRemove(True); d.setNonMaximaDrawsThreshold(1.5)
+    _, idx_d = d.compute()
+    kp_d, _ = oracle.ref_detect(xyz, nrm, forest, R_FEAT, R_NMS, 0.5, 5, 10, lf, ln, draws_remove=True, draws_thr=1.5)
+    assert np.array_equal(idx_d, kp_d)
+    d.close()
+
+
 def test_non_maxima_off_returns_every_point(kpl, views, oracle):
     xyz = np.ascontiguousarray(views["cheff001"][:5000])
     d = make_detector(kpl)

@@ -211,6 +211,62 @@ def test_binning_helpers_match_the_reference_build(oracle):
             assert np.array_equal(g.view(np.uint32), r.view(np.uint32)), B
 
 
+# ---------------------------------------------------------------------------------------------
+# oracle/_ref: the reference's OWN detector templates (include/KeypointLearning.h + impl/KeypointLearning.hpp)
+# compiled from the mounted tree against the stand-in environment oracle/ref_stubs/kplref_env.h.  Search,
+# forest traversal and the Eigen reductions are stand-ins (pinned elsewhere: scipy, cv2); everything else --
+# slot-0 skip, NaN-normal skip, the four ordered histogram updates, per-annulus normalisation, feature layout,
+# the score line, threshold compare, local-maximum NMS, the draws-remove skip list -- is the reference's code.
+# ---------------------------------------------------------------------------------------------
+def _ref_case(views, n=2500):
+    xyz = np.ascontiguousarray(views["cheff001"][:n])
+    return xyz
+
+
+def test_features_match_the_reference_templates(oracle, views):
+    if oracle.ref_lib() is None:
+        pytest.skip("oracle/_ref was not built (reference tree not mounted)")
+    xyz = _ref_case(views)
+    nrm = oracle.normals_knn(xyz, 10)
+    nrm[7::53, 0] = np.nan                                      # neighbours (and queries) without a finite normal
+    q = np.arange(0, len(xyz), 3, dtype=np.int32)
+    q = q[np.isfinite(nrm[q, 0])]                               # runForest never asks for such a query (hpp:277)
+    for r_feat, A, B in ((20.0, 5, 10), (9.0, 4, 8), (14.0, 10, 5)):
+        for order in (0, 1):
+            lists = oracle.ref_neighbour_lists(xyz, r_feat, order)
+            f_ref = oracle.ref_features(xyz, nrm, r_feat, A, B, lists, q)
+            f_orc = oracle.features(xyz, nrm, r_feat, A, B, order=order, qidx=q)
+            assert np.array_equal(f_ref.view(np.uint32), f_orc.view(np.uint32)), (r_feat, A, B, order)
+    # the order really matters at the last bit: a sorted-kd-tree order gives different (close) rows
+    f_sorted = oracle.ref_features(xyz, nrm, 20.0, 5, 10, oracle.ref_neighbour_lists(xyz, 20.0, 2), q)
+    f_canon = oracle.features(xyz, nrm, 20.0, 5, 10, order=1, qidx=q)
+    assert np.abs(f_sorted - f_canon).max() < 1e-5 and not np.array_equal(f_sorted, f_canon)
+
+
+def test_detection_matches_the_reference_templates(oracle, views):
+    if oracle.ref_lib() is None:
+        pytest.skip("oracle/_ref was not built (reference tree not mounted)")
+    xyz = _ref_case(views)
+    nrm = oracle.normals_knn(xyz, 10)
+    assert np.isfinite(nrm[:, :3]).all()                        # the reference mis-aligns its response cloud otherwise (hpp:277 vs :203)
+    forest = oracle.load_forest_yaml(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "forests", "synthetic-SHOT-like-T50-D10.yaml.gz"))
+    r_feat, A, B = 20.0, 5, 10
+    lf = oracle.ref_neighbour_lists(xyz, r_feat, 1)
+    feat = oracle.features(xyz, nrm, r_feat, A, B, order=1)
+    sc = oracle.scores(forest, feat, nrm)
+    # runForest: setNonMaxima(false) hands back the response cloud (hpp:189-196)
+    idx, sc_ref = oracle.ref_detect(xyz, nrm, forest, r_feat, 4.0, 0.5, A, B, lf, None, non_maxima=False)
+    assert np.array_equal(idx, np.arange(len(xyz))) and np.array_equal(sc_ref.view(np.uint32), sc.view(np.uint32))
+    for r_nms, th in ((4.0, 0.85), (2.0, 0.5), (6.0, 0.3), (4.0, 0.0)):
+        ln = oracle.ref_neighbour_lists(xyz, r_nms, 0)
+        idx, s = oracle.ref_detect(xyz, nrm, forest, r_feat, r_nms, th, A, B, lf, ln, non_maxima=True, draws_remove=False)
+        assert np.array_equal(idx, oracle.nms(xyz, sc, r_nms, th)), (r_nms, th)
+        assert np.array_equal(s.view(np.uint32), sc[idx].view(np.uint32))
+        for dthr in (0.0, 1.0, 3.0):
+            idx_d, _ = oracle.ref_detect(xyz, nrm, forest, r_feat, r_nms, th, A, B, lf, ln, non_maxima=True, draws_remove=True, draws_thr=dthr)
+            assert np.array_equal(idx_d, oracle.nms(xyz, sc, r_nms, th, draws_remove=True, draws_thr=dthr)), (r_nms, th, dthr)
+
+
 def test_normals_radius_order_deviation_is_small(oracle, views):
     """Canonical (cell, index) accumulation order (what the device uses) against PCL's sorted (d2, index)
     order: the same un-centred FP32 moment sums re-associated.  On the model-centred bundled view the two
