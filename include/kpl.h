@@ -148,6 +148,13 @@ KPL_API int kpl_uniform_sample(kpl_ctx* ctx, const float* xyz, int32_t xyz_strid
 KPL_API int kpl_features(kpl_ctx* ctx, const float* xyz, int32_t xyz_stride, const float* normals, int32_t normals_stride,
                          int64_t n, const int32_t* indices, int64_t m, float* features_out);
 
+/* pcl::KdTreeFLANN::nearestKSearch(point, 1, ...) as TrainDetector snaps its positive / negative samples onto
+ * cloud indices before computePointsForTrainingFeatures (src/main_train_detector.cpp:419-436): for each of the m
+ * query points (3 floats at q_stride bytes) the index of the nearest cloud point (ties: lower index) and,
+ * when d2_out != NULL, the squared distance. */
+KPL_API int kpl_nearest(kpl_ctx* ctx, const float* xyz, int32_t xyz_stride, int64_t n, const float* queries, int32_t q_stride,
+                        int64_t m, int32_t* idx_out, float* d2_out);
+
 /* searchForNeighbors / tree_->radiusSearch semantics (hpp:213,334): per point the number of
  * neighbours with d2 < (float)(r*r) (self included) and the wrapping 64-bit sum of
  * (index+1)*0x9E3779B97F4A7C15 over them; either output may be NULL. */

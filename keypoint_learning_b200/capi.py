@@ -22,7 +22,7 @@ ROLE_HALO, ROLE_SCORE, ROLE_OWNED = 0, 1, 3
 EXPORTS = ["kpl_create", "kpl_destroy", "kpl_last_error", "kpl_version", "kpl_set_stream", "kpl_params_default",
            "kpl_set_params", "kpl_get_params", "kpl_load_forest", "kpl_set_forest", "kpl_forest_info", "kpl_detect",
            "kpl_normals", "kpl_features", "kpl_radius_stats", "kpl_radius_neighbors", "kpl_detect_device",
-           "kpl_get_timings", "kpl_get_stats", "kpl_fetch", "kpl_set_keep_intermediates", "kpl_uniform_sample"]
+           "kpl_get_timings", "kpl_get_stats", "kpl_fetch", "kpl_set_keep_intermediates", "kpl_uniform_sample", "kpl_nearest"]
 
 
 class KplParams(C.Structure):
@@ -87,6 +87,7 @@ def load_library():
     L.kpl_fetch.argtypes = [vp, C.c_char_p, f32p, C.c_int64]
     L.kpl_set_keep_intermediates.argtypes = [vp, C.c_int]
     L.kpl_uniform_sample.argtypes = [vp, f32p, C.c_int32, C.c_int64, C.c_float, i32p, i64p]
+    L.kpl_nearest.argtypes = [vp, f32p, C.c_int32, C.c_int64, f32p, C.c_int32, C.c_int64, i32p, f32p]
     _lib = L
     return L
 
@@ -285,6 +286,16 @@ class KeypointLearningDetector:
         self._check(self._L.kpl_detect_device(self._h, C.c_void_p(d_xyz4), C.c_void_p(d_normals4 or None), C.c_void_p(d_role or None), int(n),
                                               C.c_void_p(d_scores or None), C.c_void_p(d_kp_idx), C.byref(nkp)))
         return nkp.value
+
+    def nearest(self, cloud, queries):
+        """Index (and squared distance) of the nearest cloud point of every query point (TrainDetector's 1-NN snap)."""
+        xyz, xs = _vec3(cloud, "cloud")
+        q, qs = _vec3(queries, "queries")
+        self._push()
+        idx = np.empty(max(1, q.shape[0]), np.int32); d2 = np.empty(max(1, q.shape[0]), np.float32)
+        self._check(self._L.kpl_nearest(self._h, _ptr(xyz, C.c_float), xs, xyz.shape[0], _ptr(q, C.c_float), qs, q.shape[0],
+                                        _ptr(idx, C.c_int32), _ptr(d2, C.c_float)))
+        return idx[:q.shape[0]].copy(), d2[:q.shape[0]].copy()
 
     def uniformSample(self, cloud, leaf):
         """pcl::UniformSampling(leaf) on the device: ascending indices of the surviving points."""

@@ -461,6 +461,27 @@ int kpl_radius_stats(kpl_ctx* ctx, const float* xyz, int32_t xyz_stride, int64_t
     return KPL_OK;
 }
 
+int kpl_nearest(kpl_ctx* ctx, const float* xyz, int32_t xyz_stride, int64_t n, const float* queries, int32_t q_stride, int64_t m,
+                int32_t* idx_out, float* d2_out)
+{
+    if (!ctx || m < 0 || (m > 0 && (!queries || !idx_out))) return KPL_E_INVALID;
+    begin_call(ctx);
+    if (m == 0) return KPL_OK;
+    if (n <= 0) return fail(ctx, KPL_E_INVALID, "the cloud is empty");
+    int rc = upload_inputs(ctx, xyz, xyz_stride, nullptr, 0, nullptr, n);
+    if (rc) return rc;
+    if ((rc = prepare_grid(ctx, ctx->in_xyz.p, nullptr, nullptr, n))) return rc;
+    if ((rc = upload_vec3(ctx, ctx->in_nrm, queries, q_stride, m))) return rc;          // the normals staging buffer is free here
+    KPL_CUDA(ensure(ctx->scratch_i, (size_t)m + 2));
+    KPL_CUDA(ensure(ctx->scratch_f, (size_t)m + 2));
+    KPL_CUDA(launch_nearest(ctx, ctx->in_nrm.p, m, ctx->scratch_i.p, ctx->scratch_f.p));
+    KPL_CUDA(cudaMemcpyAsync(idx_out, ctx->scratch_i.p, (size_t)m * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    if (d2_out) KPL_CUDA(cudaMemcpyAsync(d2_out, ctx->scratch_f.p, (size_t)m * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    KPL_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->stats.n_points = n; ctx->stats.kernel_launches = ctx->launches;
+    return KPL_OK;
+}
+
 int kpl_radius_neighbors(kpl_ctx* ctx, const float* xyz, int32_t xyz_stride, int64_t n, double radius,
                          const int32_t* queries, int64_t m, int64_t* offsets_out, int32_t* indices_out)
 {

@@ -112,6 +112,7 @@ cudaError_t launch_compact(kpl_ctx* c, int64_t n, int32_t* d_kp_idx_out);
 cudaError_t build_work_list(kpl_ctx* c, int span, DevBuf<int2>& work, int& nwarps);
 cudaError_t uniform_sample(kpl_ctx* c, const float4* xyz, int64_t n, float leaf, const float mn[3], const float mx[3],
                            int32_t* d_idx_out, std::string& err);
+cudaError_t launch_nearest(kpl_ctx* c, const float4* d_queries, int64_t m, int32_t* d_idx, float* d_d2);
 cudaError_t launch_radius_stats(kpl_ctx* c, int64_t n, double radius, int32_t* d_counts, unsigned long long* d_hash);
 cudaError_t launch_radius_lists(kpl_ctx* c, int64_t n, double radius, const int32_t* d_queries, int64_t m,
                                 const int64_t* d_offsets, int32_t* d_indices);

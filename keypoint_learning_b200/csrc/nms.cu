@@ -250,6 +250,65 @@ radius_kernel(const float4* __restrict__ s_pos, const uint32_t* __restrict__ ske
     }
 }
 
+// ---- nearest cloud point of arbitrary query points ------------------------------------------------------
+// pcl::KdTreeFLANN::nearestKSearch(point, 1, ...) as TrainDetector uses it to snap its positive / negative
+// samples onto cloud indices before computePointsForTrainingFeatures (src/main_train_detector.cpp:419-436).
+// One thread per query: shells of cells around the query's (clamped) cell until the best squared distance is
+// provably smaller than anything outside the scanned block; ties go to the lower index.
+__global__ void __launch_bounds__(128)
+nearest_kernel(const float4* __restrict__ s_pos, const int32_t* __restrict__ cell_start, GridDesc g, const float4* __restrict__ queries,
+               int64_t m, int32_t* __restrict__ idx_out, float* __restrict__ d2_out)
+{
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= m) return;
+    const float4 q = __ldg(queries + t);
+    const float v[3] = {q.x, q.y, q.z};
+    int c[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        double f = floor(__ddiv_rn(__dsub_rn((double)v[a], g.org[a]), g.cell)) - (double)g.off[a];
+        f = fmin(fmax(f, 0.0), (double)(g.dim[a] - 1));
+        c[a] = isfinite(v[a]) ? (int)f : 0;
+    }
+    float best = CUDART_INF_F;
+    uint32_t bidx = 0xFFFFFFFFu;
+    auto scan = [&](int z, int y, int x0, int x1) {
+        x0 = max(x0, 0); x1 = min(x1, g.dim[0] - 1);
+        if (z < 0 || z >= g.dim[2] || y < 0 || y >= g.dim[1] || x0 > x1) return;
+        const int64_t base = ((int64_t)z * g.dim[1] + y) * g.dim[0];
+        const int s = __ldg(cell_start + base + x0), e = __ldg(cell_start + base + x1 + 1);
+        for (int j = s; j < e; ++j) {
+            const float4 p = __ldg(s_pos + j);
+            const float d2 = dist2(q.x, q.y, q.z, p.x, p.y, p.z);
+            const uint32_t oi = __float_as_uint(p.w);
+            if (d2 < best || (d2 == best && oi < bidx)) { best = d2; bidx = oi; }
+        }
+    };
+    const int maxdim = max(g.dim[0], max(g.dim[1], g.dim[2]));
+    for (int R = 0; R <= maxdim; ++R) {
+        for (int z = c[2] - R; z <= c[2] + R; ++z)
+            for (int y = c[1] - R; y <= c[1] + R; ++y) {
+                if (abs(z - c[2]) == R || abs(y - c[1]) == R) scan(z, y, c[0] - R, c[0] + R);      // a face row of the shell
+                else { scan(z, y, c[0] - R, c[0] - R); if (R > 0) scan(z, y, c[0] + R, c[0] + R); }   // its two end cells
+            }
+        if (bidx != 0xFFFFFFFFu) {
+            double guard = (double)R * g.cell;
+            guard = guard * guard * (1.0 - 1e-6);
+            if ((double)best < guard) break;
+        }
+    }
+    idx_out[t] = (int32_t)bidx;
+    if (d2_out) d2_out[t] = best;
+}
+
+cudaError_t launch_nearest(kpl_ctx* c, const float4* d_queries, int64_t m, int32_t* d_idx, float* d_d2)
+{
+    if (m == 0) return cudaSuccess;
+    nearest_kernel<<<(unsigned)((m + 127) / 128), 128, 0, c->stream>>>(c->s_pos.p, c->cell_start.p, c->grid, d_queries, m, d_idx, d_d2);
+    c->launches++;
+    return cudaGetLastError();
+}
+
 static int reach_for(const GridDesc& g, double radius)
 {
     return (int)floor(radius * (1.0 + 4.76837158203125e-07) / g.cell) + 1;

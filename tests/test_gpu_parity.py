@@ -359,6 +359,24 @@ def test_cuda_path_against_the_reference_templates(kpl, views, oracle):
     d.close()
 
 
+def test_nearest_point_snap(kpl, views):
+    """TrainDetector's 1-NN snap (main_train_detector.cpp:419-436) against brute force in the same FP32 expression."""
+    xyz = np.ascontiguousarray(views["cheff000"][:20000])
+    rng = np.random.default_rng(3)
+    q = np.concatenate([xyz[rng.choice(len(xyz), 300, replace=False)] + rng.normal(0, 0.4, (300, 3)).astype(np.float32),
+                        xyz[:50],                                                    # exact cloud points
+                        np.float32([[1e4, 0, 0], [-500, -500, -500], [0, 0, 900]])]).astype(np.float32)   # far outside the bounding box
+    d = make_detector(kpl)
+    idx, d2 = d.nearest(xyz, q)
+    for t in range(len(q)):
+        e = q[t] - xyz
+        dd = ((e[:, 0] * e[:, 0]) + e[:, 1] * e[:, 1]) + e[:, 2] * e[:, 2]
+        j = int(np.argmin(dd))                                                       # first minimum = lowest index
+        assert idx[t] == j and d2[t].view(np.uint32) == dd[j].view(np.uint32), t
+    assert np.array_equal(idx[300:350], np.arange(50))
+    d.close()
+
+
 def test_non_maxima_off_returns_every_point(kpl, views, oracle):
     xyz = np.ascontiguousarray(views["cheff001"][:5000])
     d = make_detector(kpl)
