@@ -401,23 +401,16 @@ feature_kernel(const float4* __restrict__ s_pos, const float4* __restrict__ s_nr
                 // its second set of updates is skipped.  (Software-pipelining the loop -- computing the next
                 // pair while the current eight read-modify-writes drain -- was measured slower: 80 registers,
                 // 211 ms vs 204 ms on the 10 M-point scene; capped at 72 registers 215 ms.)
-                while (mask) {
-                    const int m0 = msb_index(mask);                // candidate k sits at bit 31-k: highest bit = smallest k
-                    mask ^= 1u << m0;
-                    const bool two = mask != 0;
-                    const int m1 = two ? msb_index(mask) : m0;
-                    mask &= ~(1u << m1);
-                    const float* t0 = sx31 - m0;
-                    const float* t1 = sx31 - m1;
-                    const uint64_t D = dist2_x2(QX, QY, QZ, pack2(t0[0], t1[0]), pack2(t0[32], t1[32]), pack2(t0[64], t1[64]), P.one2);
+                auto vote_pair = [&](const uint64_t X, const uint64_t Y, const uint64_t Z, const uint64_t NX, const uint64_t NY,
+                                     const uint64_t NZ, const bool two, const bool lane_counts) {
+                    const uint64_t D = dist2_x2(QX, QY, QZ, X, Y, Z, P.one2);
                     // 1 - (n0*m0 + (n1*m1 + n2*m2)), hpp:341-342 with Eigen's reduction order
-                    const uint64_t dot = fma2(mul2(QNX, pack2(t0[96], t1[96])), P.one2,
-                                              fma2(mul2(QNY, pack2(t0[128], t1[128])), P.one2, mul2(QNZ, pack2(t0[160], t1[160]))));
+                    const uint64_t dot = fma2(mul2(QNX, NX), P.one2, fma2(mul2(QNY, NY), P.one2, mul2(QNZ, NZ)));
                     float c0, c1, d0, d1;
                     unpack2(sub2(0x3F8000003F800000ull, dot), c0, c1);
                     unpack2(D, d0, d1);
                     uint64_t DIST = fast_sqrt_x2(D, d0, d1);                                           // hpp:345 sqrt(distances[..])
-                    if (!(fminf(d0, d1) >= FAST_SQRT_LO)) DIST = pack2(__fsqrt_rn(d0), __fsqrt_rn(d1));   // zero / denormal-range d2: rare
+                    if (lane_counts && !(fminf(d0, d1) >= FAST_SQRT_LO)) DIST = pack2(__fsqrt_rn(d0), __fsqrt_rn(d1));   // zero / denormal-range d2: rare
                     const uint64_t COS = pack2(fminf(fmaxf(c0, 0.0f), 2.0f), fminf(fmaxf(c1, 0.0f), 2.0f));   // src/KeypointLearning.cpp:70-73
                     int a0, a1, ap0, ap1, b0, b1, bp0, bp1;
                     uint64_t WA, UA, WB, UB;
@@ -430,6 +423,29 @@ feature_kernel(const float4* __restrict__ s_pos, const float4* __restrict__ s_nr
                     unpack2(mul2(WB, WA), v11a, v11b);
                     vote4(hb, row_bytes, a0, ap0, b0, bp0, v00a, v01a, v10a, v11a);
                     if (two) vote4(hb, row_bytes, a1, ap1, b1, bp1, v00b, v01b, v10b, v11b);
+                };
+                // Interior tiles -- every query of the warp takes every one of the 32 candidates, about a third of
+                // all vote iterations -- need no bit walking: the warp steps through the tile in order and the
+                // candidate pairs come straight out of 64-bit broadcast loads.  Lanes beyond the run's last point
+                // (lane >= nvalid) tag along on NaN queries; their histogram columns are never read.
+                if (__all_sync(0xFFFFFFFFu, valid ? (mask == 0xFFFFFFFFu) : true)) {
+#pragma unroll 2
+                    for (int k = 0; k < 32; k += 2)
+                        vote_pair(*reinterpret_cast<const uint64_t*>(sx + k), *reinterpret_cast<const uint64_t*>(sy + k),
+                                  *reinterpret_cast<const uint64_t*>(sz + k), *reinterpret_cast<const uint64_t*>(snx + k),
+                                  *reinterpret_cast<const uint64_t*>(sny + k), *reinterpret_cast<const uint64_t*>(snz + k), true, valid);
+                    mask = 0;
+                }
+                while (mask) {
+                    const int m0 = msb_index(mask);                // candidate k sits at bit 31-k: highest bit = smallest k
+                    mask ^= 1u << m0;
+                    const bool two = mask != 0;
+                    const int m1 = two ? msb_index(mask) : m0;
+                    mask &= ~(1u << m1);
+                    const float* t0 = sx31 - m0;
+                    const float* t1 = sx31 - m1;
+                    vote_pair(pack2(t0[0], t1[0]), pack2(t0[32], t1[32]), pack2(t0[64], t1[64]),
+                              pack2(t0[96], t1[96]), pack2(t0[128], t1[128]), pack2(t0[160], t1[160]), two, true);
                 }
             } else {
                 while (mask) {
