@@ -102,3 +102,31 @@ def test_plan_is_balanced_and_rejects_thin_slabs():
     assert plan.halo == plan.reach_nms + plan.reach_feat + 1 == 6
     with pytest.raises(ValueError):
         shard.plan_slabs(xyz, R_FEAT, R_NMS, 4, 8)       # 24 cells cannot host 8 slabs of >= 6 cells
+
+
+def test_plan_properties_on_random_clouds():
+    """Cuts are a strictly increasing cover of the cell columns, every slab is at least a halo wide, and the
+    modelled per-rank cost is balanced to within one cell column of points."""
+    sys.path.insert(0, ROOT)
+    from keypoint_learning_b200 import shard
+    rng = np.random.default_rng(11)
+    for trial in range(12):
+        n = int(rng.integers(20_000, 60_000))
+        # clumpy along x: a mixture of slabs of different density, like the closed-surface scene
+        centres = rng.uniform(-400, 400, 6)
+        x = np.concatenate([rng.normal(c, rng.uniform(20, 120), n // 6) for c in centres])
+        xyz = np.stack([x, rng.uniform(-50, 50, len(x)), rng.uniform(-20, 20, len(x))], axis=1).astype(np.float32)
+        world = int(rng.integers(2, 9))
+        try:
+            plan = shard.plan_slabs(xyz, R_FEAT, R_NMS, 4, world)
+        except ValueError:
+            continue                                            # too few columns for that many ranks: rejected, not mis-planned
+        cuts = plan.cuts
+        assert len(cuts) == world + 1 and cuts[0] == 0 and cuts[-1] == plan.dims[0]
+        assert np.all(np.diff(cuts) >= plan.halo)
+        cx = shard.cell_coords(xyz, plan.origin, plan.cell, 0)
+        hist = np.bincount(cx, minlength=int(plan.dims[0]))
+        scored = np.array([hist[max(c0 - plan.reach_nms, 0):c1 + plan.reach_nms].sum() for c0, c1 in zip(cuts[:-1], cuts[1:])])
+        assert scored.max() - scored.min() <= 2.5 * hist.max() + 0.15 * scored.mean(), (trial, world, scored.tolist())
+        owned = np.array([hist[c0:c1].sum() for c0, c1 in zip(cuts[:-1], cuts[1:])])
+        assert owned.sum() == len(xyz)
