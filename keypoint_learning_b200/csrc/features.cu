@@ -34,8 +34,11 @@
 
 namespace kpl {
 
-static constexpr int FEAT_WARPS = 4;       // upper bound; the launch uses FEAT_WARPS_DEFAULT warps per block
-static constexpr int FEAT_WARPS_DEFAULT = 1;   // one warp per block: its shared memory is released the moment it finishes (gpurun_out/sweep2.log)
+// One warp per block: its shared memory is released the moment it finishes (4 / 2 / 1 warps per block measured
+// 219.5 / -- / 204.0 ms on the 10 M-point scene, profiles/r1e_sweep_warps_per_block.txt).  __launch_bounds__(32) also
+// gives ptxas its best allocation: 64 registers without spills (bounds of 128 threads: 64 with spills, 180.0 ms;
+// (32, 28): 71 registers, 181.9 ms; (32): 178.0 ms).
+static constexpr int FEAT_WARPS = 1;
 
 struct FeatParams {
     int n, A, B, F, reach, span;
@@ -571,8 +574,7 @@ cudaError_t launch_features(kpl_ctx* c, int64_t n, bool use_role, bool fuse_fore
     bool fast = false;
     if (!getenv("KPL_NO_FAST_MATH") && (e = fast_math_verdict(c, P, fast))) return e;
     c->fast_math = fast;
-    int wpb = FEAT_WARPS_DEFAULT;
-    if (const char* e = getenv("KPL_FEAT_WARPS")) wpb = std::max(1, std::min(FEAT_WARPS, atoi(e)));   // tuning experiments only
+    const int wpb = FEAT_WARPS;
     size_t smem = (size_t)wpb * (P.F * 32 + 192) * sizeof(float);
     if (smem > 227 * 1024) return cudaErrorInvalidValue;
     auto kern = fast ? feature_kernel<true> : feature_kernel<false>;
