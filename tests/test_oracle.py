@@ -211,6 +211,31 @@ def test_binning_helpers_match_the_reference_build(oracle):
             assert np.array_equal(g.view(np.uint32), r.view(np.uint32)), B
 
 
+def test_binning_helpers_match_the_reference_build_random_shapes(oracle):
+    """hypothesis: arbitrary (n_annulus, support) / n_bins, not just the shapes the detector is used with."""
+    from hypothesis import given, settings, strategies as st
+    if oracle.ref_lib() is None:
+        pytest.skip("oracle/_ref was not built (reference tree not mounted)")
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.integers(1, 64), st.floats(0.015625, 4096.0, allow_nan=False, width=32), st.integers(0, 2**31 - 1))
+    def annulus(A, support, seed):
+        d = np.random.default_rng(seed).uniform(0, support, 2000).astype(np.float32)
+        d = np.minimum(d, np.float32(support))
+        for g, r in zip(oracle.annulus_sweep(A, support, d), oracle.ref_annulus_sweep(A, support, d)):
+            assert np.array_equal(g.view(np.uint32), r.view(np.uint32))
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.integers(1, 64), st.integers(0, 2**31 - 1))
+    def bins(B, seed):
+        c = np.random.default_rng(seed).uniform(-1.0, 3.0, 2000).astype(np.float32)
+        for g, r in zip(oracle.bin_sweep(B, c), oracle.ref_bin_sweep(B, c)):
+            assert np.array_equal(g.view(np.uint32), r.view(np.uint32))
+
+    annulus()
+    bins()
+
+
 # ---------------------------------------------------------------------------------------------
 # oracle/_ref: the reference's OWN detector templates (include/KeypointLearning.h + impl/KeypointLearning.hpp)
 # compiled from the mounted tree against the stand-in environment oracle/ref_stubs/kplref_env.h.  Search,
