@@ -42,7 +42,10 @@ enum kpl_status {
     KPL_E_GRID = 7,           /* uniform grid would exceed 2^31-2 cells / point outside a forced grid     */
     KPL_E_NOMEM = 8,
     KPL_E_IO = 9,
-    KPL_E_UNSUPPORTED = 10
+    KPL_E_UNSUPPORTED = 10,
+    KPL_E_NCCL = 11,          /* NCCL missing (libnccl.so.2 not loadable) or a collective failed              */
+    KPL_E_HALO = 12           /* slab-sharded call: a k-NN normal that an owned point depends on was clipped
+                                 by the slab edge -- widen kpl_slab_plan.normal_support_cells                */
 };
 
 enum kpl_normals_mode {
@@ -74,6 +77,12 @@ typedef struct kpl_params {
     double grid_origin[3];    /*    floor((v - grid_origin)/cell) - grid_offset, which must lie in     */
     int32_t grid_dims[3];     /*    [0, grid_dims); origin is the GLOBAL one so keys order globally    */
     int32_t grid_offset[3];
+    int32_t slab_interior_lo; /* forced grid only: 1 = the cloud continues beyond the low / high x face of the   */
+    int32_t slab_interior_hi; /*    local grid (a slab of a larger cloud): a k-NN normal search that would have   */
+    int32_t slab_guard_cells; /*    to look beyond such a face fails with KPL_E_HALO, except for points in the    */
+                              /*    outermost slab_guard_cells columns at that face (nothing kept depends on them) */
+    int32_t report_fragile;   /* 1: flag the points with a near-split forest decision (kpl_stats.n_fragile_points,
+                                 kpl_fetch_u8 "fragile"); costs ~2 % of the detection, default 0                   */
 } kpl_params;
 
 /* Device-time breakdown of the last detect call (CUDA events on the context stream), ms. */
@@ -99,6 +108,11 @@ typedef struct kpl_stats {
     int64_t n_unscored;       /* points without a finite normal: score NaN, never a keypoint (hpp:277)        */
     int64_t n_near_threshold; /* scored points with |score - threshold| <= 1e-5: the decisions a 1e-5 score
                                  difference against another implementation could flip                         */
+    int64_t n_fragile_points; /* (kpl_params.report_fragile) scored points for which at least one split decided by forest_->predict
+                                 (hpp:281) had |x[var] - thr| <= 1e-5: a feature difference of the tolerated
+                                 size sends that tree the other way and moves the score by 1/ntrees            */
+    int32_t host_syncs;       /* cudaStreamSynchronize calls the last call made                               */
+    int32_t n_views;          /* kpl_detect_batch: views in the call (1 otherwise)                            */
 } kpl_stats;
 
 /* ---- lifetime ------------------------------------------------------------------------------- */
@@ -172,6 +186,21 @@ KPL_API int kpl_radius_neighbors(kpl_ctx* ctx, const float* xyz, int32_t xyz_str
 KPL_API int kpl_detect_device(kpl_ctx* ctx, const void* d_xyz4, const void* d_normals4, const void* d_role, int64_t n,
                               void* d_scores, void* d_kp_idx, int64_t* n_kp_out);
 
+/* ---- a batch of independent views in one pass (BASELINE.json configs[4]) ------------------------ */
+/* TestDetector handles one view per process run (main_test_detector.cpp:142-187); a caller with many small views
+ * (a 200 k-point view is ~1.5 waves of the feature kernel) passes them CONCATENATED: view v is the points
+ * [view_offsets[v], view_offsets[v+1]) of xyz (and of normals when given).  Every view is processed exactly as a
+ * kpl_detect call on it alone would (own bounding box, own canonical grid and accumulation order: bit-identical
+ * scores and keypoints), but all views share one stacked grid, one launch per stage and one set of host round trips.
+ * scores_out: NULL or n floats.  kp_idx_out (capacity n): VIEW-LOCAL keypoint indices, view after view, ascending
+ * inside a view; kp_offsets_out[n_views + 1]: view v's keypoints are kp_idx_out[kp_offsets_out[v] .. kp_offsets_out[v+1]). */
+KPL_API int kpl_detect_batch(kpl_ctx* ctx, const float* xyz, int32_t xyz_stride, const float* normals, int32_t normals_stride,
+                             const int64_t* view_offsets, int32_t n_views, float* scores_out, int32_t* kp_idx_out,
+                             int64_t* kp_offsets_out);
+/* Same with device-resident clouds; view_offsets stays a HOST array, d_kp_offsets is n_views + 1 int64 on the device. */
+KPL_API int kpl_detect_batch_device(kpl_ctx* ctx, const void* d_xyz4, const void* d_normals4, const int64_t* view_offsets,
+                                    int32_t n_views, void* d_scores, void* d_kp_idx, void* d_kp_offsets, int64_t* n_kp_out);
+
 /* ---- introspection --------------------------------------------------------------------------- */
 /* kpl_detect* score each point inside the feature kernel and do not write the A*B feature rows
  * (the cv::Mat of impl/KeypointLearning.hpp:366-369) to memory; on != 0 keeps them for kpl_fetch. */
@@ -181,6 +210,8 @@ KPL_API int kpl_get_stats(const kpl_ctx* ctx, kpl_stats* s);
 /* Device copies of intermediate results of the last call, for parity tests: what = "normals"
  * (n x 4 floats, original order) or "features" (n x A*B floats, original order). */
 KPL_API int kpl_fetch(kpl_ctx* ctx, const char* what, float* out, int64_t capacity_floats);
+/* Byte masks of the last detect call, original order: what = "fragile" (see kpl_stats.n_fragile_points). */
+KPL_API int kpl_fetch_u8(kpl_ctx* ctx, const char* what, uint8_t* out, int64_t capacity);
 
 #ifdef __cplusplus
 }

@@ -46,7 +46,7 @@ def _stale(target: str, deps: list[str]) -> bool:
 
 def build_lib(force: bool = False, verbose: bool = False) -> str:
     srcs = [os.path.join(CSRC, s) for s in CU_SOURCES]
-    deps = srcs + [os.path.join(CSRC, h) for h in ("kpl_internal.h", "kpl_math.cuh")] + [os.path.join(ROOT, "include", "kpl.h"), __file__]
+    deps = srcs + [os.path.join(CSRC, h) for h in ("kpl_internal.h", "kpl_math.cuh", "forest.cuh")] + [os.path.join(ROOT, "include", "kpl.h"), __file__]
     if not force and not _stale(LIB, deps):
         return LIB
     objdir = os.path.join(HERE, "build")

@@ -15,14 +15,16 @@ LIB_PATH = os.path.join(_HERE, "libkpl_b200.so")
 
 KPL_OK = 0
 STATUS = {0: "KPL_OK", 1: "KPL_E_INVALID", 2: "KPL_E_FOREST", 3: "KPL_E_SIZE_MISMATCH", 4: "KPL_E_NONFINITE",
-          5: "KPL_E_VARCOUNT", 6: "KPL_E_CUDA", 7: "KPL_E_GRID", 8: "KPL_E_NOMEM", 9: "KPL_E_IO", 10: "KPL_E_UNSUPPORTED"}
+          5: "KPL_E_VARCOUNT", 6: "KPL_E_CUDA", 7: "KPL_E_GRID", 8: "KPL_E_NOMEM", 9: "KPL_E_IO", 10: "KPL_E_UNSUPPORTED",
+          11: "KPL_E_NCCL", 12: "KPL_E_HALO"}
 NORMALS_GIVEN, NORMALS_KNN, NORMALS_RADIUS = 0, 1, 2
 ROLE_HALO, ROLE_SCORE, ROLE_OWNED = 0, 1, 3
 
 EXPORTS = ["kpl_create", "kpl_destroy", "kpl_last_error", "kpl_version", "kpl_set_stream", "kpl_params_default",
            "kpl_set_params", "kpl_get_params", "kpl_load_forest", "kpl_set_forest", "kpl_forest_info", "kpl_detect",
            "kpl_normals", "kpl_features", "kpl_radius_stats", "kpl_radius_neighbors", "kpl_detect_device",
-           "kpl_get_timings", "kpl_get_stats", "kpl_fetch", "kpl_set_keep_intermediates", "kpl_uniform_sample", "kpl_nearest"]
+           "kpl_get_timings", "kpl_get_stats", "kpl_fetch", "kpl_set_keep_intermediates", "kpl_uniform_sample", "kpl_nearest",
+           "kpl_fetch_u8", "kpl_detect_batch", "kpl_detect_batch_device"]
 
 
 class KplParams(C.Structure):
@@ -31,7 +33,8 @@ class KplParams(C.Structure):
                 ("draws_threshold", C.c_float), ("normals_mode", C.c_int32), ("k_normals", C.c_int32),
                 ("viewpoint", C.c_float * 3), ("flip_normals", C.c_int32), ("cells_per_radius", C.c_int32),
                 ("grid_forced", C.c_int32), ("grid_origin", C.c_double * 3), ("grid_dims", C.c_int32 * 3),
-                ("grid_offset", C.c_int32 * 3)]
+                ("grid_offset", C.c_int32 * 3), ("slab_interior_lo", C.c_int32), ("slab_interior_hi", C.c_int32),
+                ("slab_guard_cells", C.c_int32), ("report_fragile", C.c_int32)]
 
 
 class KplTimings(C.Structure):
@@ -43,7 +46,7 @@ class KplStats(C.Structure):
                 ("n_above_threshold", C.c_int64), ("n_keypoints", C.c_int64), ("grid_cells", C.c_int64),
                 ("grid_dims", C.c_int32 * 3), ("kernel_launches", C.c_int32), ("grid_origin", C.c_double * 3), ("grid_cell", C.c_double),
                 ("fast_math", C.c_int32), ("reserved", C.c_int32), ("n_unscored", C.c_int64),
-                ("n_near_threshold", C.c_int64)]
+                ("n_near_threshold", C.c_int64), ("n_fragile_points", C.c_int64), ("host_syncs", C.c_int32), ("n_views", C.c_int32)]
 
 
 class KplError(RuntimeError):
@@ -88,6 +91,9 @@ def load_library():
     L.kpl_set_keep_intermediates.argtypes = [vp, C.c_int]
     L.kpl_uniform_sample.argtypes = [vp, f32p, C.c_int32, C.c_int64, C.c_float, i32p, i64p]
     L.kpl_nearest.argtypes = [vp, f32p, C.c_int32, C.c_int64, f32p, C.c_int32, C.c_int64, i32p, f32p]
+    L.kpl_fetch_u8.argtypes = [vp, C.c_char_p, u8p, C.c_int64]
+    L.kpl_detect_batch.argtypes = [vp, f32p, C.c_int32, f32p, C.c_int32, i64p, C.c_int32, f32p, i32p, i64p]
+    L.kpl_detect_batch_device.argtypes = [vp, vp, vp, i64p, C.c_int32, vp, vp, vp, i64p]
     _lib = L
     return L
 
@@ -180,13 +186,22 @@ class KeypointLearningDetector:
 
     def setCellsPerRadius(self, cpr): self._p.cells_per_radius = int(cpr)
 
-    def setForcedGrid(self, origin=None, dims=None, offset=(0, 0, 0)):
+    def setReportFragile(self, on=True):
+        """Flag the points whose forest walk decided a split within 1e-5 (stats()["n_fragile_points"], fetchFragile())."""
+        self._p.report_fragile = int(bool(on))
+
+    def setForcedGrid(self, origin=None, dims=None, offset=(0, 0, 0), interior=(False, False), guard_cells=0):
+        """Slab of a larger cloud: the global grid origin, the local dims and the local cell offset.  interior = which x
+        faces of the local grid the cloud continues behind (a clipped k-NN normal search fails with KPL_E_HALO there,
+        except in the outermost guard_cells columns)."""
         if origin is None:
             self._p.grid_forced = 0
             return
         self._p.grid_forced = 1
         for i in range(3):
             self._p.grid_origin[i] = float(origin[i]); self._p.grid_dims[i] = int(dims[i]); self._p.grid_offset[i] = int(offset[i])
+        self._p.slab_interior_lo = int(bool(interior[0])); self._p.slab_interior_hi = int(bool(interior[1]))
+        self._p.slab_guard_cells = int(guard_cells)
 
     def setStream(self, cuda_stream_ptr):
         """Run on a caller-owned cudaStream_t.  0 is the legacy default stream (what torch.cuda.current_stream()
@@ -236,6 +251,51 @@ class KeypointLearningDetector:
         out[:, :3] = xyz[self._kp_idx, :3]
         out[:, 3] = scores[self._kp_idx]
         return out, self._kp_idx
+
+    def computeBatch(self, clouds, normals=None):
+        """kpl_detect_batch: `clouds` is a list of (n_v, >=3) float32 views.  Returns (scores list, keypoint index list),
+        one entry per view, exactly what compute() returns for each view alone."""
+        arrs = [_vec3(c, "cloud")[0] for c in clouds]
+        width = arrs[0].shape[1]
+        if any(a.shape[1] != width for a in arrs):
+            raise ValueError("all views must share one point layout")
+        xyz = np.ascontiguousarray(np.concatenate(arrs)) if len(arrs) > 1 else arrs[0]
+        off = np.zeros(len(arrs) + 1, np.int64)
+        off[1:] = np.cumsum([len(a) for a in arrs])
+        nrm = ns = None
+        if normals is not None:
+            nrm = np.ascontiguousarray(np.concatenate([_vec3(x, "normals")[0] for x in normals]))
+            ns = nrm.shape[1] * 4
+        return self.computeBatchConcat(xyz, off, nrm, ns)
+
+    def computeBatchConcat(self, xyz, offsets, nrm=None, ns=None, scores_out=None, kp_out=None):
+        """kpl_detect_batch on an already concatenated host array (what bench.py times)."""
+        n = xyz.shape[0]
+        nv = len(offsets) - 1
+        self._push()
+        scores = np.empty(n, np.float32) if scores_out is None else scores_out
+        kp = np.empty(max(n, 1), np.int32) if kp_out is None else kp_out
+        kpo = np.empty(nv + 1, np.int64)
+        off = np.ascontiguousarray(offsets, np.int64)
+        self._check(self._L.kpl_detect_batch(self._h, _ptr(xyz, C.c_float), xyz.shape[1] * 4, _ptr(nrm, C.c_float), ns or 0,
+                                             _ptr(off, C.c_int64), nv, _ptr(scores, C.c_float), _ptr(kp, C.c_int32), _ptr(kpo, C.c_int64)))
+        return ([scores[off[v]:off[v + 1]] for v in range(nv)], [kp[kpo[v]:kpo[v + 1]].copy() for v in range(nv)])
+
+    def detectBatchDevice(self, d_xyz4, offsets, d_scores=0, d_kp_idx=0, d_kp_offsets=0, d_normals4=0):
+        """Device-resident batch: raw device pointers (ints), host offsets.  Returns the total keypoint count."""
+        self._push()
+        off = np.ascontiguousarray(offsets, np.int64)
+        nkp = C.c_int64(0)
+        self._check(self._L.kpl_detect_batch_device(self._h, C.c_void_p(d_xyz4), C.c_void_p(d_normals4 or None), _ptr(off, C.c_int64),
+                                                    len(off) - 1, C.c_void_p(d_scores or None), C.c_void_p(d_kp_idx), C.c_void_p(d_kp_offsets),
+                                                    C.byref(nkp)))
+        return nkp.value
+
+    def fetchFragile(self, n):
+        """Per-point mask of the last detection: 1 = a split on the point's forest walk was decided within 1e-5."""
+        out = np.empty(n, np.uint8)
+        self._check(self._L.kpl_fetch_u8(self._h, b"fragile", _ptr(out, C.c_uint8), n))
+        return out
 
     def getKeypointsIndices(self): return self._kp_idx
     def getResponse(self): return self._scores

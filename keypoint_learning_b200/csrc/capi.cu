@@ -8,7 +8,7 @@
 #include "kpl_internal.h"
 
 namespace kpl {
-int pack_forest(const HostForestArrays& in, std::vector<PackedNode>& nodes, std::vector<int32_t>& roots, int& max_depth, std::string& err);
+int pack_forest(const HostForestArrays& in, std::vector<PackedNode>& nodes, std::vector<int32_t>& roots, int& max_depth, int& max_var, std::string& err);
 cudaError_t launch_all_flags(kpl_ctx* c, int64_t n);
 }
 using namespace kpl;
@@ -62,6 +62,9 @@ int kpl_params_default(kpl_params* p)
     p->flip_normals = 0;
     p->cells_per_radius = 4;
     p->grid_forced = 0;
+    p->slab_interior_lo = p->slab_interior_hi = 0;
+    p->slab_guard_cells = 0;
+    p->report_fragile = 0;
     return KPL_OK;
 }
 
@@ -85,7 +88,7 @@ int kpl_create(int device, kpl_ctx** out)
     ctx->stream = ctx->own_stream;
     for (int i = 0; ok && i < 8; ++i) ok = cudaEventCreate(&ctx->ev[i]) == cudaSuccess;
     ok = ok && cudaMalloc((void**)&ctx->d_bbox, 8 * sizeof(uint32_t)) == cudaSuccess;
-    ok = ok && ensure(ctx->counters, 8) == cudaSuccess;
+    ok = ok && ensure(ctx->counters, kpl_ctx::NCOUNTERS) == cudaSuccess;
     if (!ok) { kpl_destroy(ctx); return KPL_E_CUDA; }
     *out = ctx;
     return KPL_OK;
@@ -98,6 +101,8 @@ void kpl_destroy(kpl_ctx* ctx)
     if (ctx->own_stream) cudaStreamSynchronize(ctx->own_stream);
     release(ctx->in_xyz); release(ctx->in_nrm); release(ctx->in_role); release(ctx->s_role);
     release(ctx->key_a); release(ctx->key_b); release(ctx->idx_a); release(ctx->idx_b); release(ctx->cub_tmp);
+    release(ctx->row_warps_n); release(ctx->row_offset_n); release(ctx->fragile); release(ctx->views); release(ctx->layer_view);
+    release(ctx->view_offsets); release(ctx->qlist);
     release(ctx->cell_start); release(ctx->row_warps); release(ctx->row_offset); release(ctx->work); release(ctx->work_n); release(ctx->s_pos); release(ctx->s_nrm); release(ctx->feat);
     release(ctx->s_score); release(ctx->score); release(ctx->flag); release(ctx->s_state); release(ctx->kp_idx);
     release(ctx->scratch_f); release(ctx->scratch_i); release(ctx->counters);
@@ -149,9 +154,9 @@ static int install_forest(kpl_ctx* ctx, const HostForestArrays& H)
 {
     std::vector<PackedNode> nodes;
     std::vector<int32_t> roots;
-    int max_depth = 0;
+    int max_depth = 0, max_var = -1;
     std::string err;
-    int rc = pack_forest(H, nodes, roots, max_depth, err);
+    int rc = pack_forest(H, nodes, roots, max_depth, max_var, err);
     if (rc) return fail(ctx, rc, err);
     if (roots.empty()) return fail(ctx, KPL_E_FOREST, "forest has no trees");
     KPL_CUDA(cudaSetDevice(ctx->device));
@@ -163,7 +168,7 @@ static int install_forest(kpl_ctx* ctx, const HostForestArrays& H)
     KPL_CUDA(cudaMalloc((void**)&F.d_roots, roots.size() * sizeof(int32_t)));
     KPL_CUDA(cudaMemcpy(F.d_nodes, nodes.data(), nodes.size() * sizeof(PackedNode), cudaMemcpyHostToDevice));
     KPL_CUDA(cudaMemcpy(F.d_roots, roots.data(), roots.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
-    F.ntrees = (int32_t)roots.size(); F.nnodes = (int32_t)H.var.size(); F.var_count = H.var_count; F.max_depth = max_depth;
+    F.ntrees = (int32_t)roots.size(); F.nnodes = (int32_t)H.var.size(); F.var_count = H.var_count; F.max_depth = max_depth; F.max_var = max_var;
     F.roots = roots;
     return KPL_OK;
 }
@@ -204,41 +209,143 @@ int kpl_forest_info(const kpl_ctx* ctx, int32_t* ntrees, int32_t* nnodes, int32_
 // ------------------------------------------------------------------------------------------------
 // stage orchestration (device pointers in, device results out)
 // ------------------------------------------------------------------------------------------------
-static int prepare_grid(kpl_ctx* ctx, const float4* d_xyz, const float4* d_nrm, const uint8_t* d_role, int64_t n)
+static const double CELL_PAD = 1.0 + 9.5367431640625e-07;    // 1 + 2^-20: points closer than r never lie more than cells_per_radius cells apart
+static const double REACH_PAD = 1.0 + 4.76837158203125e-07;   // 1 + 2^-21
+
+static void clear_batch(GridDesc& g)
 {
-    const kpl_params& P = ctx->params;
-    KPL_CUDA(launch_bbox(ctx, d_xyz, n, ctx->d_bbox));
-    uint32_t hb[8];
-    KPL_CUDA(cudaMemcpyAsync(hb, ctx->d_bbox, sizeof hb, cudaMemcpyDeviceToHost, ctx->stream));
-    KPL_CUDA(cudaStreamSynchronize(ctx->stream));
-    if (hb[6]) return fail(ctx, KPL_E_NONFINITE, "input cloud holds non-finite points");
+    g.views = nullptr; g.layer_view = nullptr; g.view_offsets = nullptr; g.nviews = 0;
+    g.interior_lo = g.interior_hi = 0; g.guard_cells = 0;
+}
+
+static int finish_grid(kpl_ctx* ctx, int64_t n)
+{
     GridDesc& g = ctx->grid;
-    g.cell = (double)P.radius_features * (1.0 + 9.5367431640625e-07) / (double)P.cells_per_radius;
+    const kpl_params& P = ctx->params;
     double ncells = 1.0;
     for (int a = 0; a < 3; ++a) {
-        double lo = (double)dec_float(hb[a]), hi = (double)dec_float(hb[3 + a]);
-        g.off[a] = 0;
-        if (P.grid_forced) { g.org[a] = P.grid_origin[a]; g.dim[a] = P.grid_dims[a]; g.off[a] = P.grid_offset[a]; }
-        else { g.org[a] = lo; g.dim[a] = (int32_t)std::min(2147483000.0, std::floor((hi - lo) / g.cell) + 1.0); }
         if (g.dim[a] < 1) return fail(ctx, KPL_E_GRID, "bad grid dimensions");
         ncells *= (double)g.dim[a];
     }
     if (ncells > 2147483646.0) return fail(ctx, KPL_E_GRID, "uniform grid would exceed 2^31-2 cells: cloud too sparse for radius_features/cells_per_radius");
     g.ncells = (int64_t)ncells;
-    g.reach_feat = (int)std::floor((double)P.radius_features * (1.0 + 4.76837158203125e-07) / g.cell) + 1;
-    g.reach_nms = (int)std::floor((double)P.radius_nms * (1.0 + 4.76837158203125e-07) / g.cell) + 1;
-    ctx->cur_xyz = d_xyz;
-    ctx->cur_nrm = d_nrm;
-    KPL_CUDA(build_grid(ctx, d_xyz, d_nrm, d_role, n));
-    if (P.grid_forced) {
-        KPL_CUDA(cudaMemcpyAsync(hb, ctx->d_bbox, sizeof hb, cudaMemcpyDeviceToHost, ctx->stream));
-        KPL_CUDA(cudaStreamSynchronize(ctx->stream));
-        if (hb[7]) return fail(ctx, KPL_E_GRID, "a point lies outside the forced grid");
-    }
+    g.reach_feat = (int)std::floor((double)P.radius_features * REACH_PAD / g.cell) + 1;
+    g.reach_nms = (int)std::floor((double)P.radius_nms * REACH_PAD / g.cell) + 1;
     ctx->stats.grid_cells = g.ncells;
     for (int a = 0; a < 3; ++a) { ctx->stats.grid_dims[a] = g.dim[a]; ctx->stats.grid_origin[a] = g.org[a]; }
     ctx->stats.grid_cell = g.cell;
     ctx->last_n = n;
+    return KPL_OK;
+}
+
+// Grid of ONE cloud.  A forced grid (slab of a larger cloud) is known a priori: no bounding-box pass and no host
+// synchronisation; a non-finite point or a point outside the forced grid is reported by the flags cell_key_kernel
+// raises, which finish_call() reads together with the counters.  cell_override > 0 replaces the canonical cell size
+// (kpl_normals sizes its k-NN grid from the data).
+static int prepare_grid(kpl_ctx* ctx, const float4* d_xyz, const float4* d_nrm, const uint8_t* d_role, int64_t n, double cell_override = 0.0)
+{
+    const kpl_params& P = ctx->params;
+    GridDesc& g = ctx->grid;
+    clear_batch(g);
+    g.cell = cell_override > 0.0 ? cell_override : (double)P.radius_features * CELL_PAD / (double)P.cells_per_radius;
+    if (P.grid_forced) {
+        KPL_CUDA(launch_bbox_init(ctx));
+        for (int a = 0; a < 3; ++a) { g.org[a] = P.grid_origin[a]; g.dim[a] = P.grid_dims[a]; g.off[a] = P.grid_offset[a]; }
+        g.interior_lo = P.slab_interior_lo; g.interior_hi = P.slab_interior_hi; g.guard_cells = P.slab_guard_cells;
+    } else {
+        KPL_CUDA(launch_bbox(ctx, d_xyz, n, ctx->d_bbox));
+        uint32_t hb[8];
+        KPL_CUDA(cudaMemcpyAsync(hb, ctx->d_bbox, sizeof hb, cudaMemcpyDeviceToHost, ctx->stream));
+        KPL_CUDA(cudaStreamSynchronize(ctx->stream));
+        ctx->syncs++;
+        if (hb[6]) return fail(ctx, KPL_E_NONFINITE, "input cloud holds non-finite points");
+        for (int a = 0; a < 3; ++a) {
+            const double lo = (double)dec_float(hb[a]), hi = (double)dec_float(hb[3 + a]);
+            g.off[a] = 0; g.org[a] = lo;
+            g.dim[a] = (int32_t)std::min(2147483000.0, std::floor((hi - lo) / g.cell) + 1.0);
+        }
+    }
+    int rc = finish_grid(ctx, n);
+    if (rc) return rc;
+    ctx->cur_xyz = d_xyz;
+    ctx->cur_nrm = d_nrm;
+    KPL_CUDA(build_grid(ctx, d_xyz, d_nrm, d_role, n));
+    return KPL_OK;
+}
+
+// Grid of a batch of independent views (kpl_detect_batch): view v keeps the cells of its own canonical grid (origin =
+// its bounding-box minimum) and occupies the z layers [zoff_v, zoff_v + dimz_v) of one stacked grid; `pad` empty
+// layers separate two views, so no radius search of any kernel can pair points of different views, and the k-NN
+// search is confined to the view's own layers (normals.cu: LocalGrid).  One host synchronisation for all boxes.
+static int prepare_grid_batch(kpl_ctx* ctx, const float4* d_xyz, const float4* d_nrm, int64_t n, const int64_t* h_offsets, int nviews)
+{
+    const kpl_params& P = ctx->params;
+    GridDesc& g = ctx->grid;
+    clear_batch(g);
+    g.cell = (double)P.radius_features * CELL_PAD / (double)P.cells_per_radius;
+    KPL_CUDA(ensure(ctx->view_offsets, (size_t)nviews + 1));
+    KPL_CUDA(ensure(ctx->views, (size_t)nviews));
+    KPL_CUDA(ensure(ctx->scratch_i, (size_t)nviews * 8 + 16));
+    KPL_CUDA(cudaMemcpyAsync(ctx->view_offsets.p, h_offsets, ((size_t)nviews + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
+    KPL_CUDA(launch_bbox_init(ctx));
+    uint32_t* d_boxes = (uint32_t*)ctx->scratch_i.p;
+    KPL_CUDA(launch_bbox_views(ctx, d_xyz, n, ctx->view_offsets.p, nviews, d_boxes));
+    std::vector<uint32_t> hb((size_t)nviews * 8);
+    KPL_CUDA(cudaMemcpyAsync(hb.data(), d_boxes, hb.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    KPL_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->syncs++;
+    const int reach_f = (int)std::floor((double)P.radius_features * REACH_PAD / g.cell) + 1;
+    const int reach_n = (int)std::floor((double)P.radius_nms * REACH_PAD / g.cell) + 1;
+    const int pad = std::max(std::max(reach_f, reach_n), 1);
+    std::vector<ViewDesc> hv((size_t)nviews);
+    int64_t z = 0;
+    int dimx = 1, dimy = 1;
+    for (int v = 0; v < nviews; ++v) {
+        const uint32_t* b = hb.data() + (size_t)v * 8;
+        if (b[6]) return fail(ctx, KPL_E_NONFINITE, "a view of the batch holds non-finite points");
+        int d[3];
+        for (int a = 0; a < 3; ++a) {
+            const double lo = (double)dec_float(b[a]), hi = (double)dec_float(b[3 + a]);
+            hv[(size_t)v].org[a] = lo;
+            d[a] = (int)std::min(2147483000.0, std::floor((hi - lo) / g.cell) + 1.0);
+        }
+        dimx = std::max(dimx, d[0]); dimy = std::max(dimy, d[1]);
+        hv[(size_t)v].zoff = (int32_t)z; hv[(size_t)v].dimz = d[2];
+        z += (int64_t)d[2] + pad;
+        if (z > 2147483000ll) return fail(ctx, KPL_E_GRID, "the stacked grid of the batch exceeds 2^31 layers");
+    }
+    g.dim[0] = dimx; g.dim[1] = dimy; g.dim[2] = (int32_t)(z - pad);
+    for (int a = 0; a < 3; ++a) { g.off[a] = 0; g.org[a] = hv[0].org[a]; }
+    int rc = finish_grid(ctx, n);
+    if (rc) return rc;
+    std::vector<int32_t> layer((size_t)g.dim[2], -1);
+    for (int v = 0; v < nviews; ++v)
+        for (int l = 0; l < hv[(size_t)v].dimz; ++l) layer[(size_t)hv[(size_t)v].zoff + l] = v;
+    KPL_CUDA(ensure(ctx->layer_view, layer.size()));
+    KPL_CUDA(cudaMemcpyAsync(ctx->views.p, hv.data(), hv.size() * sizeof(ViewDesc), cudaMemcpyHostToDevice, ctx->stream));
+    KPL_CUDA(cudaMemcpyAsync(ctx->layer_view.p, layer.data(), layer.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    KPL_CUDA(cudaStreamSynchronize(ctx->stream));      // hv / layer are stack-lifetime host buffers
+    ctx->syncs++;
+    g.views = ctx->views.p; g.layer_view = ctx->layer_view.p; g.view_offsets = ctx->view_offsets.p; g.nviews = nviews;
+    ctx->cur_xyz = d_xyz;
+    ctx->cur_nrm = d_nrm;
+    KPL_CUDA(build_grid(ctx, d_xyz, d_nrm, nullptr, n));
+    return KPL_OK;
+}
+
+// Warp work lists of the normal / feature kernels for the grid in place: ONE host synchronisation for both.
+static int prepare_lists(kpl_ctx* ctx, bool normals_given, bool want_features)
+{
+    const kpl_params& P = ctx->params;
+    int span_n = -1;
+    if (!normals_given) {
+        if (P.normals_mode == KPL_NORMALS_KNN) span_n = normals_knn_uses_work_list(P) ? 1 : -1;
+        else if (P.normals_mode == KPL_NORMALS_RADIUS) span_n = P.cells_per_radius;
+    }
+    const int span_f = want_features ? feature_span(P) : -1;
+    ctx->nwarps_norm = ctx->nwarps_feat = 0;
+    if (span_n < 0 && span_f < 0) return KPL_OK;
+    KPL_CUDA(build_work_lists(ctx, span_n, span_f));
     return KPL_OK;
 }
 
@@ -247,11 +354,8 @@ static int prepare_normals(kpl_ctx* ctx, bool given, int64_t n)
     const kpl_params& P = ctx->params;
     if (!given) {
         if (P.normals_mode == KPL_NORMALS_KNN) KPL_CUDA(launch_normals_knn(ctx, n));
-        else if (P.normals_mode == KPL_NORMALS_RADIUS) {
-            cudaError_t e = launch_normals_radius(ctx, n);
-            if (e == cudaErrorNotSupported) return fail(ctx, KPL_E_UNSUPPORTED, "radius-mode normals are not implemented yet");
-            KPL_CUDA(e);
-        } else return fail(ctx, KPL_E_SIZE_MISMATCH, "normals_mode is GIVEN but no normals were passed");
+        else if (P.normals_mode == KPL_NORMALS_RADIUS) KPL_CUDA(launch_normals_radius(ctx, n));
+        else return fail(ctx, KPL_E_SIZE_MISMATCH, "normals_mode is GIVEN but no normals were passed");
         if (P.flip_normals) KPL_CUDA(launch_flip_normals(ctx, n));
     }
     ctx->last_has_normals = true;
@@ -261,53 +365,86 @@ static int prepare_normals(kpl_ctx* ctx, bool given, int64_t n)
 static void begin_call(kpl_ctx* ctx)
 {
     ctx->launches = 0;
+    ctx->syncs = 0;
     ctx->err.clear();
-    ctx->last_has_normals = ctx->last_has_features = false;
+    ctx->last_has_normals = ctx->last_has_features = ctx->last_has_fragile = false;
     memset(&ctx->timings, 0, sizeof ctx->timings);
     memset(&ctx->stats, 0, sizeof ctx->stats);
+    ctx->stats.n_views = 1;
 }
 
-static int run_detect(kpl_ctx* ctx, const float4* d_xyz, const float4* d_nrm, const uint8_t* d_role, int64_t n,
-                      float* d_scores_out, int32_t* d_kp_out, int64_t* n_kp_out)
+namespace kpl {
+
+int detect_check(kpl_ctx* ctx, int64_t n, bool sharded)
 {
     const kpl_params& P = ctx->params;
-    begin_call(ctx);
-    if (n_kp_out) *n_kp_out = 0;
     if (n < 0 || n > 2147483000ll) return fail(ctx, KPL_E_INVALID, "point count out of range");
     if (ctx->forest.ntrees < 1) return fail(ctx, KPL_E_FOREST, "no forest loaded");
-    if (P.draws_remove && P.non_maxima && d_role)
+    if (P.draws_remove && P.non_maxima && sharded)
         return fail(ctx, KPL_E_UNSUPPORTED, "draws-remove NMS walks the whole cloud in index order (hpp:233-250): not available for slab-sharded calls");
     const int F = P.n_annulus * P.n_bins;
     if (ctx->forest.var_count > 0 && ctx->forest.var_count != F) return fail(ctx, KPL_E_VARCOUNT, "annuli*bins does not match the forest's var_count");
-    ctx->stats.n_points = n;
-    if (n == 0) return KPL_OK;
-    KPL_CUDA(cudaSetDevice(ctx->device));
-    KPL_CUDA(cudaMemsetAsync(ctx->counters.p, 0, 8 * sizeof(unsigned long long), ctx->stream));
-    KPL_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
-    int rc = prepare_grid(ctx, d_xyz, d_nrm, d_role, n);
+    // whatever var_count says, no split may read beyond the A*B floats of a feature row
+    if (ctx->forest.max_var >= F) return fail(ctx, KPL_E_VARCOUNT, "the forest splits on a variable index >= annuli*bins");
+    return KPL_OK;
+}
+
+// Phase A of a detection: grid (already built by the caller), normals, features + forest -> scores of every point
+// whose role asks for one.  Events 1..4 bracket the stages.
+int detect_score_phase(kpl_ctx* ctx, bool normals_given, bool use_role, int64_t n)
+{
+    const kpl_params& P = ctx->params;
+    const int F = P.n_annulus * P.n_bins;
+    int rc = prepare_lists(ctx, normals_given, true);
     if (rc) return rc;
     KPL_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
-    rc = prepare_normals(ctx, d_nrm != nullptr, n);
+    rc = prepare_normals(ctx, normals_given, n);
     if (rc) return rc;
-    KPL_CUDA(launch_check_normals(ctx, n));
+    KPL_CUDA(launch_check_normals(ctx, n, use_role));
     KPL_CUDA(cudaEventRecord(ctx->ev[2], ctx->stream));
-    // the forest is evaluated in the tail of the feature kernel; KPL_NO_FUSE=1 keeps the two-kernel path for A/B tests
-    const bool fuse = getenv("KPL_NO_FUSE") == nullptr;
+    bool fuse = true;      // the forest is evaluated in the tail of the feature kernel
+#ifdef KPL_EXPERIMENTS
+    fuse = getenv("KPL_NO_FUSE") == nullptr;
+#endif
     const bool rows = ctx->keep_intermediates || !fuse;
-    KPL_CUDA(launch_features(ctx, n, d_role != nullptr, fuse, rows));
+    KPL_CUDA(launch_features(ctx, n, use_role, fuse, rows));
     ctx->last_has_features = rows; ctx->last_F = F;
+    ctx->last_has_fragile = fuse && P.report_fragile != 0;
     KPL_CUDA(cudaEventRecord(ctx->ev[3], ctx->stream));
-    if (!fuse) KPL_CUDA(launch_forest(ctx, n, d_role != nullptr));
+#ifdef KPL_EXPERIMENTS
+    if (!fuse) KPL_CUDA(launch_forest(ctx, n, use_role));
+#endif
     KPL_CUDA(cudaEventRecord(ctx->ev[4], ctx->stream));
-    if (P.non_maxima && P.draws_remove) KPL_CUDA(launch_nms_draws(ctx, n, d_role != nullptr));
-    else if (P.non_maxima) KPL_CUDA(launch_nms(ctx, n, d_role != nullptr));
+    return KPL_OK;
+}
+
+// Phase B: threshold + NMS over the scores in place, ascending keypoint indices into d_kp_out.
+int detect_nms_phase(kpl_ctx* ctx, bool use_role, int64_t n, int32_t* d_kp_out)
+{
+    const kpl_params& P = ctx->params;
+    if (P.non_maxima && P.draws_remove) KPL_CUDA(launch_nms_draws(ctx, n, use_role));
+    else if (P.non_maxima) KPL_CUDA(launch_nms(ctx, n, use_role));
     else KPL_CUDA(launch_all_flags(ctx, n));
     KPL_CUDA(launch_compact(ctx, n, d_kp_out));
-    if (d_scores_out) KPL_CUDA(cudaMemcpyAsync(d_scores_out, ctx->score.p, (size_t)n * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+    return KPL_OK;
+}
+
+// End of a call: counters and grid flags to the host (the one unavoidable synchronisation), stats and timings.
+int detect_finish(kpl_ctx* ctx, int64_t n, int64_t* n_kp_out)
+{
     KPL_CUDA(cudaEventRecord(ctx->ev[5], ctx->stream));
-    unsigned long long hc[8];
+    unsigned long long hc[kpl_ctx::NCOUNTERS];
+    uint32_t hb[8];
     KPL_CUDA(cudaMemcpyAsync(hc, ctx->counters.p, sizeof hc, cudaMemcpyDeviceToHost, ctx->stream));
+    KPL_CUDA(cudaMemcpyAsync(hb, ctx->d_bbox, sizeof hb, cudaMemcpyDeviceToHost, ctx->stream));
     KPL_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->syncs++;
+    if (ctx->params.grid_forced && hb[7]) return fail(ctx, KPL_E_GRID, "a point lies outside the forced grid (or is not finite)");
+    if (hc[9]) {
+        char b[256];
+        snprintf(b, sizeof b, "%llu k-NN normals that kept points depend on were clipped by a slab face: widen normal_support_cells", hc[9]);
+        return fail(ctx, KPL_E_HALO, b);
+    }
     const int32_t nkp = (int32_t)(hc[3] & 0xFFFFFFFFull);
     if (n_kp_out) *n_kp_out = nkp;
     kpl_timings& T = ctx->timings;
@@ -318,10 +455,70 @@ static int run_detect(kpl_ctx* ctx, const float4* d_xyz, const float4* d_nrm, co
     cudaEventElapsedTime(&T.nms_ms, ctx->ev[4], ctx->ev[5]);
     cudaEventElapsedTime(&T.total_ms, ctx->ev[0], ctx->ev[5]);
     kpl_stats& S = ctx->stats;
+    S.n_points = n;
     S.feature_pairs = (int64_t)hc[0]; S.candidate_pairs = (int64_t)hc[1]; S.n_above_threshold = (int64_t)hc[2];
-    S.n_keypoints = nkp; S.kernel_launches = ctx->launches; S.n_scored = n; S.n_unscored = (int64_t)hc[4]; S.fast_math = ctx->fast_math ? 1 : 0;
-    S.n_near_threshold = (int64_t)hc[7];
+    S.n_keypoints = nkp; S.kernel_launches = ctx->launches; S.n_scored = (int64_t)hc[5]; S.n_unscored = (int64_t)hc[4];
+    S.fast_math = ctx->fast_math ? 1 : 0;
+    S.n_near_threshold = (int64_t)hc[7]; S.n_fragile_points = (int64_t)hc[8];
+    S.host_syncs = ctx->syncs;
     return KPL_OK;
+}
+
+int detect_begin(kpl_ctx* ctx)
+{
+    KPL_CUDA(cudaSetDevice(ctx->device));
+    KPL_CUDA(cudaMemsetAsync(ctx->counters.p, 0, kpl_ctx::NCOUNTERS * sizeof(unsigned long long), ctx->stream));
+    KPL_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
+    return KPL_OK;
+}
+
+int detect_grid_phase(kpl_ctx* ctx, const float4* d_xyz, const float4* d_nrm, const uint8_t* d_role, int64_t n)
+{
+    return prepare_grid(ctx, d_xyz, d_nrm, d_role, n);
+}
+
+}  // namespace kpl
+
+static int run_detect(kpl_ctx* ctx, const float4* d_xyz, const float4* d_nrm, const uint8_t* d_role, int64_t n,
+                      float* d_scores_out, int32_t* d_kp_out, int64_t* n_kp_out)
+{
+    begin_call(ctx);
+    if (n_kp_out) *n_kp_out = 0;
+    int rc = detect_check(ctx, n, d_role != nullptr);
+    if (rc) return rc;
+    ctx->stats.n_points = n;
+    if (n == 0) return KPL_OK;
+    if ((rc = detect_begin(ctx))) return rc;
+    if ((rc = prepare_grid(ctx, d_xyz, d_nrm, d_role, n))) return rc;
+    if ((rc = detect_score_phase(ctx, d_nrm != nullptr, d_role != nullptr, n))) return rc;
+    if ((rc = detect_nms_phase(ctx, d_role != nullptr, n, d_kp_out))) return rc;
+    if (d_scores_out) KPL_CUDA(cudaMemcpyAsync(d_scores_out, ctx->score.p, (size_t)n * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+    return detect_finish(ctx, n, n_kp_out);
+}
+
+// A batch of independent views in ONE pass: one stacked grid, one work list, one launch per stage, per-view
+// keypoint ranges -- a 200 k-point view alone is 1.5 waves of the feature kernel and a handful of host round trips.
+static int run_detect_batch(kpl_ctx* ctx, const float4* d_xyz, const float4* d_nrm, int64_t n, const int64_t* h_offsets, int nviews,
+                            float* d_scores_out, int32_t* d_kp_out, int64_t* d_kp_offsets_out, int64_t* n_kp_out)
+{
+    begin_call(ctx);
+    if (n_kp_out) *n_kp_out = 0;
+    int rc = detect_check(ctx, n, false);
+    if (rc) return rc;
+    if (ctx->params.grid_forced) return fail(ctx, KPL_E_INVALID, "a forced grid cannot be combined with a batch of views");
+    if (ctx->params.draws_remove && ctx->params.non_maxima)
+        return fail(ctx, KPL_E_UNSUPPORTED, "draws-remove NMS is not available for batched calls");
+    ctx->stats.n_points = n; ctx->stats.n_views = nviews;
+    if (n == 0) return KPL_OK;
+    if ((rc = detect_begin(ctx))) return rc;
+    if ((rc = prepare_grid_batch(ctx, d_xyz, d_nrm, n, h_offsets, nviews))) return rc;
+    if ((rc = detect_score_phase(ctx, d_nrm != nullptr, false, n))) return rc;
+    if ((rc = detect_nms_phase(ctx, false, n, d_kp_out))) return rc;
+    KPL_CUDA(launch_view_ranges(ctx, n, d_kp_out, ctx->view_offsets.p, nviews, d_kp_offsets_out));
+    if (d_scores_out) KPL_CUDA(cudaMemcpyAsync(d_scores_out, ctx->score.p, (size_t)n * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+    rc = detect_finish(ctx, n, n_kp_out);
+    ctx->stats.n_views = nviews;
+    return rc;
 }
 
 // host (possibly strided) -> device float4 staging
@@ -380,6 +577,106 @@ int kpl_detect_device(kpl_ctx* ctx, const void* d_xyz4, const void* d_normals4, 
                       (int32_t*)d_kp_idx, n_kp_out);
 }
 
+// Forced grids skip the bounding-box round trip (prepare_grid): entry points other than kpl_detect* read the
+// out-of-grid flag here.
+static int check_forced_grid(kpl_ctx* ctx)
+{
+    if (!ctx->params.grid_forced) return KPL_OK;
+    uint32_t hb[8];
+    KPL_CUDA(cudaMemcpyAsync(hb, ctx->d_bbox, sizeof hb, cudaMemcpyDeviceToHost, ctx->stream));
+    KPL_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->syncs++;
+    if (hb[7]) return fail(ctx, KPL_E_GRID, "a point lies outside the forced grid (or is not finite)");
+    return KPL_OK;
+}
+
+// The k-NN search is exact on any grid, so a stand-alone kpl_normals call (TestDetector runs the normal estimation
+// before the detector exists, main_test_detector.cpp:162-169, and knows no radiusFeatures there) sizes its grid from
+// the data: about KNN_TARGET points per occupied cell, whatever the unit of the cloud.
+static const double KNN_TARGET = 14.0;
+
+static int prepare_knn_grid(kpl_ctx* ctx, int64_t n)
+{
+    const kpl_params& P = ctx->params;
+    if (P.grid_forced || P.normals_mode != KPL_NORMALS_KNN) return prepare_grid(ctx, ctx->in_xyz.p, nullptr, nullptr, n);
+    // first guess from the bounding box as if the points filled it; surfaces and curves then show far more points per
+    // occupied cell than wanted, and the cell is refined from the measured occupancy (occupancy ~ cell^2 on a surface)
+    KPL_CUDA(launch_bbox(ctx, ctx->in_xyz.p, n, ctx->d_bbox));
+    uint32_t hb[8];
+    KPL_CUDA(cudaMemcpyAsync(hb, ctx->d_bbox, sizeof hb, cudaMemcpyDeviceToHost, ctx->stream));
+    KPL_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->syncs++;
+    if (hb[6]) return fail(ctx, KPL_E_NONFINITE, "input cloud holds non-finite points");
+    double ext[3], vol = 1.0, longest = 0.0;
+    for (int a = 0; a < 3; ++a) { ext[a] = (double)dec_float(hb[3 + a]) - (double)dec_float(hb[a]); longest = std::max(longest, ext[a]); }
+    if (!(longest > 0.0)) longest = 1.0;                                   // all points coincide: any cell will do
+    for (int a = 0; a < 3; ++a) vol *= std::max(ext[a], longest * 1e-3);
+    const double k = (double)std::max(P.k_normals, 1);
+    const double target = KNN_TARGET * k / 10.0;
+    const double min_cell = std::cbrt(vol / 1.0e9) * 1.001 + longest * 1e-7;  // at most ~1e9 cells
+    double cell = std::max(std::cbrt(vol * target / (double)n), min_cell);
+    for (int pass = 0; pass < 3; ++pass) {
+        int rc = prepare_grid(ctx, ctx->in_xyz.p, nullptr, nullptr, n, cell);
+        if (rc) return rc;
+        if (pass == 2) break;
+        KPL_CUDA(cudaMemsetAsync(ctx->counters.p + 10, 0, sizeof(unsigned long long), ctx->stream));
+        KPL_CUDA(launch_count_occupied_cells(ctx, n, ctx->counters.p + 10));
+        unsigned long long occupied = 0;
+        KPL_CUDA(cudaMemcpyAsync(&occupied, ctx->counters.p + 10, sizeof occupied, cudaMemcpyDeviceToHost, ctx->stream));
+        KPL_CUDA(cudaStreamSynchronize(ctx->stream));
+        ctx->syncs++;
+        const double occ = (double)n / (double)std::max<unsigned long long>(occupied, 1);
+        if (occ <= 3.0 * target || cell <= min_cell) break;
+        cell = std::max(cell * std::sqrt(target / occ), min_cell);
+    }
+    return KPL_OK;
+}
+
+static int check_view_offsets(kpl_ctx* ctx, const int64_t* view_offsets, int32_t n_views, int64_t& n)
+{
+    if (n_views < 1 || !view_offsets) return fail(ctx, KPL_E_INVALID, "view_offsets / n_views missing");
+    if (view_offsets[0] != 0) return fail(ctx, KPL_E_INVALID, "view_offsets[0] must be 0");
+    for (int32_t v = 0; v < n_views; ++v)
+        if (view_offsets[v + 1] <= view_offsets[v]) return fail(ctx, KPL_E_INVALID, "view_offsets must be strictly ascending (empty views are not allowed)");
+    n = view_offsets[n_views];
+    return KPL_OK;
+}
+
+int kpl_detect_batch(kpl_ctx* ctx, const float* xyz, int32_t xyz_stride, const float* normals, int32_t normals_stride,
+                     const int64_t* view_offsets, int32_t n_views, float* scores_out, int32_t* kp_idx_out, int64_t* kp_offsets_out)
+{
+    if (!ctx) return KPL_E_INVALID;
+    if (!kp_idx_out || !kp_offsets_out) return fail(ctx, KPL_E_INVALID, "kp_idx_out / kp_offsets_out is NULL");
+    int64_t n = 0;
+    int rc = check_view_offsets(ctx, view_offsets, n_views, n);
+    if (rc) return rc;
+    if ((rc = upload_inputs(ctx, xyz, xyz_stride, normals, normals_stride, nullptr, n))) return rc;
+    KPL_CUDA(ensure(ctx->kp_idx, (size_t)n));
+    KPL_CUDA(ensure(ctx->scratch_f, ((size_t)n_views + 1) * 2 + 16));
+    int64_t* d_kpo = reinterpret_cast<int64_t*>(ctx->scratch_f.p);
+    int64_t nkp = 0;
+    rc = run_detect_batch(ctx, ctx->in_xyz.p, normals ? ctx->in_nrm.p : nullptr, n, view_offsets, n_views, nullptr, ctx->kp_idx.p, d_kpo, &nkp);
+    if (rc) return rc;
+    if (scores_out) KPL_CUDA(cudaMemcpyAsync(scores_out, ctx->score.p, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    if (nkp > 0) KPL_CUDA(cudaMemcpyAsync(kp_idx_out, ctx->kp_idx.p, (size_t)nkp * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    KPL_CUDA(cudaMemcpyAsync(kp_offsets_out, d_kpo, ((size_t)n_views + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    KPL_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->syncs++; ctx->stats.host_syncs = ctx->syncs;
+    return KPL_OK;
+}
+
+int kpl_detect_batch_device(kpl_ctx* ctx, const void* d_xyz4, const void* d_normals4, const int64_t* view_offsets, int32_t n_views,
+                            void* d_scores, void* d_kp_idx, void* d_kp_offsets, int64_t* n_kp_out)
+{
+    if (!ctx) return KPL_E_INVALID;
+    if (!d_xyz4 || !d_kp_idx || !d_kp_offsets) return fail(ctx, KPL_E_INVALID, "NULL device pointer");
+    int64_t n = 0;
+    int rc = check_view_offsets(ctx, view_offsets, n_views, n);
+    if (rc) return rc;
+    return run_detect_batch(ctx, (const float4*)d_xyz4, (const float4*)d_normals4, n, view_offsets, n_views, (float*)d_scores,
+                            (int32_t*)d_kp_idx, (int64_t*)d_kp_offsets, n_kp_out);
+}
+
 int kpl_normals(kpl_ctx* ctx, const float* xyz, int32_t xyz_stride, int64_t n, float* normals_out)
 {
     if (!ctx || (n > 0 && !normals_out)) return KPL_E_INVALID;
@@ -388,16 +685,23 @@ int kpl_normals(kpl_ctx* ctx, const float* xyz, int32_t xyz_stride, int64_t n, f
     if (ctx->params.normals_mode == KPL_NORMALS_GIVEN) return fail(ctx, KPL_E_INVALID, "normals_mode must be KNN or RADIUS");
     int rc = upload_inputs(ctx, xyz, xyz_stride, nullptr, 0, nullptr, n);
     if (rc) return rc;
-    if ((rc = prepare_grid(ctx, ctx->in_xyz.p, nullptr, nullptr, n))) return rc;
+    KPL_CUDA(cudaMemsetAsync(ctx->counters.p, 0, kpl_ctx::NCOUNTERS * sizeof(unsigned long long), ctx->stream));
+    if ((rc = prepare_knn_grid(ctx, n))) return rc;
+    if ((rc = check_forced_grid(ctx))) return rc;
+    if ((rc = prepare_lists(ctx, false, false))) return rc;
     if ((rc = prepare_normals(ctx, false, n))) return rc;
     KPL_CUDA(ensure(ctx->scratch_f, (size_t)n * 4));
     KPL_CUDA(launch_unsort_normals(ctx, n, (float4*)ctx->scratch_f.p));
     KPL_CUDA(cudaMemcpyAsync(normals_out, ctx->scratch_f.p, (size_t)n * 16, cudaMemcpyDeviceToHost, ctx->stream));
     KPL_CUDA(cudaStreamSynchronize(ctx->stream));
-    ctx->stats.kernel_launches = ctx->launches;
+    ctx->syncs++;
+    ctx->stats.n_points = n; ctx->stats.kernel_launches = ctx->launches; ctx->stats.host_syncs = ctx->syncs;
     return KPL_OK;
 }
 
+// computePointsForTrainingFeatures (hpp:299-318).  With an index subset (TrainDetector's pattern: a few thousand
+// samples of a large cloud, main_train_detector.cpp:419-439) only the listed queries are evaluated and only m x F
+// floats are ever materialised.
 int kpl_features(kpl_ctx* ctx, const float* xyz, int32_t xyz_stride, const float* normals, int32_t normals_stride,
                  int64_t n, const int32_t* indices, int64_t m, float* features_out)
 {
@@ -405,40 +709,43 @@ int kpl_features(kpl_ctx* ctx, const float* xyz, int32_t xyz_stride, const float
     begin_call(ctx);
     if (!indices && m != n) return fail(ctx, KPL_E_INVALID, "indices == NULL requires m == n");
     if (n == 0 || m == 0) return KPL_OK;
+    if (m > 2147483000ll) return fail(ctx, KPL_E_INVALID, "too many feature indices");
     const int F = ctx->params.n_annulus * ctx->params.n_bins;
-    std::vector<uint8_t> role;
-    if (indices) {
-        role.assign((size_t)n, 0);
-        for (int64_t k = 0; k < m; ++k) {
+    if (indices)
+        for (int64_t k = 0; k < m; ++k)
             if (indices[k] < 0 || indices[k] >= n) return fail(ctx, KPL_E_INVALID, "feature index out of range");
-            role[(size_t)indices[k]] = KPL_ROLE_SCORE;
-        }
-    }
-    int rc = upload_inputs(ctx, xyz, xyz_stride, normals, normals_stride, indices ? role.data() : nullptr, n);
+    int rc = upload_inputs(ctx, xyz, xyz_stride, normals, normals_stride, nullptr, n);
     if (rc) return rc;
-    KPL_CUDA(cudaMemsetAsync(ctx->counters.p, 0, 8 * sizeof(unsigned long long), ctx->stream));
-    if ((rc = prepare_grid(ctx, ctx->in_xyz.p, normals ? ctx->in_nrm.p : nullptr, indices ? ctx->in_role.p : nullptr, n))) return rc;
+    KPL_CUDA(cudaMemsetAsync(ctx->counters.p, 0, kpl_ctx::NCOUNTERS * sizeof(unsigned long long), ctx->stream));
+    if ((rc = prepare_grid(ctx, ctx->in_xyz.p, normals ? ctx->in_nrm.p : nullptr, nullptr, n))) return rc;
+    if ((rc = check_forced_grid(ctx))) return rc;
+    if ((rc = prepare_lists(ctx, normals != nullptr, indices == nullptr))) return rc;
     if ((rc = prepare_normals(ctx, normals != nullptr, n))) return rc;
-    KPL_CUDA(launch_features(ctx, n, indices != nullptr, false, true));
-    ctx->last_has_features = true; ctx->last_F = F;
-    KPL_CUDA(ensure(ctx->scratch_f, (size_t)n * F + (size_t)m * F));
-    float* d_orig = ctx->scratch_f.p;
-    KPL_CUDA(launch_unsort_rows(ctx, ctx->feat.p, n, F, d_orig));
-    const float* d_src = d_orig;
+    const float* d_src = nullptr;
     if (indices) {
-        KPL_CUDA(ensure(ctx->scratch_i, (size_t)m));
-        KPL_CUDA(cudaMemcpyAsync(ctx->scratch_i.p, indices, (size_t)m * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
-        float* d_sel = d_orig + (size_t)n * F;
-        KPL_CUDA(launch_gather_rows(ctx, d_orig, ctx->scratch_i.p, m, F, d_sel));
-        d_src = d_sel;
+        KPL_CUDA(ensure(ctx->in_role, (size_t)m * sizeof(int32_t)));          // the role staging buffer is free here
+        int32_t* d_idx = reinterpret_cast<int32_t*>(ctx->in_role.p);
+        KPL_CUDA(cudaMemcpyAsync(d_idx, indices, (size_t)m * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+        KPL_CUDA(build_query_list(ctx, n, d_idx, m));
+        KPL_CUDA(launch_features(ctx, n, false, false, true, ctx->qlist.p, m));
+        KPL_CUDA(ensure(ctx->scratch_f, (size_t)m * F));
+        KPL_CUDA(launch_scatter_rows(ctx, ctx->feat.p, m, F, ctx->scratch_f.p));
+        d_src = ctx->scratch_f.p;
+    } else {
+        KPL_CUDA(launch_features(ctx, n, false, false, true));
+        ctx->last_has_features = true; ctx->last_F = F;
+        KPL_CUDA(ensure(ctx->scratch_f, (size_t)n * F));
+        KPL_CUDA(launch_unsort_rows(ctx, ctx->feat.p, n, F, ctx->scratch_f.p));
+        d_src = ctx->scratch_f.p;
     }
     KPL_CUDA(cudaMemcpyAsync(features_out, d_src, (size_t)m * F * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
-    unsigned long long hc[8];
+    unsigned long long hc[kpl_ctx::NCOUNTERS];
     KPL_CUDA(cudaMemcpyAsync(hc, ctx->counters.p, sizeof hc, cudaMemcpyDeviceToHost, ctx->stream));
     KPL_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->syncs++;
     ctx->stats.fast_math = ctx->fast_math ? 1 : 0;
-    ctx->stats.n_points = n; ctx->stats.n_scored = m; ctx->stats.feature_pairs = (int64_t)hc[0]; ctx->stats.candidate_pairs = (int64_t)hc[1];
-    ctx->stats.kernel_launches = ctx->launches;
+    ctx->stats.n_points = n; ctx->stats.n_scored = (int64_t)hc[5]; ctx->stats.feature_pairs = (int64_t)hc[0]; ctx->stats.candidate_pairs = (int64_t)hc[1];
+    ctx->stats.kernel_launches = ctx->launches; ctx->stats.host_syncs = ctx->syncs;
     return KPL_OK;
 }
 
@@ -450,6 +757,7 @@ int kpl_radius_stats(kpl_ctx* ctx, const float* xyz, int32_t xyz_stride, int64_t
     int rc = upload_inputs(ctx, xyz, xyz_stride, nullptr, 0, nullptr, n);
     if (rc) return rc;
     if ((rc = prepare_grid(ctx, ctx->in_xyz.p, nullptr, nullptr, n))) return rc;
+    if ((rc = check_forced_grid(ctx))) return rc;
     KPL_CUDA(ensure(ctx->scratch_i, (size_t)n * 3 + 2));
     int32_t* d_counts = ctx->scratch_i.p;
     unsigned long long* d_hash = (unsigned long long*)(ctx->scratch_i.p + ((n + 1) & ~1ll));
@@ -471,6 +779,7 @@ int kpl_nearest(kpl_ctx* ctx, const float* xyz, int32_t xyz_stride, int64_t n, c
     int rc = upload_inputs(ctx, xyz, xyz_stride, nullptr, 0, nullptr, n);
     if (rc) return rc;
     if ((rc = prepare_grid(ctx, ctx->in_xyz.p, nullptr, nullptr, n))) return rc;
+    if ((rc = check_forced_grid(ctx))) return rc;
     if ((rc = upload_vec3(ctx, ctx->in_nrm, queries, q_stride, m))) return rc;          // the normals staging buffer is free here
     KPL_CUDA(ensure(ctx->scratch_i, (size_t)m + 2));
     KPL_CUDA(ensure(ctx->scratch_f, (size_t)m + 2));
@@ -493,6 +802,7 @@ int kpl_radius_neighbors(kpl_ctx* ctx, const float* xyz, int32_t xyz_stride, int
     int rc = upload_inputs(ctx, xyz, xyz_stride, nullptr, 0, nullptr, n);
     if (rc) return rc;
     if ((rc = prepare_grid(ctx, ctx->in_xyz.p, nullptr, nullptr, n))) return rc;
+    if ((rc = check_forced_grid(ctx))) return rc;
     KPL_CUDA(ensure(ctx->scratch_i, (size_t)n + 2));
     KPL_CUDA(launch_radius_stats(ctx, n, radius, ctx->scratch_i.p, nullptr));
     std::vector<int32_t> counts((size_t)n), sidx((size_t)n);
@@ -553,6 +863,21 @@ int kpl_uniform_sample(kpl_ctx* ctx, const float* xyz, int32_t xyz_stride, int64
     KPL_CUDA(cudaStreamSynchronize(ctx->stream));
     *m_out = m;
     ctx->stats.n_points = n; ctx->stats.kernel_launches = ctx->launches;
+    return KPL_OK;
+}
+
+int kpl_fetch_u8(kpl_ctx* ctx, const char* what, uint8_t* out, int64_t capacity)
+{
+    if (!ctx || !what || !out) return KPL_E_INVALID;
+    const int64_t n = ctx->last_n;
+    if (n <= 0) return fail(ctx, KPL_E_INVALID, "nothing to fetch");
+    if (strcmp(what, "fragile")) return fail(ctx, KPL_E_INVALID, "unknown fetch target");
+    if (capacity < n) return fail(ctx, KPL_E_INVALID, "fetch buffer too small");
+    if (!ctx->last_has_fragile || ctx->fragile.cap < (size_t)n)
+        return fail(ctx, KPL_E_INVALID, "the last call did not report fragile splits (kpl_params.report_fragile)");
+    KPL_CUDA(cudaSetDevice(ctx->device));
+    KPL_CUDA(cudaMemcpyAsync(out, ctx->fragile.p, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    KPL_CUDA(cudaStreamSynchronize(ctx->stream));
     return KPL_OK;
 }
 

@@ -57,6 +57,7 @@ struct FusedForest {
     int ntrees;
     float* s_score;   // sorted order
     float* score;     // original order
+    uint8_t* fragile; // original order: 1 = some split on the point's walks was decided within 1e-5 (forest.cuh)
 };
 
 __device__ __forceinline__ void key_to_cell_f(uint32_t key, int dimx, int dimy, int& cx, int& cy, int& cz)
@@ -249,10 +250,11 @@ __device__ __forceinline__ void vote4(unsigned hb, unsigned row_bytes, int a, in
     sts_f32(rp + op, __fadd_rn(lds_f32(rp + op), v11));
 }
 
-template <bool FAST>
+template <bool FAST, bool FRAGILE>
 __global__ void __launch_bounds__(FEAT_WARPS * 32)
 feature_kernel(const float4* __restrict__ s_pos, const float4* __restrict__ s_nrm, const uint32_t* __restrict__ skey,
                const int32_t* __restrict__ cell_start, const uint8_t* __restrict__ s_role, const int2* __restrict__ work, int nwarps,
+               const int32_t* __restrict__ qlist, int nlist,
                int dimx, int dimy, int dimz, FeatParams P, FusedForest FF, float* __restrict__ feat,
                unsigned long long* __restrict__ counters)
 {
@@ -265,18 +267,23 @@ feature_kernel(const float4* __restrict__ s_pos, const float4* __restrict__ s_nr
 
     const int w = blockIdx.x * (blockDim.x >> 5) + warp;
     if (w >= nwarps) return;
-    const int2 item = __ldg(work + w);                       // up to 32 consecutive sorted points of one run
+    // work list: up to 32 consecutive sorted points of one run.  Query list (computePointsForTrainingFeatures on an
+    // index subset, hpp:299-318): 32 consecutive entries of the ascending list of sorted positions; the group loop
+    // below copes with lanes that lie in different cell rows.  q0 is also the first output row of the warp.
+    const int2 item = qlist ? make_int2(w * 32, min(32, nlist - w * 32)) : __ldg(work + w);
     const int q0 = item.x, nvalid = item.y;
-    const int q = q0 + lane;
     const bool valid = lane < nvalid;
+    const int q = qlist ? (valid ? __ldg(qlist + q0 + lane) : 0) : q0 + lane;
     bool active = valid;
     if (active && s_role) active = (s_role[q] & 1) != 0;
     if (!__any_sync(0xFFFFFFFFu, active)) {
         if (feat)
             for (int e = lane; e < nvalid * P.F; e += 32) feat[(int64_t)q0 * P.F + e] = 0.0f;
         if (FF.nodes && valid) {
+            const uint32_t orig = __float_as_uint(__ldg(&s_pos[q].w));
             FF.s_score[q] = CUDART_NAN_F;
-            FF.score[__float_as_uint(__ldg(&s_pos[q].w))] = CUDART_NAN_F;
+            FF.score[orig] = CUDART_NAN_F;
+            if (FRAGILE) FF.fragile[orig] = 0;
         }
         return;
     }
@@ -489,12 +496,17 @@ feature_kernel(const float4* __restrict__ s_pos, const float4* __restrict__ s_nr
     }
     __syncwarp();
     // fused forest: score = 1 - sum/ntrees (hpp:281-287); unscored points (halo role, no finite normal) get NaN
+    unsigned nfragile = 0;
     if (FF.nodes) {
-        const float sc = active ? forest_score(hist + lane, 32, FF.nodes, FF.roots, FF.ntrees) : CUDART_NAN_F;
+        bool fragile = false;
+        const float sc = active ? forest_score<FRAGILE>(hist + lane, 32, FF.nodes, FF.roots, FF.ntrees, fragile) : CUDART_NAN_F;
         if (valid) {
+            const uint32_t orig = __float_as_uint(__ldg(&s_pos[q].w));
             FF.s_score[q] = sc;
-            FF.score[__float_as_uint(__ldg(&s_pos[q].w))] = sc;
+            FF.score[orig] = sc;
+            if (FRAGILE) FF.fragile[orig] = (active && fragile) ? 1 : 0;
         }
+        if (FRAGILE) nfragile = __popc(__ballot_sync(0xFFFFFFFFu, active && fragile));
     }
     // coalesced store of the warp's 32 rows (row-major, sorted order)
     if (feat) {
@@ -506,9 +518,12 @@ feature_kernel(const float4* __restrict__ s_pos, const float4* __restrict__ s_nr
         }
     }
     npairs = __reduce_add_sync(0xFFFFFFFFu, npairs);
+    const unsigned nscored = __popc(__ballot_sync(0xFFFFFFFFu, active));
     if (lane == 0) {
+        atomicAdd(counters + 5, (unsigned long long)nscored);
         atomicAdd(counters + 0, (unsigned long long)npairs);
         atomicAdd(counters + 1, (unsigned long long)ncand * 32ull);
+        if (nfragile) atomicAdd(counters + 8, (unsigned long long)nfragile);
     }
 }
 
@@ -542,13 +557,21 @@ static cudaError_t fast_math_verdict(kpl_ctx* c, const FeatParams& P, bool& fast
     return cudaGetLastError();
 }
 
-cudaError_t launch_features(kpl_ctx* c, int64_t n, bool use_role, bool fuse_forest, bool store_rows)
+// cells a warp's run may span in x beyond its first: 1/2/3/4 measured 197/192/190/189 ms (10 M points, 4 cells per radius)
+int feature_span(const kpl_params& U)
+{
+#ifdef KPL_EXPERIMENTS
+    if (const char* e = getenv("KPL_FEAT_SPAN")) return atoi(e);
+#endif
+    return U.cells_per_radius;
+}
+
+cudaError_t launch_features(kpl_ctx* c, int64_t n, bool use_role, bool fuse_forest, bool store_rows, const int32_t* d_qlist, int64_t m_list)
 {
     const kpl_params& U = c->params;
     FeatParams P;
     P.n = (int)n; P.A = U.n_annulus; P.B = U.n_bins; P.F = P.A * P.B; P.reach = c->grid.reach_feat;
-    P.span = U.cells_per_radius;                // cells a warp's run may span in x beyond its first: 1/2/3/4 measured 197/192/190/189 ms (10 M points)
-    if (const char* e = getenv("KPL_FEAT_SPAN")) P.span = atoi(e);   // tuning experiments only
+    P.span = feature_span(U);
     const double r = (double)U.radius_features;
     P.r2 = (float)(r * r);                       // static_cast<float>(radius*radius), KdTreeFLANN::radiusSearch
     P.support = (float)r;                        // findAnnulusPair(.., (float)search_radius_, ..) hpp:345
@@ -565,27 +588,36 @@ cudaError_t launch_features(kpl_ctx* c, int64_t n, bool use_role, bool fuse_fore
     P.adim2 = dup(P.adim); P.nadim2 = dup(-P.adim); P.ainv2 = dup(P.ainv); P.ahalf2 = dup(P.ahalf);
     P.bdim2 = dup(P.bdim); P.nbdim2 = dup(-P.bdim); P.binv2 = dup(P.binv); P.bhalf2 = dup(P.bhalf);
     cudaError_t e;
-    if (store_rows && (e = ensure(c->feat, (size_t)n * P.F))) return e;
-    FusedForest FF = {nullptr, nullptr, 0, nullptr, nullptr};
+    if (d_qlist && (fuse_forest || !store_rows)) return cudaErrorInvalidValue;
+    if (store_rows && (e = ensure(c->feat, (size_t)(d_qlist ? m_list : n) * P.F))) return e;
+    FusedForest FF = {nullptr, nullptr, 0, nullptr, nullptr, nullptr};
     if (fuse_forest) {
-        if ((e = ensure(c->s_score, n)) || (e = ensure(c->score, n))) return e;
-        FF = {c->forest.d_nodes, c->forest.d_roots, c->forest.ntrees, c->s_score.p, c->score.p};
+        if ((e = ensure(c->s_score, n)) || (e = ensure(c->score, n)) || (e = ensure(c->fragile, n))) return e;
+        FF = {c->forest.d_nodes, c->forest.d_roots, c->forest.ntrees, c->s_score.p, c->score.p, c->fragile.p};
     }
     bool fast = false;
-    if (!getenv("KPL_NO_FAST_MATH") && (e = fast_math_verdict(c, P, fast))) return e;
+    bool try_fast = true;
+#ifdef KPL_EXPERIMENTS
+    try_fast = getenv("KPL_NO_FAST_MATH") == nullptr;
+#endif
+    if (try_fast && (e = fast_math_verdict(c, P, fast))) return e;
     c->fast_math = fast;
     const int wpb = FEAT_WARPS;
     size_t smem = (size_t)wpb * (P.F * 32 + 192) * sizeof(float);
     if (smem > 227 * 1024) return cudaErrorInvalidValue;
-    auto kern = fast ? feature_kernel<true> : feature_kernel<false>;
+    // the near-split report (kpl_params.report_fragile) costs ~2 % of the kernel: a separate instantiation
+    const bool frag = fuse_forest && U.report_fragile != 0;
+    auto kern = fast ? (frag ? feature_kernel<true, true> : feature_kernel<true, false>)
+                     : (frag ? feature_kernel<false, true> : feature_kernel<false, false>);
     // per device and per process state of the runtime: set it on every launch that needs it (a host-side call)
     if (smem > 48 * 1024 && (e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return e;
-    int warps = 0;
-    if ((e = build_work_list(c, P.span, c->work, warps))) return e;
+    // the work list was built by the caller (build_work_lists: one host synchronisation for all lists of the call)
+    const int warps = d_qlist ? (int)((m_list + 31) / 32) : c->nwarps_feat;
     if (warps == 0) return cudaSuccess;
     int blocks = (warps + wpb - 1) / wpb;
     kern<<<blocks, wpb * 32, smem, c->stream>>>(c->s_pos.p, c->s_nrm.p, c->key_b.p, c->cell_start.p,
                                                        use_role ? c->s_role.p : nullptr, c->work.p, warps,
+                                                       d_qlist, (int)m_list,
                                                        c->grid.dim[0], c->grid.dim[1], c->grid.dim[2], P, FF,
                                                        store_rows ? c->feat.p : nullptr, c->counters.p);
     c->launches++;

@@ -7,12 +7,16 @@
 // conflicts for the data-dependent var), and four trees are walked concurrently per thread so four
 // independent node loads are in flight (the node arrays live in L2 / L1).
 #include <algorithm>
+#include <cmath>
 #include "kpl_internal.h"
 #include "kpl_math.cuh"
 #include "forest.cuh"
 
 namespace kpl {
 
+#ifdef KPL_EXPERIMENTS
+// Stand-alone form of the forest stage (the product path evaluates the forest in the tail of feature_kernel):
+// kept for A/B measurements of the fusion only.
 static constexpr int FOREST_THREADS = 128;
 
 __global__ void __launch_bounds__(FOREST_THREADS)
@@ -41,7 +45,8 @@ forest_kernel(const float* __restrict__ feat, const PackedNode* __restrict__ nod
         score[orig] = CUDART_NAN_F;
         return;
     }
-    const float sc = forest_score(sf + tid, FOREST_THREADS, nodes, roots, ntrees);
+    bool fragile = false;
+    const float sc = forest_score<false>(sf + tid, FOREST_THREADS, nodes, roots, ntrees, fragile);
     s_score[i] = sc;
     score[orig] = sc;
     (void)counters;
@@ -62,6 +67,7 @@ cudaError_t launch_forest(kpl_ctx* c, int64_t n, bool use_role)
     c->launches++;
     return cudaGetLastError();
 }
+#endif  // KPL_EXPERIMENTS
 
 // Host side: arbitrary (roots,var,thr,left,right,value) arrays -> 32-byte BLOCKS of four PackedNodes
 // {P, L, R, unused}: a node P of even depth together with its two children.  One 32-byte sector -- the unit
@@ -71,10 +77,10 @@ cudaError_t launch_forest(kpl_ctx* c, int64_t n, bool use_role)
 //   L.packed = var | (offset << 10)     block of L's left child = this block + offset, L's right child the next block
 //   R.packed likewise for R's children; a leaf child has var 1023 and its value in thr.
 // `nodes` is the flat array of 4 * nblocks PackedNodes.
-int pack_forest(const HostForestArrays& in, std::vector<PackedNode>& nodes, std::vector<int32_t>& roots, int& max_depth, std::string& err)
+int pack_forest(const HostForestArrays& in, std::vector<PackedNode>& nodes, std::vector<int32_t>& roots, int& max_depth, int& max_var, std::string& err)
 {
     const int32_t nn = (int32_t)in.var.size();
-    nodes.clear(); roots.clear(); max_depth = 0;
+    nodes.clear(); roots.clear(); max_depth = 0; max_var = -1;
     struct Item { int32_t src, block, depth; };
     std::vector<Item> queue;
     const PackedNode empty = {0.f, KPL_LEAF_VAR};
@@ -93,6 +99,8 @@ int pack_forest(const HostForestArrays& in, std::vector<PackedNode>& nodes, std:
             const size_t b = (size_t)it.block * 4;
             if (in.var[it.src] < 0) { nodes[b] = PackedNode{in.value[it.src], KPL_LEAF_VAR}; continue; }
             if (in.var[it.src] >= (int32_t)KPL_LEAF_VAR) { err = "forest: variable index >= 1023"; return KPL_E_FOREST; }
+            if (!std::isfinite(in.thr[it.src])) { err = "forest: non-finite split threshold"; return KPL_E_FOREST; }
+            max_var = std::max(max_var, in.var[it.src]);
             nodes[b] = PackedNode{in.thr[it.src], (uint32_t)in.var[it.src]};
             const int32_t kids[2] = {in.left[it.src], in.right[it.src]};
             for (int side = 0; side < 2; ++side) {
@@ -104,6 +112,8 @@ int pack_forest(const HostForestArrays& in, std::vector<PackedNode>& nodes, std:
                 const int32_t first = (int32_t)(nodes.size() / 4);
                 const int64_t off = (int64_t)first - it.block;
                 if (off >= (1 << 22)) { err = "forest: tree larger than 2^22 blocks"; return KPL_E_FOREST; }
+                if (!std::isfinite(in.thr[c])) { err = "forest: non-finite split threshold"; return KPL_E_FOREST; }
+                max_var = std::max(max_var, in.var[c]);
                 nodes[b + 1 + side] = PackedNode{in.thr[c], (uint32_t)in.var[c] | ((uint32_t)off << 10)};
                 nodes.insert(nodes.end(), 8, empty);
                 queue.push_back({in.left[c], first, it.depth + 2});

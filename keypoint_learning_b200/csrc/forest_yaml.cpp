@@ -7,6 +7,7 @@
 // splits are rejected.
 #include <zlib.h>
 #include <cctype>
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include "kpl_internal.h"
@@ -38,6 +39,7 @@ int parse_forest_yaml(const char* path, HostForestArrays& F, std::string& err)
     bool cur_has_var = false, cur_has_thr = false, in_trees = false;
     long declared_ntrees = -1, is_classifier = 1;
     std::vector<long> var_idx;
+    std::vector<uint8_t> has_thr;
     const char* s = txt.c_str();
     const size_t L = txt.size();
     size_t i = 0;
@@ -79,6 +81,7 @@ int parse_forest_yaml(const char* path, HostForestArrays& F, std::string& err)
         } else if (key == "depth") {
             if (F.roots.empty()) { err = "forest: node outside a tree"; return KPL_E_FOREST; }
             cur = (int32_t)F.var.size();
+            has_thr.push_back(0);
             F.var.push_back(-1); F.thr.push_back(0.f); F.left.push_back(-1); F.right.push_back(-1); F.value.push_back(0.f);
             cur_has_var = cur_has_thr = false;
             if (!stack.empty()) {
@@ -90,8 +93,10 @@ int parse_forest_yaml(const char* path, HostForestArrays& F, std::string& err)
             F.value[cur] = (float)num;
         } else if (key == "var" && cur >= 0 && has_num) {
             if (!cur_has_var) { F.var[cur] = (int32_t)num; cur_has_var = true; stack.push_back({cur, 0}); }
-        } else if (key == "le" && cur >= 0 && has_num) {
-            if (!cur_has_thr) { F.thr[cur] = (float)num; cur_has_thr = true; }
+        } else if (key == "le" && cur >= 0) {
+            // `.Inf` / `.Nan` thresholds are not numbers strtod accepts: refuse them instead of keeping 0
+            if (!has_num || !std::isfinite(num)) { err = "forest: non-numeric or non-finite 'le' threshold"; return KPL_E_FOREST; }
+            if (!cur_has_thr) { F.thr[cur] = (float)num; cur_has_thr = true; has_thr[(size_t)cur] = 1; }
         } else if (key == "gt" || key == "in" || key == "not_in") {
             err = "forest: unsupported split type '" + key + "' (only ordered 'le' splits)"; return KPL_E_FOREST;
         }
@@ -104,6 +109,8 @@ int parse_forest_yaml(const char* path, HostForestArrays& F, std::string& err)
         if (var_idx[k] != (long)k) { err = "forest: non-identity var_idx is not supported"; return KPL_E_FOREST; }
     for (size_t k = 0; k < F.var.size(); ++k)
         if (F.var[k] >= 0 && (F.left[k] < 0 || F.right[k] < 0)) { err = "forest: internal node without two children"; return KPL_E_FOREST; }
+    for (size_t k = 0; k < F.var.size(); ++k)
+        if (F.var[k] >= 0 && !has_thr[k]) { err = "forest: split without an 'le' threshold"; return KPL_E_FOREST; }
     return KPL_OK;
 }
 

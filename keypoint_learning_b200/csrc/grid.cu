@@ -70,6 +70,72 @@ cudaError_t launch_bbox(kpl_ctx* c, const float4* xyz, int64_t n, float* d_bbox)
     return cudaGetLastError();
 }
 
+// view of point i: the last v with view_offsets[v] <= i
+__device__ __forceinline__ int view_of_point(const int64_t* __restrict__ view_offsets, int nviews, int64_t i)
+{
+    int lo = 0, hi = nviews - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (__ldg(view_offsets + mid) <= i) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+// Per-view bounding boxes of a batch: bbox[8 * v + ..] laid out like the single-cloud box.
+__global__ void __launch_bounds__(256) bbox_views_kernel(const float4* __restrict__ xyz, int64_t n, const int64_t* __restrict__ view_offsets,
+                                                         int nviews, uint32_t* __restrict__ bbox)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const bool in = i < n;
+    int v = -1;
+    uint32_t e[3] = {0u, 0u, 0u};
+    bool bad = false;
+    if (in) {
+        v = view_of_point(view_offsets, nviews, i);
+        const float4 p = __ldg(xyz + i);
+        bad = !(isfinite(p.x) && isfinite(p.y) && isfinite(p.z));
+        e[0] = enc_float(p.x); e[1] = enc_float(p.y); e[2] = enc_float(p.z);
+    }
+    // the lanes of a warp almost always share one view: one set of atomics per warp then
+    const int v0 = __shfl_sync(0xFFFFFFFFu, v, 0);
+    if (__all_sync(0xFFFFFFFFu, v == v0 && !bad)) {
+        uint32_t lo[3], hi[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { lo[a] = __reduce_min_sync(0xFFFFFFFFu, e[a]); hi[a] = __reduce_max_sync(0xFFFFFFFFu, e[a]); }
+        if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+            for (int a = 0; a < 3; ++a) { atomicMin(bbox + 8 * v0 + a, lo[a]); atomicMax(bbox + 8 * v0 + 3 + a, hi[a]); }
+        }
+    } else if (in) {
+        if (bad) atomicOr(bbox + 8 * v + 6, 1u);
+        else {
+#pragma unroll
+            for (int a = 0; a < 3; ++a) { atomicMin(bbox + 8 * v + a, e[a]); atomicMax(bbox + 8 * v + 3 + a, e[a]); }
+        }
+    }
+}
+
+__global__ void bbox_views_init_kernel(uint32_t* bbox, int nviews)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < nviews * 8) bbox[t] = ((t & 7) < 3) ? 0xFFFFFFFFu : 0u;
+}
+
+cudaError_t launch_bbox_views(kpl_ctx* c, const float4* xyz, int64_t n, const int64_t* d_view_offsets, int nviews, uint32_t* d_bbox)
+{
+    bbox_views_init_kernel<<<(nviews * 8 + 255) / 256, 256, 0, c->stream>>>(d_bbox, nviews);
+    bbox_views_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(xyz, n, d_view_offsets, nviews, d_bbox);
+    c->launches += 2;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_bbox_init(kpl_ctx* c)
+{
+    bbox_init_kernel<<<1, 32, 0, c->stream>>>((uint32_t*)c->d_bbox);
+    c->launches++;
+    return cudaGetLastError();
+}
+
 __global__ void __launch_bounds__(256) cell_key_kernel(const float4* __restrict__ xyz, int64_t n, GridDesc g,
                                                        uint32_t* __restrict__ keys, uint32_t* __restrict__ idx,
                                                        uint32_t* __restrict__ bbox_flags)
@@ -80,11 +146,19 @@ __global__ void __launch_bounds__(256) cell_key_kernel(const float4* __restrict_
     float v[3] = {p.x, p.y, p.z};
     int cc[3];
     bool out = false;
+    double org[3] = {g.org[0], g.org[1], g.org[2]};
+    int lo[3] = {0, 0, 0}, hi[3] = {g.dim[0] - 1, g.dim[1] - 1, g.dim[2] - 1};
+    int zoff = 0;
+    if (g.views) {                                   // batch: the point's cell in its own view grid, stacked along z
+        const ViewDesc* V = g.views + view_of_point(g.view_offsets, g.nviews, i);
+        org[0] = V->org[0]; org[1] = V->org[1]; org[2] = V->org[2];
+        zoff = V->zoff; lo[2] = V->zoff; hi[2] = V->zoff + V->dimz - 1;
+    }
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
-        double q = floor(__ddiv_rn(__dsub_rn((double)v[a], g.org[a]), g.cell)) - (double)g.off[a];
-        if (!(q >= 0.0)) { out = true; q = 0.0; }
-        if (q > (double)(g.dim[a] - 1)) { out = true; q = (double)(g.dim[a] - 1); }
+        double q = floor(__ddiv_rn(__dsub_rn((double)v[a], org[a]), g.cell)) - (double)g.off[a] + (a == 2 ? (double)zoff : 0.0);
+        if (!(q >= (double)lo[a])) { out = true; q = (double)lo[a]; }
+        if (q > (double)hi[a]) { out = true; q = (double)hi[a]; }
         cc[a] = (int)q;
     }
     if (out) atomicOr(bbox_flags + 7, 1u);
@@ -190,28 +264,144 @@ __global__ void __launch_bounds__(128) run_list_kernel(const int32_t* __restrict
     if (!FILL) row_warps[row] = warps;
 }
 
-// Builds the list for the current grid into `work` (device) and returns the number of warps.
-cudaError_t build_work_list(kpl_ctx* c, int span, DevBuf<int2>& work, int& nwarps)
+// Builds the work lists of the normal kernels (span_n) and the feature kernel (span_f) for the grid in place;
+// a negative span skips that list.  Both totals come back with ONE host synchronisation.
+cudaError_t build_work_lists(kpl_ctx* c, int span_n, int span_f)
 {
     const GridDesc& g = c->grid;
     const int64_t nrows = (int64_t)g.dim[1] * g.dim[2];
-    cudaError_t e;
-    if ((e = ensure(c->row_warps, (size_t)nrows + 1)) || (e = ensure(c->row_offset, (size_t)nrows + 1))) return e;
     const unsigned blocks = (unsigned)((nrows + 127) / 128);
-    run_list_kernel<false><<<blocks, 128, 0, c->stream>>>(c->cell_start.p, g.dim[0], nrows, span, c->row_warps.p, nullptr, nullptr);
+    cudaError_t e;
+    struct L { int span; DevBuf<int32_t>* rw; DevBuf<int32_t>* ro; DevBuf<int2>* work; int* total; };
+    L lists[2] = {{span_n, &c->row_warps_n, &c->row_offset_n, &c->work_n, &c->nwarps_norm},
+                  {span_f, &c->row_warps, &c->row_offset, &c->work, &c->nwarps_feat}};
     size_t bytes = 0;
-    cub::DeviceScan::ExclusiveSum(nullptr, bytes, c->row_warps.p, c->row_offset.p, (int)nrows + 1, c->stream);
+    cub::DeviceScan::ExclusiveSum(nullptr, bytes, (int32_t*)nullptr, (int32_t*)nullptr, (int)nrows + 1, c->stream);
     if ((e = ensure(c->cub_tmp, bytes))) return e;
-    bytes = c->cub_tmp.cap;
-    if ((e = cudaMemsetAsync(c->row_warps.p + nrows, 0, sizeof(int32_t), c->stream))) return e;
-    if ((e = cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, bytes, c->row_warps.p, c->row_offset.p, (int)nrows + 1, c->stream))) return e;
-    int32_t total = 0;
-    if ((e = cudaMemcpyAsync(&total, c->row_offset.p + nrows, sizeof total, cudaMemcpyDeviceToHost, c->stream))) return e;
+    int32_t total[2] = {0, 0};
+    for (int k = 0; k < 2; ++k) {
+        L& l = lists[k];
+        *l.total = 0;
+        if (l.span < 0) continue;
+        if ((e = ensure(*l.rw, (size_t)nrows + 1)) || (e = ensure(*l.ro, (size_t)nrows + 1))) return e;
+        run_list_kernel<false><<<blocks, 128, 0, c->stream>>>(c->cell_start.p, g.dim[0], nrows, l.span, l.rw->p, nullptr, nullptr);
+        if ((e = cudaMemsetAsync(l.rw->p + nrows, 0, sizeof(int32_t), c->stream))) return e;
+        size_t tmp = c->cub_tmp.cap;
+        if ((e = cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, tmp, l.rw->p, l.ro->p, (int)nrows + 1, c->stream))) return e;
+        if ((e = cudaMemcpyAsync(&total[k], l.ro->p + nrows, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream))) return e;
+        c->launches += 3;
+    }
     if ((e = cudaStreamSynchronize(c->stream))) return e;
-    if ((e = ensure(work, (size_t)total + 1))) return e;
-    run_list_kernel<true><<<blocks, 128, 0, c->stream>>>(c->cell_start.p, g.dim[0], nrows, span, nullptr, c->row_offset.p, work.p);
-    c->launches += 4;
-    nwarps = total;
+    c->syncs++;
+    for (int k = 0; k < 2; ++k) {
+        L& l = lists[k];
+        if (l.span < 0 || total[k] == 0) continue;
+        if ((e = ensure(*l.work, (size_t)total[k] + 1))) return e;
+        run_list_kernel<true><<<blocks, 128, 0, c->stream>>>(c->cell_start.p, g.dim[0], nrows, l.span, nullptr, l.ro->p, l.work->p);
+        *l.total = total[k];
+        c->launches++;
+    }
+    return cudaGetLastError();
+}
+
+// ---- occupied cells (kpl_normals sizes its k-NN grid from the data) ---------------------------------------
+__global__ void __launch_bounds__(256) count_heads_kernel(const uint32_t* __restrict__ skey, int64_t n, unsigned long long* __restrict__ out)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const bool head = i < n && (i == 0 || skey[i - 1] != skey[i]);
+    const unsigned m = __ballot_sync(0xFFFFFFFFu, head);
+    if (m && (threadIdx.x & 31) == 0) atomicAdd(out, (unsigned long long)__popc(m));
+}
+cudaError_t launch_count_occupied_cells(kpl_ctx* c, int64_t n, unsigned long long* d_out)
+{
+    count_heads_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->key_b.p, n, d_out);
+    c->launches++;
+    return cudaGetLastError();
+}
+
+// ---- query lists (computePointsForTrainingFeatures on an index subset, hpp:299-318) -----------------------
+// indices[m] (original order) -> qlist[m]: their sorted positions in ascending order, perm[m]: the caller's row of
+// each list entry.  Only n + O(m) words of scratch: nothing of size n x F is ever allocated for a subset.
+__global__ void __launch_bounds__(256) inverse_perm_kernel(const uint32_t* __restrict__ sidx, int64_t n, int32_t* __restrict__ inv)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) inv[sidx[i]] = (int32_t)i;
+}
+__global__ void __launch_bounds__(256) query_pos_kernel(const int32_t* __restrict__ indices, int64_t m, const int32_t* __restrict__ inv,
+                                                        uint32_t* __restrict__ qpos, uint32_t* __restrict__ row)
+{
+    const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (k < m) { qpos[k] = (uint32_t)inv[indices[k]]; row[k] = (uint32_t)k; }
+}
+__global__ void __launch_bounds__(256) scatter_rows_kernel(const float* __restrict__ rows, const uint32_t* __restrict__ perm, int64_t m, int width,
+                                                           float* __restrict__ out)
+{
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= m * width) return;
+    const int64_t j = t / width;
+    const int f = (int)(t - j * width);
+    out[(int64_t)perm[j] * width + f] = rows[t];
+}
+// d_indices: m original indices (device).  Leaves qlist in c->qlist[0..m) and perm in c->qlist[m..2m).
+cudaError_t build_query_list(kpl_ctx* c, int64_t n, const int32_t* d_indices, int64_t m)
+{
+    cudaError_t e;
+    if ((e = ensure(c->scratch_i, (size_t)n + 2 * (size_t)m + 16)) || (e = ensure(c->qlist, 2 * (size_t)m + 16))) return e;
+    int32_t* inv = c->scratch_i.p;
+    uint32_t* qpos = (uint32_t*)(c->scratch_i.p + n);
+    uint32_t* row = qpos + m;
+    uint32_t* qsorted = (uint32_t*)c->qlist.p;
+    uint32_t* perm = qsorted + m;
+    int end_bit = 1;
+    while (end_bit < 32 && (1ll << end_bit) < n) end_bit++;
+    size_t bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, bytes, qpos, qsorted, row, perm, (int)m, 0, end_bit, c->stream);
+    if ((e = ensure(c->cub_tmp, bytes))) return e;
+    inverse_perm_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->idx_b.p, n, inv);
+    query_pos_kernel<<<(unsigned)((m + 255) / 256), 256, 0, c->stream>>>(d_indices, m, inv, qpos, row);
+    bytes = c->cub_tmp.cap;
+    if ((e = cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, bytes, qpos, qsorted, row, perm, (int)m, 0, end_bit, c->stream))) return e;
+    c->launches += 2 + (end_bit + 7) / 8 + 1;
+    return cudaGetLastError();
+}
+cudaError_t launch_scatter_rows(kpl_ctx* c, const float* d_rows, int64_t m, int width, float* d_out)
+{
+    const int64_t total = m * width;
+    scatter_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(d_rows, (const uint32_t*)c->qlist.p + m, m, width, d_out);
+    c->launches++;
+    return cudaGetLastError();
+}
+
+// ---- batch of views: per-view keypoint ranges of the ascending concatenated index list ---------------------
+// kp_offsets[v] = number of keypoints with concatenated index < view_offsets[v]; kp_idx is made view-local.
+__global__ void __launch_bounds__(256) view_ranges_kernel(const int32_t* __restrict__ kp_idx, const int32_t* __restrict__ d_count,
+                                                          const int64_t* __restrict__ view_offsets, int nviews, int64_t* __restrict__ kp_offsets)
+{
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v > nviews) return;
+    const int cnt = *d_count;
+    const int64_t bound = view_offsets[v];
+    int lo = 0, hi = cnt;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if ((int64_t)kp_idx[mid] < bound) lo = mid + 1; else hi = mid;
+    }
+    kp_offsets[v] = lo;
+}
+__global__ void __launch_bounds__(256) view_localise_kernel(int32_t* __restrict__ kp_idx, const int32_t* __restrict__ d_count,
+                                                            const int64_t* __restrict__ view_offsets, int nviews)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= *d_count) return;
+    const int32_t g = kp_idx[i];
+    kp_idx[i] = (int32_t)(g - view_offsets[view_of_point(view_offsets, nviews, g)]);
+}
+cudaError_t launch_view_ranges(kpl_ctx* c, int64_t n, int32_t* d_kp_idx, const int64_t* d_view_offsets, int nviews, int64_t* d_kp_offsets)
+{
+    const int32_t* d_cnt = (const int32_t*)(c->counters.p + 3);
+    view_ranges_kernel<<<(nviews + 1 + 255) / 256, 256, 0, c->stream>>>(d_kp_idx, d_cnt, d_view_offsets, nviews, d_kp_offsets);
+    view_localise_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(d_kp_idx, d_cnt, d_view_offsets, nviews);
+    c->launches += 2;
     return cudaGetLastError();
 }
 

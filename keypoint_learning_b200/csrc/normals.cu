@@ -24,6 +24,51 @@ __device__ __forceinline__ void key_to_cell(uint32_t key, const GridDesc& g, int
     cy = (int)(t - (uint32_t)cz * (uint32_t)g.dim[1]);
 }
 
+
+// Per-lane view of the grid: the whole grid for a single cloud, the point's own view (origin, z range) inside a
+// stacked batch grid (kpl_internal.h: ViewDesc).
+struct LocalGrid {
+    double org[3];
+    int zlo, zhi;      // z layers the search may visit
+};
+__device__ __forceinline__ LocalGrid local_grid(const GridDesc& g, int cz)
+{
+    LocalGrid L;
+    L.org[0] = g.org[0]; L.org[1] = g.org[1]; L.org[2] = g.org[2];
+    L.zlo = 0; L.zhi = g.dim[2] - 1;
+    if (g.layer_view) {
+        const int v = __ldg(g.layer_view + cz);
+        if (v >= 0) {
+            const ViewDesc* V = g.views + v;
+            L.org[0] = V->org[0]; L.org[1] = V->org[1]; L.org[2] = V->org[2];
+            L.zlo = V->zoff; L.zhi = V->zoff + V->dimz - 1;
+        }
+    }
+    return L;
+}
+// fractional position of coordinate v inside its cell cc along axis a, in [0, 1)
+__device__ __forceinline__ double cell_fraction(const GridDesc& g, const LocalGrid& L, int a, float v, int cc)
+{
+    const int local = (a == 2) ? cc - L.zlo : cc;      // zlo = the view's first stacked layer (0 for a single cloud)
+    return __ddiv_rn(__dsub_rn((double)v, L.org[a]), g.cell) - (double)g.off[a] - (double)local;
+}
+// Slab of a larger cloud: the k nearest points found inside the slab are the k nearest of the whole cloud only if
+// the ball that holds them does not reach an x face behind which the cloud continues.  Points in the outermost
+// guard_cells columns at such a face are expected to be clipped (nothing that is kept depends on their normals).
+__device__ __forceinline__ bool knn_clipped(const GridDesc& g, int cx, float px, float kth_d2)
+{
+    bool clipped = false;
+    if (g.interior_lo && cx >= g.guard_cells) {
+        const double d = (double)px - (g.org[0] + (double)g.off[0] * g.cell);
+        clipped |= !((double)kth_d2 < d * d * (1.0 - 1e-6));
+    }
+    if (g.interior_hi && cx < g.dim[0] - g.guard_cells) {
+        const double d = (g.org[0] + (double)(g.off[0] + g.dim[0]) * g.cell) - (double)px;
+        clipped |= !((double)kth_d2 < d * d * (1.0 - 1e-6));
+    }
+    return clipped;
+}
+
 // K > 0: compile-time k, candidates in registers.  K == 0: runtime k <= 64, candidates in local memory.
 //
 // Search order: the query's own cell, then those of the 26 surrounding cells whose box can still hold a
@@ -35,7 +80,7 @@ template <int K>
 __global__ void __launch_bounds__(128) normals_knn_kernel(const float4* __restrict__ s_pos, const uint32_t* __restrict__ skey,
                                                           const int32_t* __restrict__ cell_start, const float4* __restrict__ xyz,
                                                           GridDesc g, int n, int k_rt, float vpx, float vpy, float vpz,
-                                                          float4* __restrict__ s_nrm)
+                                                          float4* __restrict__ s_nrm, unsigned long long* __restrict__ counters)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -46,6 +91,7 @@ __global__ void __launch_bounds__(128) normals_knn_kernel(const float4* __restri
     const float4 p = s_pos[i];
     int cx, cy, cz;
     key_to_cell(skey[i], g, cx, cy, cz);
+    const LocalGrid LG = local_grid(g, cz);
     int seen = 0;
 #pragma unroll
     for (int t = 0; t < KM; ++t) { bd2[t] = CUDART_INF_F; bi[t] = 0xFFFFFFFFu; }
@@ -83,7 +129,7 @@ __global__ void __launch_bounds__(128) normals_knn_kernel(const float4* __restri
         const int cc[3] = {cx, cy, cz};
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
-            const double q = __ddiv_rn(__dsub_rn((double)v[a], g.org[a]), g.cell) - (double)g.off[a] - (double)cc[a];   // in [0, 1)
+            const double q = cell_fraction(g, LG, a, v[a], cc[a]);   // in [0, 1)
             const float dl = fmaxf((float)(q * g.cell) * 0.99999f - 1e-30f, 0.0f);
             const float dh = fmaxf((float)((1.0 - q) * g.cell) * 0.99999f - 1e-30f, 0.0f);
             lo2[a] = dl * dl * 0.99999f; hi2[a] = dh * dh * 0.99999f;
@@ -94,7 +140,7 @@ __global__ void __launch_bounds__(128) normals_knn_kernel(const float4* __restri
         scan(__ldg(cell_start + base0 + cx), __ldg(cell_start + base0 + cx + 1));
         for (int dz = -1; dz <= 1; ++dz) {
             const int z = cz + dz;
-            if (z < 0 || z >= g.dim[2]) continue;
+            if (z < LG.zlo || z > LG.zhi) continue;
             const float gz2 = dz < 0 ? lo2[2] : (dz > 0 ? hi2[2] : 0.0f);
             for (int dy = -1; dy <= 1; ++dy) {
                 const int y = cy + dy;
@@ -116,7 +162,7 @@ __global__ void __launch_bounds__(128) normals_knn_kernel(const float4* __restri
     // ---- exactness guard; growing rings (rescan from scratch) when the block was not enough ---------
     const int maxdim = max(g.dim[0], max(g.dim[1], g.dim[2]));
     for (int R = 1; R <= maxdim; ++R) {
-        const int z0 = max(cz - R, 0), z1 = min(cz + R, g.dim[2] - 1);
+        const int z0 = max(cz - R, LG.zlo), z1 = min(cz + R, LG.zhi);
         const int y0 = max(cy - R, 0), y1 = min(cy + R, g.dim[1] - 1);
         const int x0 = max(cx - R, 0), x1 = min(cx + R, g.dim[0] - 1);
         if (R > 1) {
@@ -129,7 +175,7 @@ __global__ void __launch_bounds__(128) normals_knn_kernel(const float4* __restri
                     scan(__ldg(cell_start + base + x0), __ldg(cell_start + base + x1 + 1));
                 }
         }
-        const bool all = (z0 == 0 && y0 == 0 && x0 == 0 && z1 == g.dim[2] - 1 && y1 == g.dim[1] - 1 && x1 == g.dim[0] - 1);
+        const bool all = (z0 == LG.zlo && y0 == 0 && x0 == 0 && z1 == LG.zhi && y1 == g.dim[1] - 1 && x1 == g.dim[0] - 1);
         if (all) break;
         if (bd2[k - 1] < CUDART_INF_F) {       // k candidates found (culling never skips a cell while fewer than k are known)
             double guard = (double)R * g.cell;
@@ -142,6 +188,7 @@ __global__ void __launch_bounds__(128) normals_knn_kernel(const float4* __restri
 #pragma unroll
     for (int t = 0; t < KM; ++t) cnt += (t < k && bi[t] != 0xFFFFFFFFu) ? 1 : 0;
     (void)seen;
+    if ((g.interior_lo | g.interior_hi) && knn_clipped(g, cx, p.x, bd2[k - 1])) atomicAdd(counters + 9, 1ull);
     float accu[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int t = 0; t < KM; ++t) {
@@ -191,7 +238,8 @@ template <int K>
 __global__ void __launch_bounds__(32) normals_knn_coop_kernel(const float4* __restrict__ s_pos, const uint32_t* __restrict__ skey,
                                                               const int32_t* __restrict__ cell_start, const float4* __restrict__ xyz,
                                                               GridDesc g, const int2* __restrict__ work, uint64_t one2,
-                                                              float vpx, float vpy, float vpz, float4* __restrict__ s_nrm)
+                                                              float vpx, float vpy, float vpz, float4* __restrict__ s_nrm,
+                                                              unsigned long long* __restrict__ counters)
 {
     __shared__ __align__(16) float tile[128];
     float* sx = tile; float* sy = tile + 32; float* sz = tile + 64;
@@ -203,6 +251,8 @@ __global__ void __launch_bounds__(32) normals_knn_coop_kernel(const float4* __re
     float4 p = make_float4(CUDART_NAN_F, 0.f, 0.f, 0.f);
     int cx = 0, cy = 0, cz = 0;
     if (active) { p = __ldg(s_pos + q); key_to_cell(__ldg(skey + q), g, cx, cy, cz); }
+    // every point of a work item lies in ONE cell row, hence in one view: lane 0 is always valid
+    const LocalGrid LG = local_grid(g, __shfl_sync(0xFFFFFFFFu, cz, 0));
     uint32_t bd2[K];          // bit patterns of the k smallest squared distances, ascending by (d2, index)
     uint32_t bi[K];
 #pragma unroll
@@ -217,7 +267,7 @@ __global__ void __launch_bounds__(32) normals_knn_coop_kernel(const float4* __re
         const int cc[3] = {cx, cy, cz};
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
-            const double f = __ddiv_rn(__dsub_rn((double)v[a], g.org[a]), g.cell) - (double)g.off[a] - (double)cc[a];   // in [0, 1)
+            const double f = cell_fraction(g, LG, a, v[a], cc[a]);   // in [0, 1)
             const float dl = fmaxf((float)(f * g.cell) * 0.99999f - 1e-30f, 0.0f);
             const float dh = fmaxf((float)((1.0 - f) * g.cell) * 0.99999f - 1e-30f, 0.0f);
             lo2[a] = active ? dl * dl * 0.99999f : CUDART_INF_F; hi2[a] = active ? dh * dh * 0.99999f : CUDART_INF_F;
@@ -241,7 +291,7 @@ __global__ void __launch_bounds__(32) normals_knn_coop_kernel(const float4* __re
             const int o = (r == 0) ? 4 : (r <= 4 ? r - 1 : r);       // 4, 0, 1, 2, 3, 5, 6, 7, 8
             const int dy = o % 3 - 1, dz = o / 3 - 1;
             const int y = gy0 + dy, z = gz0 + dz;
-            if (y < 0 || y >= g.dim[1] || z < 0 || z >= g.dim[2]) continue;
+            if (y < 0 || y >= g.dim[1] || z < LG.zlo || z > LG.zhi) continue;
             const float gap2 = (dy < 0 ? lo2[1] : (dy > 0 ? hi2[1] : 0.0f)) + (dz < 0 ? lo2[2] : (dz > 0 ? hi2[2] : 0.0f));
             if (!__any_sync(0xFFFFFFFFu, member && gap2 <= __uint_as_float(bd2[K - 1]))) continue;     // no member can use this row
             const int64_t base = ((int64_t)z * g.dim[1] + y) * g.dim[0];
@@ -286,14 +336,14 @@ __global__ void __launch_bounds__(32) normals_knn_coop_kernel(const float4* __re
     if (!active) return;
     // exactness guard of the 3 x 3 x 3 block; growing rings (per lane, rescanning) where it does not hold
     {
-        const bool all1 = (cz - 1 <= 0 && cy - 1 <= 0 && cx - 1 <= 0 && cz + 1 >= g.dim[2] - 1 && cy + 1 >= g.dim[1] - 1 && cx + 1 >= g.dim[0] - 1);
+        const bool all1 = (cz - 1 <= LG.zlo && cy - 1 <= 0 && cx - 1 <= 0 && cz + 1 >= LG.zhi && cy + 1 >= g.dim[1] - 1 && cx + 1 >= g.dim[0] - 1);
         double guard = g.cell;
         guard = guard * guard * (1.0 - 1e-6);
         const bool exact = all1 || (bd2[K - 1] < 0x7F800000u && (double)__uint_as_float(bd2[K - 1]) < guard);
         if (!exact) {
             const int maxdim = max(g.dim[0], max(g.dim[1], g.dim[2]));
             for (int R = 2; R <= maxdim; ++R) {
-                const int z0 = max(cz - R, 0), z1 = min(cz + R, g.dim[2] - 1);
+                const int z0 = max(cz - R, LG.zlo), z1 = min(cz + R, LG.zhi);
                 const int y0 = max(cy - R, 0), y1 = min(cy + R, g.dim[1] - 1);
                 const int x0 = max(cx - R, 0), x1 = min(cx + R, g.dim[0] - 1);
 #pragma unroll
@@ -308,7 +358,7 @@ __global__ void __launch_bounds__(32) normals_knn_coop_kernel(const float4* __re
                             if (d2 <= __uint_as_float(bd2[K - 1])) knn_insert<K>(bd2, bi, __float_as_uint(d2), __float_as_uint(c.w));
                         }
                     }
-                if (z0 == 0 && y0 == 0 && x0 == 0 && z1 == g.dim[2] - 1 && y1 == g.dim[1] - 1 && x1 == g.dim[0] - 1) break;
+                if (z0 == LG.zlo && y0 == 0 && x0 == 0 && z1 == LG.zhi && y1 == g.dim[1] - 1 && x1 == g.dim[0] - 1) break;
                 if (bd2[K - 1] < 0x7F800000u) {
                     double gr = (double)R * g.cell;
                     gr = gr * gr * (1.0 - 1e-6);
@@ -317,6 +367,7 @@ __global__ void __launch_bounds__(32) normals_knn_coop_kernel(const float4* __re
             }
         }
     }
+    if ((g.interior_lo | g.interior_hi) && knn_clipped(g, cx, p.x, __uint_as_float(bd2[K - 1]))) atomicAdd(counters + 9, 1ull);
     int cnt = 0;
 #pragma unroll
     for (int t = 0; t < K; ++t) cnt += (bi[t] != 0xFFFFFFFFu) ? 1 : 0;
@@ -339,26 +390,34 @@ __global__ void __launch_bounds__(32) normals_knn_coop_kernel(const float4* __re
     s_nrm[q] = normal_from_moments(accu, cnt, p.x, p.y, p.z, vpx, vpy, vpz);
 }
 
+bool normals_knn_uses_work_list(const kpl_params& P)
+{
+    bool coop = P.k_normals == 10;
+#ifdef KPL_EXPERIMENTS
+    if (getenv("KPL_NORMALS_PER_THREAD")) coop = false;
+#endif
+    return coop;
+}
+
+// The work list of the warp-cooperative kernel (runs of at most two cells: one group per warp) is built by the
+// caller together with the feature kernel's (build_work_lists, one host synchronisation for both).
 cudaError_t launch_normals_knn(kpl_ctx* c, int64_t n)
 {
     const kpl_params& P = c->params;
     int blocks = (int)((n + 127) / 128);
     const float4* xyz = c->cur_xyz;
-    if (P.k_normals == 10 && !getenv("KPL_NORMALS_PER_THREAD")) {
-        int warps = 0;
-        cudaError_t e = build_work_list(c, 1, c->work_n, warps);      // runs of at most two cells: one group per warp
-        if (e) return e;
-        if (warps > 0)
-            normals_knn_coop_kernel<10><<<(unsigned)warps, 32, 0, c->stream>>>(c->s_pos.p, c->key_b.p, c->cell_start.p, xyz, c->grid, c->work_n.p,
-                                                                                0x3F8000003F800000ull, P.viewpoint[0], P.viewpoint[1],
-                                                                                P.viewpoint[2], c->s_nrm.p);
+    if (normals_knn_uses_work_list(P)) {
+        if (c->nwarps_norm > 0)
+            normals_knn_coop_kernel<10><<<(unsigned)c->nwarps_norm, 32, 0, c->stream>>>(c->s_pos.p, c->key_b.p, c->cell_start.p, xyz, c->grid, c->work_n.p,
+                                                                                        0x3F8000003F800000ull, P.viewpoint[0], P.viewpoint[1],
+                                                                                        P.viewpoint[2], c->s_nrm.p, c->counters.p);
     }
     else if (P.k_normals == 10)
         normals_knn_kernel<10><<<blocks, 128, 0, c->stream>>>(c->s_pos.p, c->key_b.p, c->cell_start.p, xyz, c->grid, (int)n, 10,
-                                                               P.viewpoint[0], P.viewpoint[1], P.viewpoint[2], c->s_nrm.p);
+                                                               P.viewpoint[0], P.viewpoint[1], P.viewpoint[2], c->s_nrm.p, c->counters.p);
     else
         normals_knn_kernel<0><<<blocks, 128, 0, c->stream>>>(c->s_pos.p, c->key_b.p, c->cell_start.p, xyz, c->grid, (int)n, P.k_normals,
-                                                              P.viewpoint[0], P.viewpoint[1], P.viewpoint[2], c->s_nrm.p);
+                                                              P.viewpoint[0], P.viewpoint[1], P.viewpoint[2], c->s_nrm.p, c->counters.p);
     c->launches++;
     return cudaGetLastError();
 }
@@ -395,9 +454,9 @@ __global__ void __launch_bounds__(256) check_normals_kernel(const float4* __rest
     const unsigned m = __ballot_sync(0xFFFFFFFFu, bad);
     if (m && (threadIdx.x & 31) == 0) atomicAdd(counters + 4, (unsigned long long)__popc(m));
 }
-cudaError_t launch_check_normals(kpl_ctx* c, int64_t n)
+cudaError_t launch_check_normals(kpl_ctx* c, int64_t n, bool use_role)
 {
-    check_normals_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->s_nrm.p, nullptr, n, c->counters.p);
+    check_normals_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->s_nrm.p, use_role ? c->s_role.p : nullptr, n, c->counters.p);
     c->launches++;
     return cudaGetLastError();
 }
@@ -552,11 +611,8 @@ cudaError_t launch_normals_radius(kpl_ctx* c, int64_t n)
     P.rcull2 = (float)(r * r * (1.0 + 1e-5));
     P.vpx = U.viewpoint[0]; P.vpy = U.viewpoint[1]; P.vpz = U.viewpoint[2];
     P.one2 = 0x3F8000003F800000ull;
-    int warps = 0;
-    cudaError_t e = build_work_list(c, P.span, c->work_n, warps);
-    if (e) return e;
-    if (warps > 0)
-        normals_radius_kernel<<<(unsigned)warps, 32, 0, c->stream>>>(c->s_pos.p, c->key_b.p, c->cell_start.p, c->work_n.p,
+    if (c->nwarps_norm > 0)
+        normals_radius_kernel<<<(unsigned)c->nwarps_norm, 32, 0, c->stream>>>(c->s_pos.p, c->key_b.p, c->cell_start.p, c->work_n.p,
                                                                     c->grid.dim[0], c->grid.dim[1], c->grid.dim[2], P, c->s_nrm.p);
     c->launches++;
     return cudaGetLastError();

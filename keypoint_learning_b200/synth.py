@@ -114,6 +114,17 @@ def scene_closed_surfaces(n_points=10_000_000, seed=4321, n_shapes=32, dtype=np.
     return np.ascontiguousarray(xyz), (0.0, 0.0, 0.0)
 
 
+def cube_crop(xyz, m):
+    """The m points nearest (Chebyshev distance) to the median point of the cloud, in their original order: a bounded
+    sample with the density and geometry of the full workload (bench.py's CPU legs and parity check, tests)."""
+    if m >= len(xyz):
+        return np.ascontiguousarray(xyz)
+    c = np.median(xyz, axis=0)
+    d = np.abs(xyz - c).max(axis=1)
+    sel = np.argpartition(d, m)[:m]
+    return np.ascontiguousarray(xyz[np.sort(sel)])
+
+
 def small_patch(n_side=64, pitch=0.64, seed=0):
     """Tiny 2.5D patch for unit tests (n_side^2 points)."""
     return view_25d(n_side, n_side, pitch, seed)

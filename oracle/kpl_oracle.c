@@ -705,6 +705,31 @@ KPLO_API void kplo_forest_sum(const int32_t* roots, int ntrees, const int32_t* v
         sums[i] = (float)sum;
     }
 }
+/* "Fragile split" report: per row, 1 if any split DECIDED while forest_->predict walks the trees
+ * (hpp:281) had |x[var] - thr| <= eps in FP32 -- a feature difference of the tolerated size would send that tree
+ * the other way.  Returns the number of flagged rows. */
+KPLO_API int64_t kplo_forest_fragile(const int32_t* roots, int ntrees, const int32_t* var, const float* thr,
+                                     const int32_t* left, const int32_t* right,
+                                     const float* feat, int64_t m, int F, float eps, uint8_t* flags)
+{
+    int64_t cnt = 0;
+#pragma omp parallel for schedule(static) reduction(+ : cnt)
+    for (int64_t i = 0; i < m; ++i) {
+        const float* x = feat + i * (int64_t)F;
+        int frag = 0;
+        for (int t = 0; t < ntrees; ++t) {
+            int32_t nidx = roots[t];
+            while (var[nidx] >= 0) {
+                const float d = x[var[nidx]] - thr[nidx];
+                if (fabsf(d) <= eps) frag = 1;
+                nidx = (x[var[nidx]] <= thr[nidx]) ? left[nidx] : right[nidx];
+            }
+        }
+        flags[i] = (uint8_t)frag;
+        cnt += frag;
+    }
+    return cnt;
+}
 KPLO_API void kplo_scores(const float* sums, int64_t m, int ntrees, float* scores)
 {
     for (int64_t i = 0; i < m; ++i) scores[i] = 1 - (sums[i] / ((float)ntrees * 1.0f));

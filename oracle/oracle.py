@@ -348,6 +348,19 @@ def forest_sum(forest, feat):
     return out
 
 
+def forest_fragile(forest, feat, eps=1e-5):
+    """Per row: 1 if a split decided on the row's walks had |x[var] - thr| <= eps (the fragile decisions of BASELINE.md s5)."""
+    feat = np.ascontiguousarray(feat, np.float32)
+    m, F = feat.shape
+    out = np.empty(m, np.uint8)
+    L = lib()
+    L.kplo_forest_fragile.restype = C.c_int64
+    L.kplo_forest_fragile(_p(forest["roots"], C.c_int32), forest["ntrees"], _p(forest["var"], C.c_int32), _p(forest["thr"], C.c_float),
+                          _p(forest["left"], C.c_int32), _p(forest["right"], C.c_int32), _p(feat, C.c_float), C.c_int64(m), F,
+                          C.c_float(eps), _p(out, C.c_uint8))
+    return out
+
+
 def scores_from_sums(sums, ntrees):
     sums = np.ascontiguousarray(sums, np.float32)
     out = np.empty_like(sums)

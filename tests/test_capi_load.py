@@ -31,7 +31,8 @@ def test_struct_layouts_match_header(kpl):
     import tempfile
     from keypoint_learning_b200 import capi
     src = '#include <stdio.h>\n#include <stddef.h>\n#include "kpl.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(kpl_params), sizeof(kpl_timings), sizeof(kpl_stats),' \
-          ' offsetof(kpl_params, grid_origin), offsetof(kpl_stats, grid_origin), offsetof(kpl_stats, n_unscored));return 0;}\n'
+          ' offsetof(kpl_params, grid_origin), offsetof(kpl_stats, grid_origin), offsetof(kpl_stats, n_unscored));' \
+          'printf("%zu %zu %zu\\n", offsetof(kpl_params, slab_guard_cells), offsetof(kpl_stats, n_fragile_points), offsetof(kpl_stats, n_views));return 0;}\n'
     with tempfile.TemporaryDirectory() as d:
         c = os.path.join(d, "p.c")
         open(c, "w").write(src)
@@ -41,7 +42,8 @@ def test_struct_layouts_match_header(kpl):
         out = subprocess.check_output([exe]).split()
     got = [int(x) for x in out]
     exp = [C.sizeof(capi.KplParams), C.sizeof(capi.KplTimings), C.sizeof(capi.KplStats),
-           capi.KplParams.grid_origin.offset, capi.KplStats.grid_origin.offset, capi.KplStats.n_unscored.offset]
+           capi.KplParams.grid_origin.offset, capi.KplStats.grid_origin.offset, capi.KplStats.n_unscored.offset,
+           capi.KplParams.slab_guard_cells.offset, capi.KplStats.n_fragile_points.offset, capi.KplStats.n_views.offset]
     assert got == exp
 
 

@@ -22,6 +22,13 @@ R_FEAT, R_NMS, TH = 20.0, 4.0, 0.85
 TOL = 1e-5   # absolute tolerance of north_star for features and scores
 
 
+def same_bits(a, b):
+    """Bit-identical float arrays; NaNs compare equal whatever their payload (the device writes 0x7FFFFFFF, x86 0/0
+    gives 0xFFC00000: both mean "no value")."""
+    a = np.ascontiguousarray(a, np.float32); b = np.ascontiguousarray(b, np.float32)
+    return a.shape == b.shape and bool(np.all((a.view(np.uint32) == b.view(np.uint32)) | (np.isnan(a) & np.isnan(b))))
+
+
 def sha(a):
     return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
 
@@ -271,11 +278,8 @@ def test_forest_against_opencv(kpl, views, oracle):
 
 
 def test_nms_semantics(kpl, oracle):
-    """plateaus survive, strictly greater neighbours suppress, d2 == r^2 does not count (hpp:219)."""
-    # two-leaf forest: score = 1 if feature[0] <= 0.5 else 0 -> not useful to steer scores, so drive
-    # NMS through the device API surrogate: use a forest of 4 stumps on different variables instead.
-    # Simpler and exact: craft scores with a lookup forest on a 1x1 histogram is impossible, so this
-    # test checks the GPU NMS against the oracle NMS on the real scores with several radii/thresholds.
+    """Threshold + local-maximum NMS (hpp:203-256) against the oracle on the golden scores for several radii and
+    thresholds: plateaus survive, strictly greater neighbours suppress, d2 == r^2 does not count (hpp:219)."""
     xyz = np.load(os.path.join(os.path.dirname(__file__), "golden", "views", "cheff000.npz"))["xyz"]
     g = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_cheff000.npz"))
     nrm = oracle.normals_knn(xyz, 10)
@@ -558,4 +562,223 @@ def test_slab_results_equal_unsharded(kpl, views, golden, world):
     assert seen.all()
     assert np.array_equal(np.sort(np.concatenate(kps)), idx_full)
     d.setForcedGrid(None)
+    d.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# the headline workload: closed 3-D surfaces at |coords| up to 1000 mm (BASELINE.json configs[3])
+# ---------------------------------------------------------------------------------------------
+def scene_crop(n_scene, m):
+    from keypoint_learning_b200 import synth
+    xyz, vp = synth.scene_closed_surfaces(n_scene, seed=4321)
+    return synth.cube_crop(xyz, m), vp
+
+
+def test_scene_closed_surfaces_vs_oracle(kpl, oracle, main_forest):
+    """configs[3] geometry (multi-layer z cells, runs crossing a cell row several times, the computeRoots2 fallback of the
+    un-centred covariance far from the origin): normals, features, scores and keypoints uint32-exact against the oracle
+    (semantics: impl/KeypointLearning.hpp:179-376)."""
+    xyz, vp = scene_crop(1_250_000, 300_000)
+    assert np.abs(xyz).max() > 300.0
+    d = make_detector(kpl)
+    d.setNormalsMode(1, k=10, viewpoint=vp)
+    d.keepIntermediates(True)
+    d.setInputCloud(xyz)
+    _, idx = d.compute()
+    st = d.stats()
+    assert st["grid_dims"][2] > 3                                   # really a 3-D grid
+    ref = oracle.detect(xyz, main_forest, R_FEAT, R_NMS, TH, 5, 10, normals_mode=1, k=10, viewpoint=vp, order=1)
+    assert same_bits(d.fetch("normals", len(xyz), 4), ref["normals"])
+    assert same_bits(d.fetch("features", len(xyz), 50), ref["features"])
+    assert same_bits(d.getResponse(), ref["scores"])
+    assert np.array_equal(idx, ref["keypoints"])
+    assert len(idx) > 0
+    assert st["n_unscored"] == int(np.isnan(ref["scores"]).sum())
+    # exact pair counter = the oracle's neighbour counts (self excluded) minus the pairs that never vote: a query
+    # without a finite normal is not scored (hpp:277) and a neighbour without one is skipped (hpp:338)
+    counts = oracle.radius_counts(xyz, R_FEAT)
+    bad = np.nonzero(np.isnan(ref["normals"][:, :3]).any(axis=1))[0].astype(np.int32)
+    off, nb = oracle.radius_neighbors(xyz, R_FEAT, bad)
+    removed = 0
+    for k, b in enumerate(bad):
+        mine = nb[off[k]:off[k + 1]]
+        removed += (len(mine) - 1) + int(np.sum(~np.isin(mine, bad)))
+    assert st["feature_pairs"] == int(counts.sum()) - len(xyz) - removed
+    d.close()
+
+
+def test_scene_crop_against_the_reference_templates(kpl, oracle):
+    """A 3 k-point crop of the closed-surface scene through oracle/_ref (the reference's own templates)."""
+    if oracle.ref_lib() is None:
+        pytest.skip("oracle/_ref was not built (reference tree not mounted)")
+    xyz, vp = scene_crop(1_250_000, 3000)
+    nrm = oracle.normals_knn(xyz, 10, vp)
+    fname = "synthetic-SHOT-like-T50-D10"
+    forest = oracle.load_forest_yaml(forest_path(fname))
+    lf = oracle.ref_neighbour_lists(xyz, R_FEAT, 1)
+    ln = oracle.ref_neighbour_lists(xyz, R_NMS, 0)
+    d = make_detector(kpl, forest=forest_path(fname), th=0.5)
+    d.keepIntermediates(True)
+    d.setInputCloud(xyz); d.setNormals(nrm)
+    _, idx = d.compute()
+    f_ref = oracle.ref_features(xyz, nrm, R_FEAT, 5, 10, lf)
+    assert np.array_equal(d.fetch("features", len(xyz), 50).view(np.uint32), f_ref.view(np.uint32))
+    _, sc_ref = oracle.ref_detect(xyz, nrm, forest, R_FEAT, R_NMS, 0.5, 5, 10, lf, None, non_maxima=False)
+    assert np.array_equal(d.getResponse().view(np.uint32), sc_ref.view(np.uint32))
+    kp_ref, _ = oracle.ref_detect(xyz, nrm, forest, R_FEAT, R_NMS, 0.5, 5, 10, lf, ln)
+    assert np.array_equal(idx, kp_ref)
+    d.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# fragile splits (BASELINE.md s5): decisions of forest_->predict (hpp:281) within 1e-5 of the threshold
+# ---------------------------------------------------------------------------------------------
+def test_fragile_split_report(kpl, views, golden, oracle, main_forest):
+    xyz = views["cheff001"]
+    nrm = oracle.normals_knn(xyz, 10)
+    d = make_detector(kpl)
+    d.keepIntermediates(True)
+    d.setInputCloud(xyz); d.setNormals(nrm)
+    d.compute()
+    assert d.stats()["n_fragile_points"] == 0            # off by default
+    with pytest.raises(kpl.KplError):
+        d.fetchFragile(len(xyz))
+    d.setReportFragile(True)
+    d.compute()
+    assert np.array_equal(d.getResponse().view(np.uint32), golden["cheff001"]["scores"].view(np.uint32))
+    feat = d.fetch("features", len(xyz), 50)
+    ref = oracle.forest_fragile(main_forest, feat)
+    got = d.fetchFragile(len(xyz))
+    assert np.array_equal(got, ref)
+    assert d.stats()["n_fragile_points"] == int(ref.sum())
+    assert 0 < int(ref.sum()) < len(xyz)
+    # a score that differs between two accumulation orders implies a fragile decision: the grid-free oracle
+    # (ascending-index accumulation) must not disagree on any point that is not flagged
+    f0 = oracle.features(xyz, nrm, R_FEAT, 5, 10, order=0)
+    s0 = oracle.scores_from_sums(oracle.forest_sum(main_forest, f0), main_forest["ntrees"])
+    differs = s0 != d.getResponse()
+    assert not np.any(differs & (got == 0))
+    d.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# batch of independent views in one pass (BASELINE.json configs[4])
+# ---------------------------------------------------------------------------------------------
+def test_batch_equals_per_view_calls(kpl, views, golden):
+    """kpl_detect_batch: every view bit-identical to its stand-alone kpl_detect run (own grid, own order)."""
+    from keypoint_learning_b200 import synth
+    clouds = [views["cheff000"], views["cheff002"][:20000], synth.view_25d(200, 150, seed=5)[0], views["cheff001"],
+              np.ascontiguousarray(views["cheff001"][:7] + np.float32(300.0))]       # a tiny view: fewer points than k
+    d = make_detector(kpl)
+    d.setNormalsMode(1, k=10)
+    sc_b, kp_b = d.computeBatch(clouds)
+    st = d.stats()
+    assert st["n_views"] == len(clouds) and st["n_points"] == sum(len(c) for c in clouds)
+    pairs = 0
+    for c, sc, kp in zip(clouds, sc_b, kp_b):
+        d.setInputCloud(c); d.setNormals(None)
+        _, idx = d.compute()
+        assert np.array_equal(d.getResponse().view(np.uint32), sc.view(np.uint32))
+        assert np.array_equal(idx, kp)
+        pairs += d.stats()["feature_pairs"]
+    assert st["feature_pairs"] == pairs
+    assert np.array_equal(sc_b[0].view(np.uint32), golden["cheff000"]["scores"].view(np.uint32))
+    assert np.array_equal(kp_b[3], golden["cheff001"]["keypoints"])
+    # given normals + one single view behave like kpl_detect
+    sc1, kp1 = d.computeBatch([views["cheff001"]])
+    assert np.array_equal(kp1[0], golden["cheff001"]["keypoints"])
+    with pytest.raises(kpl.KplError):
+        d.computeBatchConcat(np.zeros((4, 4), np.float32), np.array([0, 2, 2, 4], np.int64))      # an empty view
+    d.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# computePointsForTrainingFeatures on a small index subset of a large cloud (main_train_detector.cpp:419-439)
+# ---------------------------------------------------------------------------------------------
+def test_feature_subset_is_compact(kpl, oracle):
+    import torch
+    from keypoint_learning_b200 import synth
+    xyz, vp = synth.scene_closed_surfaces(10_000_000, seed=4321)
+    rng = np.random.default_rng(11)
+    q = rng.choice(len(xyz), 5000, replace=False).astype(np.int32)
+    q[10] = q[3]                                                     # duplicates are allowed
+    torch.cuda.synchronize()
+    free0, _ = torch.cuda.mem_get_info()
+    d = make_detector(kpl)
+    d.setNormalsMode(1, k=10, viewpoint=vp)
+    d.setInputCloud(xyz)
+    rows = d.computePointsForTrainingFeatures(q)
+    free1, _ = torch.cuda.mem_get_info()
+    assert free0 - free1 < 1.5e9, "kpl_features on 5 k indices of a 10 M-point cloud used %.2f GB" % ((free0 - free1) / 1e9)
+    assert rows.shape == (5000, 50)
+    # check 40 of the rows against the oracle evaluated on the query's own neighbourhood (canonical order needs the
+    # grid of the WHOLE cloud: pass it explicitly)
+    org, cell, dims = oracle.canon_grid(xyz, R_FEAT, 4)
+    nrm_all = d.fetch("normals", len(xyz), 4)
+    for k in range(0, 5000, 125):
+        c = xyz[q[k]]
+        near = np.nonzero(np.abs(xyz - c).max(axis=1) < R_FEAT + 1.0)[0]
+        loc = int(np.searchsorted(near, q[k]))
+        f = oracle.features(xyz[near], nrm_all[near], R_FEAT, 5, 10, order=1, qidx=np.array([loc], np.int32),
+                            canon=(org, cell, dims))
+        assert np.array_equal(f[0].view(np.uint32), rows[k].view(np.uint32)), k
+    d.close()
+
+
+def test_feature_subset_matches_full_rows(kpl, views, oracle):
+    xyz = views["cheff002"]
+    nrm = oracle.normals_knn(xyz, 10)
+    d = make_detector(kpl)
+    d.setInputCloud(xyz); d.setNormals(nrm)
+    full = d.computePointsForTrainingFeatures()
+    rng = np.random.default_rng(2)
+    for m in (1, 31, 32, 33, 1000, 20000):
+        q = rng.choice(len(xyz), m, replace=(m > 5000)).astype(np.int32)
+        rows = d.computePointsForTrainingFeatures(q)
+        assert np.array_equal(rows.view(np.uint32), full[q].view(np.uint32)), m
+    d.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# stand-alone normal estimation sizes its k-NN grid from the data, whatever the unit of the cloud
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("scale", [1e-3, 1.0, 250.0])
+def test_knn_normals_any_unit(kpl, views, oracle, scale):
+    import time
+    xyz = np.ascontiguousarray(views["cheff001"] * np.float32(scale))
+    d = kpl.KeypointLearningDetector()
+    d.setNormalsMode(1, k=10)                          # radiusFeatures stays at its default of 20, as in TestDetector's `ne`
+    t0 = time.perf_counter()
+    got = d.computeNormals(xyz)
+    dt = time.perf_counter() - t0
+    ref = oracle.normals_knn(xyz, 10)
+    assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+    cells = d.stats()["grid_cells"]
+    assert 1000 < cells < 5e7, cells                   # neither one cell (brute force) nor an exploding grid
+    assert dt < 5.0
+    d.close()
+
+
+def test_forest_guards(kpl, views, tmp_path):
+    """A forest that splits on a variable >= annuli*bins, or holds a non-numeric threshold, is refused instead of
+    reading beyond the feature row."""
+    import gzip
+    xyz = np.ascontiguousarray(views["cheff001"][:2000])
+    d = kpl.KeypointLearningDetector()
+    d.setRadiusSearch(R_FEAT); d.setNonMaxRadius(R_NMS); d.setNonMaximaDrawsRemove(False)
+    d.setInputCloud(xyz)
+    # var_count 0 (unknown) but a split on variable 50 with 5 x 10 = 50 features
+    d.setForestArrays(dict(ntrees=1, roots=[0], var=[50, -1, -1], thr=[0.1, 0, 0], left=[1, -1, -1], right=[2, -1, -1], value=[0, 0, 1], var_count=0))
+    with pytest.raises(kpl.KplError) as e:
+        d.compute()
+    assert e.value.code == 5
+    d.setForestArrays(dict(ntrees=1, roots=[0], var=[49, -1, -1], thr=[0.1, 0, 0], left=[1, -1, -1], right=[2, -1, -1], value=[0, 0, 1], var_count=0))
+    d.compute()
+    txt = gzip.open(forest_path("synthetic-A4xB8-T20-D8"), "rt").read()
+    import re
+    bad = re.sub(r"le:\s*[-+0-9.eE]+", "le:.Inf", txt, count=1)
+    assert bad != txt
+    p = tmp_path / "inf.yaml"
+    p.write_text(bad)
+    assert not d.loadForest(str(p))
     d.close()
