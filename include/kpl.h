@@ -201,6 +201,81 @@ KPL_API int kpl_detect_batch(kpl_ctx* ctx, const float* xyz, int32_t xyz_stride,
 KPL_API int kpl_detect_batch_device(kpl_ctx* ctx, const void* d_xyz4, const void* d_normals4, const int64_t* view_offsets,
                                     int32_t n_views, void* d_scores, void* d_kp_idx, void* d_kp_offsets, int64_t* n_kp_out);
 
+/* ---- ONE large cloud over the GPUs of a node: x slabs + halo over NCCL (BASELINE.json configs[3]) ---------- */
+/* The reference is a single process (main_test_detector.cpp:123-187 drives one detector); this is the layer a
+ * multi-GPU driver binds to.  The cloud is cut along x at CELL-COLUMN boundaries of the canonical grid of the WHOLE
+ * cloud; rank r owns the columns [cuts[r], cuts[r+1]).  Per detection every rank
+ *   1. sends its boundary strips (halo = reach(radiusFeatures) + normal_support_cells columns, 16 B per point) to
+ *      its two neighbours and receives theirs                                              [ncclSend/ncclRecv]
+ *   2. builds the grid of [left halo | owned | right halo] with the GLOBAL origin (same cell keys, hence the same
+ *      accumulation order, hence bit-identical floats as the single-GPU run), estimates normals for all of it and
+ *      scores the points it OWNS -- every point of the cloud is scored exactly once
+ *   3. exchanges the 4-byte scores of the strips, so that NMS sees the neighbours' scores  [ncclSend/ncclRecv]
+ *   4. runs threshold + NMS for its owned points; rank 0 gathers the ascending GLOBAL keypoint index list.
+ * A k-NN normal search that the slab edge would clip fails the call on every rank with KPL_E_HALO (widen
+ * normal_support_cells).  draws-remove NMS is not available (its dependency chain crosses slabs). */
+#define KPL_MAX_RANKS 64
+typedef struct kpl_slab_plan {
+    double origin[3];              /* grid origin = bounding-box minimum of the whole cloud                        */
+    double cell;                   /* r_feat * (1 + 2^-20) / cells_per_radius                                       */
+    int32_t dims[3];               /* grid dimensions of the whole cloud                                            */
+    int32_t world;                 /* number of slabs / ranks                                                       */
+    int32_t reach_feat, reach_nms; /* search reach of the two radii in cells                                        */
+    int32_t normal_support_cells;  /* columns of k-NN support beyond reach_feat                                     */
+    int32_t halo;                  /* max(reach_feat + normal_support_cells, reach_nms) columns per interior side   */
+    int32_t cuts[KPL_MAX_RANKS + 1];
+    int64_t n_points;
+    double cost[KPL_MAX_RANKS];    /* modelled cost of each rank (neighbour pairs + per-point work), for reports    */
+} kpl_slab_plan;
+
+typedef struct kpl_shard kpl_shard;
+
+typedef struct kpl_shard_info {
+    int64_t n_owned, n_left, n_right;     /* points owned / received from the left / right neighbour              */
+    int64_t send_left, send_right;        /* points sent to the neighbours per detection                          */
+    int64_t halo_bytes;                   /* bytes this rank sends per detection (positions + scores)             */
+    int32_t local_dims[3], local_offset[3];
+    int32_t rank, world;
+    float exchange_ms;                    /* device time of the two exchanges of the last detection               */
+    float gather_ms;                      /* device time of the keypoint gather + sort (rank 0)                   */
+} kpl_shard_info;
+
+/* Host only (no GPU needed): balanced cuts for `world` slabs.  The cost of a rank is modelled from the cloud itself:
+ * neighbour pairs of the points it owns (cell histogram convolved with the search box) plus the per-point work of
+ * everything it holds including the halo.  Fails with KPL_E_INVALID when the grid has too few columns for `world`
+ * slabs of at least `halo` columns. */
+KPL_API int kpl_slab_plan_make(const float* xyz, int32_t xyz_stride, int64_t n, const kpl_params* p, int32_t world,
+                               int32_t normal_support_cells, kpl_slab_plan* out);
+/* Host only: ascending indices of the points rank `rank` owns; idx_out capacity n. */
+KPL_API int kpl_slab_partition(const kpl_slab_plan* plan, const float* xyz, int32_t xyz_stride, int64_t n, int32_t rank,
+                               int32_t* idx_out, int64_t* m_out);
+
+/* 128-byte NCCL unique id (ncclGetUniqueId): create on one rank, hand to the others by the host's own means. */
+KPL_API int kpl_nccl_unique_id(void* id128_out);
+/* Joins the communicator (ncclCommInitRank: blocks until all `plan->world` ranks called it).  nccl_id128 == NULL
+ * creates a rank of an IN-PROCESS group instead (no NCCL: the ranks are driven together by kpl_shard_detect_group,
+ * strips move by cudaMemcpyPeerAsync) -- for hosts without NCCL and for tests on a single GPU. */
+KPL_API int kpl_shard_create(kpl_ctx* ctx, const kpl_slab_plan* plan, int32_t rank, const void* nccl_id128, kpl_shard** out);
+KPL_API void kpl_shard_destroy(kpl_shard* s);
+/* Replace the plan (same world size) without rebuilding the communicator -- e.g. after KPL_E_HALO, with a plan made
+ * for a larger normal_support_cells; kpl_shard_set_slab must follow. */
+KPL_API int kpl_shard_set_plan(kpl_shard* s, const kpl_slab_plan* plan);
+/* The points this rank owns (host, ascending global index; kpl_slab_partition) and their global indices.  Uploads
+ * them and exchanges the strip sizes: once per resident slab, not per detection. */
+KPL_API int kpl_shard_set_slab(kpl_shard* s, const float* xyz_owned, int32_t xyz_stride, const int32_t* gidx_owned, int64_t n_owned);
+/* New coordinates for the same partition (a detection loop that streams its slab from the host every step). */
+KPL_API int kpl_shard_upload(kpl_shard* s, const float* xyz_owned, int32_t xyz_stride);
+/* One detection (all ranks call it).  scores_owned_out: NULL or n_owned floats (host).  kp_global_out (rank 0; NULL
+ * elsewhere): ascending global keypoint indices, capacity kp_capacity; *n_kp_out = global keypoint count on every rank. */
+KPL_API int kpl_shard_detect(kpl_shard* s, float* scores_owned_out, int32_t* kp_global_out, int64_t kp_capacity, int64_t* n_kp_out);
+/* The same for the ranks of an in-process group, driven together from one host thread; outputs are per-rank arrays
+ * (entries may be NULL), the global list lands in kp_global_out. */
+KPL_API int kpl_shard_detect_group(kpl_shard** shards, int32_t world, float** scores_owned_out, int32_t* kp_global_out,
+                                   int64_t kp_capacity, int64_t* n_kp_out);
+KPL_API int kpl_shard_get_info(const kpl_shard* s, kpl_shard_info* out);
+/* Device pointer of the owned scores of the last detection (n_owned floats), for callers that keep results on the GPU. */
+KPL_API const void* kpl_shard_device_scores(const kpl_shard* s);
+
 /* ---- introspection --------------------------------------------------------------------------- */
 /* kpl_detect* score each point inside the feature kernel and do not write the A*B feature rows
  * (the cv::Mat of impl/KeypointLearning.hpp:366-369) to memory; on != 0 keeps them for kpl_fetch. */

@@ -18,7 +18,7 @@ LIB = os.path.join(HERE, "libkpl_b200.so")
 TEST_DETECTOR = os.path.join(HERE, "TestDetector")
 PCD_TOOL = os.path.join(HERE, "pcd_tool")
 
-CU_SOURCES = ["capi.cu", "grid.cu", "normals.cu", "features.cu", "forest.cu", "nms.cu", "forest_yaml.cpp"]
+CU_SOURCES = ["capi.cu", "grid.cu", "normals.cu", "features.cu", "forest.cu", "nms.cu", "shard.cu", "forest_yaml.cpp"]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-fmad=false",
     "-Xcompiler", "-fPIC,-fvisibility=hidden,-O2", "--expt-relaxed-constexpr", "-cudart", "static",
@@ -68,7 +68,7 @@ def build_lib(force: bool = False, verbose: bool = False) -> str:
         if p.returncode:
             raise RuntimeError("nvcc failed: " + " ".join(cmd))
     link = [_nvcc(), "-shared", "-o", LIB, *objs, "-ccbin", _host_cxx(), "-gencode", "arch=compute_100a,code=sm_100a",
-            "-cudart", "static", "-lz", "-Xlinker", "--no-undefined"]
+            "-cudart", "static", "-lz", "-ldl", "-Xlinker", "--no-undefined"]
     subprocess.check_call(link)
     return LIB
 

@@ -24,7 +24,11 @@ EXPORTS = ["kpl_create", "kpl_destroy", "kpl_last_error", "kpl_version", "kpl_se
            "kpl_set_params", "kpl_get_params", "kpl_load_forest", "kpl_set_forest", "kpl_forest_info", "kpl_detect",
            "kpl_normals", "kpl_features", "kpl_radius_stats", "kpl_radius_neighbors", "kpl_detect_device",
            "kpl_get_timings", "kpl_get_stats", "kpl_fetch", "kpl_set_keep_intermediates", "kpl_uniform_sample", "kpl_nearest",
-           "kpl_fetch_u8", "kpl_detect_batch", "kpl_detect_batch_device"]
+           "kpl_fetch_u8", "kpl_detect_batch", "kpl_detect_batch_device",
+           "kpl_slab_plan_make", "kpl_slab_partition", "kpl_nccl_unique_id", "kpl_shard_create", "kpl_shard_destroy", "kpl_shard_set_plan",
+           "kpl_shard_set_slab", "kpl_shard_upload", "kpl_shard_detect", "kpl_shard_detect_group", "kpl_shard_get_info",
+           "kpl_shard_device_scores"]
+KPL_MAX_RANKS = 64
 
 
 class KplParams(C.Structure):
@@ -47,6 +51,18 @@ class KplStats(C.Structure):
                 ("grid_dims", C.c_int32 * 3), ("kernel_launches", C.c_int32), ("grid_origin", C.c_double * 3), ("grid_cell", C.c_double),
                 ("fast_math", C.c_int32), ("reserved", C.c_int32), ("n_unscored", C.c_int64),
                 ("n_near_threshold", C.c_int64), ("n_fragile_points", C.c_int64), ("host_syncs", C.c_int32), ("n_views", C.c_int32)]
+
+
+class KplSlabPlan(C.Structure):
+    _fields_ = [("origin", C.c_double * 3), ("cell", C.c_double), ("dims", C.c_int32 * 3), ("world", C.c_int32),
+                ("reach_feat", C.c_int32), ("reach_nms", C.c_int32), ("normal_support_cells", C.c_int32), ("halo", C.c_int32),
+                ("cuts", C.c_int32 * (KPL_MAX_RANKS + 1)), ("n_points", C.c_int64), ("cost", C.c_double * KPL_MAX_RANKS)]
+
+
+class KplShardInfo(C.Structure):
+    _fields_ = [("n_owned", C.c_int64), ("n_left", C.c_int64), ("n_right", C.c_int64), ("send_left", C.c_int64), ("send_right", C.c_int64),
+                ("halo_bytes", C.c_int64), ("local_dims", C.c_int32 * 3), ("local_offset", C.c_int32 * 3), ("rank", C.c_int32),
+                ("world", C.c_int32), ("exchange_ms", C.c_float), ("gather_ms", C.c_float)]
 
 
 class KplError(RuntimeError):
@@ -92,6 +108,18 @@ def load_library():
     L.kpl_uniform_sample.argtypes = [vp, f32p, C.c_int32, C.c_int64, C.c_float, i32p, i64p]
     L.kpl_nearest.argtypes = [vp, f32p, C.c_int32, C.c_int64, f32p, C.c_int32, C.c_int64, i32p, f32p]
     L.kpl_fetch_u8.argtypes = [vp, C.c_char_p, u8p, C.c_int64]
+    L.kpl_slab_plan_make.argtypes = [f32p, C.c_int32, C.c_int64, C.POINTER(KplParams), C.c_int32, C.c_int32, C.POINTER(KplSlabPlan)]
+    L.kpl_slab_partition.argtypes = [C.POINTER(KplSlabPlan), f32p, C.c_int32, C.c_int64, C.c_int32, i32p, i64p]
+    L.kpl_nccl_unique_id.argtypes = [vp]
+    L.kpl_shard_create.argtypes = [vp, C.POINTER(KplSlabPlan), C.c_int32, vp, C.POINTER(vp)]
+    L.kpl_shard_destroy.argtypes = [vp]; L.kpl_shard_destroy.restype = None
+    L.kpl_shard_set_plan.argtypes = [vp, C.POINTER(KplSlabPlan)]
+    L.kpl_shard_set_slab.argtypes = [vp, f32p, C.c_int32, i32p, C.c_int64]
+    L.kpl_shard_upload.argtypes = [vp, f32p, C.c_int32]
+    L.kpl_shard_detect.argtypes = [vp, f32p, i32p, C.c_int64, i64p]
+    L.kpl_shard_detect_group.argtypes = [C.POINTER(vp), C.c_int32, C.POINTER(f32p), i32p, C.c_int64, i64p]
+    L.kpl_shard_get_info.argtypes = [vp, C.POINTER(KplShardInfo)]
+    L.kpl_shard_device_scores.argtypes = [vp]; L.kpl_shard_device_scores.restype = vp
     L.kpl_detect_batch.argtypes = [vp, f32p, C.c_int32, f32p, C.c_int32, i64p, C.c_int32, f32p, i32p, i64p]
     L.kpl_detect_batch_device.argtypes = [vp, vp, vp, i64p, C.c_int32, vp, vp, vp, i64p]
     _lib = L

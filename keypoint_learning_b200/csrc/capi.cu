@@ -364,6 +364,7 @@ static int prepare_normals(kpl_ctx* ctx, bool given, int64_t n)
 
 static void begin_call(kpl_ctx* ctx)
 {
+    (void)cudaGetLastError();      // a stale error of an earlier, unrelated runtime call must not be blamed on this call
     ctx->launches = 0;
     ctx->syncs = 0;
     ctx->err.clear();

@@ -1,29 +1,26 @@
-"""Spatial-slab sharding of ONE large cloud over the GPUs of a node (BASELINE.json configs[3]).
+"""Slab sharding of ONE large cloud over the GPUs of a node (BASELINE.json configs[3]): thin ctypes caller of the
+`kpl_slab_*` / `kpl_shard_*` entry points of include/kpl.h.  Planning, strip packing, the NCCL exchanges, role
+handling and the keypoint gather all live in csrc/shard.cu; nothing on the step path runs in Python or torch.
 
-The reference is single process; this is the new build's multi-GPU layer.  The cloud is cut along x
-into `world` slabs at CELL boundaries of the global canonical grid (balanced point counts).  Every
-step each rank
-  1. exchanges halo strips with its left / right neighbour (torch.distributed P2P: NCCL over NVLink
-     on GPUs, gloo in the CPU tests) -- the only data-path communication;
-  2. runs the whole detection path on [left halo | owned | right halo] with the GLOBAL grid forced
-     (origin / cell offset), so cell keys, hence the canonical accumulation order, hence every float,
-     are identical to the single-GPU run;
-  3. keeps the keypoints of the points it owns; rank 0 gathers the global index lists.
-Halo width in cells = reach(radiusNMS) + reach(radiusFeatures) + normal_support_cells: a keypoint
-decision of an owned point needs scores within r_nms, which need normals within r_feat, which need
-the k nearest points of those (k-NN support, at most `normal_support_cells` cells, checked by the
-N-GPU == 1-GPU bit-exactness tests).
-Roles (include/kpl.h): owned = 3 (scored + NMS output), halo within reach(r_nms) of the owned range = 1
-(scored only), outer halo = 0 (normals / neighbours only).
+The reference is a single process (src/main_test_detector.cpp:123-187); this is what a multi-GPU driver of that loop
+uses.  Schedule per detection (see include/kpl.h):
+  1. position strips (halo = reach(radiusFeatures) + normal_support_cells columns) to / from the two neighbours
+  2. grid with the GLOBAL origin, normals for everything held, scores for the OWNED points only
+  3. score strips (4 B / point) to / from the two neighbours
+  4. threshold + NMS for the owned points, global keypoint list gathered and sorted on rank 0.
+
+`HostSlab` is the same schedule written with numpy, the transport and the detection stage left to the caller: the CPU
+tests run it over a `gloo` process group with the oracle in the middle, which pins the schedule itself (what is sent,
+what is scored where, what NMS sees) independently of CUDA and NCCL.
 """
 from __future__ import annotations
 
-import math
+import ctypes as C
 from dataclasses import dataclass
 
 import numpy as np
-import torch
-import torch.distributed as dist
+
+from . import capi
 
 ROLE_HALO, ROLE_SCORE, ROLE_OWNED = 0, 1, 3
 
@@ -37,237 +34,233 @@ class SlabPlan:
     halo: int               # halo width in cells
     reach_nms: int
     reach_feat: int
+    normal_support_cells: int
+    cost: np.ndarray        # modelled per-rank cost
+    c_plan: capi.KplSlabPlan
+
+    @property
+    def world(self):
+        return len(self.cuts) - 1
 
 
-def canonical_cell(r_feat: float, cpr: int) -> float:
-    return float(np.float32(r_feat)) * (1.0 + 2.0 ** -20) / float(cpr)
+def _xyz_arg(xyz):
+    a = np.ascontiguousarray(xyz, np.float32)
+    if a.ndim != 2 or a.shape[1] < 3:
+        raise ValueError("xyz must be (n, >=3) float32")
+    return a, a.shape[1] * 4
 
 
-def reach(radius: float, cell: float) -> int:
-    return int(math.floor(float(np.float32(radius)) * (1.0 + 2.0 ** -21) / cell)) + 1
+def plan_slabs(xyz, r_feat, r_nms, cpr, world, normal_support_cells=1) -> SlabPlan:
+    """kpl_slab_plan_make (host only, no GPU): balanced x cuts at cell-column boundaries of the grid of the whole cloud."""
+    L = capi.load_library()
+    p = capi.KplParams()
+    L.kpl_params_default(C.byref(p))
+    p.radius_features = float(r_feat); p.radius_nms = float(r_nms); p.cells_per_radius = int(cpr)
+    a, stride = _xyz_arg(xyz)
+    cp = capi.KplSlabPlan()
+    rc = L.kpl_slab_plan_make(a.ctypes.data_as(C.POINTER(C.c_float)), stride, len(a), C.byref(p), int(world), int(normal_support_cells), C.byref(cp))
+    if rc == 1:
+        raise ValueError("cannot cut this cloud into %d slabs of at least one halo width (kpl_slab_plan_make -> KPL_E_INVALID)" % world)
+    if rc != 0:
+        raise capi.KplError(rc, "kpl_slab_plan_make failed")
+    return SlabPlan(np.array(cp.origin[:], np.float64), float(cp.cell), np.array(cp.dims[:], np.int32), np.array(cp.cuts[:world + 1], np.int64),
+                    int(cp.halo), int(cp.reach_nms), int(cp.reach_feat), int(cp.normal_support_cells), np.array(cp.cost[:world], np.float64), cp)
 
 
-def cell_coords(xyz: np.ndarray, origin: np.ndarray, cell: float, axis: int = 0) -> np.ndarray:
-    return np.floor((xyz[:, axis].astype(np.float64) - origin[axis]) / cell).astype(np.int64)
+def partition(plan: SlabPlan, xyz, rank) -> np.ndarray:
+    """kpl_slab_partition: ascending global indices of the points `rank` owns."""
+    L = capi.load_library()
+    a, stride = _xyz_arg(xyz)
+    idx = np.empty(len(a), np.int32)
+    m = C.c_int64(0)
+    rc = L.kpl_slab_partition(C.byref(plan.c_plan), a.ctypes.data_as(C.POINTER(C.c_float)), stride, len(a), int(rank),
+                              idx.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(m))
+    if rc != 0:
+        raise capi.KplError(rc, "kpl_slab_partition failed")
+    return idx[:m.value].copy()
 
 
-def plan_slabs(xyz: np.ndarray, r_feat: float, r_nms: float, cpr: int, world: int, normal_support_cells: int = 1) -> SlabPlan:
-    cell = canonical_cell(r_feat, cpr)
-    lo = xyz.min(axis=0).astype(np.float64)
-    hi = xyz.max(axis=0).astype(np.float64)
-    dims = (np.floor((hi - lo) / cell) + 1).astype(np.int32)
-    cx = cell_coords(xyz, lo, cell, 0)
-    hist = np.bincount(cx, minlength=int(dims[0])).astype(np.float64)
-    rn, rf = reach(r_nms, cell), reach(r_feat, cell)
-    halo = rn + rf + normal_support_cells
-    nx = int(dims[0])
-    cum = np.concatenate([[0.0], np.cumsum(hist)])
-
-    def pts(a, b):                                   # points in columns [a, b), clipped to the grid
-        return cum[min(max(b, 0), nx)] - cum[min(max(a, 0), nx)]
-
-    def cost(c0, c1):
-        # what a rank owning [c0, c1) computes: features + forest for its columns and the reach_nms margin
-        # (cost ~ 1 per point, the neighbour count is set by the sampling density, not by the slab), normals
-        # and grid for everything including the halo (~7 % of a scored point each)
-        return pts(c0 - rn, c1 + rn) + 0.07 * pts(c0 - halo, c1 + halo)
-
-    def greedy(limit):
-        cuts, c0 = [0], 0
-        while c0 < nx and len(cuts) <= world:
-            c1 = c0 + 1
-            while c1 < nx and cost(c0, c1 + 1) <= limit:
-                c1 += 1
-            cuts.append(c1)
-            c0 = c1
-        return cuts if cuts[-1] == nx and len(cuts) - 1 <= world else None
-
-    lo_t, hi_t = 0.0, cost(0, nx)
-    for _ in range(50):                               # smallest per-rank cost bound that needs <= world slabs
-        mid = 0.5 * (lo_t + hi_t)
-        if greedy(mid) is None:
-            lo_t = mid
-        else:
-            hi_t = mid
-    cuts = greedy(hi_t)
-    while len(cuts) - 1 < world:                      # fewer slabs than ranks: split the widest
-        w = np.diff(cuts)
-        k = int(np.argmax(w))
-        if w[k] < 2:
-            break
-        cuts.insert(k + 1, cuts[k] + int(w[k]) // 2)
-    if len(cuts) - 1 != world:
-        raise ValueError("cannot cut %d cell columns into %d slabs" % (nx, world))
-    plan = SlabPlan(lo, cell, dims, np.asarray(cuts, np.int64), halo, rn, rf)
-    widths = np.diff(plan.cuts)
-    if world > 1 and widths.min() < plan.halo:
-        raise ValueError("slabs (%s cells) are thinner than the halo (%d cells): use fewer ranks" % (widths.tolist(), plan.halo))
-    return plan
+def cell_coords(xyz, origin, cell, axis=0):
+    return np.floor((np.asarray(xyz)[:, axis].astype(np.float64) - origin[axis]) / cell).astype(np.int64)
 
 
-def reference_slab(xyz: np.ndarray, plan: SlabPlan, rank: int):
-    """What rank `rank` must end up with after the halo exchange, computed directly from the full cloud
-    (no communication).  Used by the tests as the check of exchange_halo()/assemble() and to emulate a
-    sharded run on one GPU.  Returns dict(xyz4, role, gidx, local_dims, offset)."""
-    world = len(plan.cuts) - 1
-    cx = cell_coords(xyz, plan.origin, plan.cell, 0)
-    c0, c1 = int(plan.cuts[rank]), int(plan.cuts[rank + 1])
-    pieces = []
-    if rank > 0:
-        pieces.append(np.nonzero((cx >= c0 - plan.halo) & (cx < c0))[0])
-    pieces.append(np.nonzero((cx >= c0) & (cx < c1))[0])
-    if rank < world - 1:
-        pieces.append(np.nonzero((cx >= c1) & (cx < c1 + plan.halo))[0])
-    gidx = np.concatenate(pieces).astype(np.int64)
-    xyz4 = np.ones((len(gidx), 4), np.float32)
-    xyz4[:, :3] = xyz[gidx]
-    c = cx[gidx]
-    role = np.zeros(len(gidx), np.uint8)
-    role[(c >= c0 - plan.reach_nms) & (c < c1 + plan.reach_nms)] = ROLE_SCORE
-    role[(c >= c0) & (c < c1)] = ROLE_OWNED
-    x0 = max(c0 - plan.halo, 0)
-    x1 = min(c1 + plan.halo, int(plan.dims[0]))
-    return dict(xyz4=xyz4, role=role, gidx=gidx, local_dims=np.array([x1 - x0, plan.dims[1], plan.dims[2]], np.int32),
-                offset=np.array([x0, 0, 0], np.int32))
+def nccl_unique_id() -> bytes:
+    L = capi.load_library()
+    buf = C.create_string_buffer(128)
+    rc = L.kpl_nccl_unique_id(buf)
+    if rc != 0:
+        raise capi.KplError(rc, "kpl_nccl_unique_id failed (is libnccl.so.2 loadable?)")
+    return buf.raw
 
 
 class SlabJob:
-    """Per-rank state of a sharded detection job.  `device` may be a CUDA device (NCCL) or 'cpu' (gloo)."""
+    """One rank of a sharded detection job on a GPU.  `det` is this rank's KeypointLearningDetector (forest and parameters
+    set); `nccl_id` the 128-byte id shared by all ranks (None: a rank of an in-process group, see detect_group)."""
 
-    def __init__(self, xyz: np.ndarray, r_feat: float, r_nms: float, cpr: int, rank: int, world: int, device, plan: SlabPlan | None = None):
-        self.rank, self.world, self.device = rank, world, torch.device(device)
-        self.plan = plan or plan_slabs(xyz, r_feat, r_nms, cpr, world)
-        p = self.plan
-        cx = cell_coords(xyz, p.origin, p.cell, 0)
-        self.c0, self.c1 = int(p.cuts[rank]), int(p.cuts[rank + 1])
-        own = np.nonzero((cx >= self.c0) & (cx < self.c1))[0]           # ascending global index
-        self.n_owned = len(own)
-        self.n_total = len(xyz)
-        xyz4 = np.ones((len(own), 4), np.float32)
-        xyz4[:, :3] = xyz[own]
-        self.host_xyz4 = torch.from_numpy(xyz4)
-        if self.device.type == "cuda":
-            self.host_xyz4 = self.host_xyz4.pin_memory()
-        self.xyz4 = self.host_xyz4.to(self.device)
-        self.gidx = torch.from_numpy(own.astype(np.int64)).to(self.device)
-        self.cx = torch.from_numpy(cx[own].astype(np.int32)).to(self.device)
-        # the local grid: global origin, x offset so that local keys stay small
-        self.x0 = max(self.c0 - p.halo, 0)
-        self.x1 = min(self.c1 + p.halo, int(p.dims[0]))
-        self.local_dims = np.array([self.x1 - self.x0, p.dims[1], p.dims[2]], np.int32)
-        self.offset = np.array([self.x0, 0, 0], np.int32)
-        self._scores = None
-        self._kp = None
-        # which of my points the neighbours need: a property of the resident slab, not of a step
-        self._left_sel = torch.nonzero(self.cx < self.c0 + p.halo).flatten() if rank > 0 else None
-        self._right_sel = torch.nonzero(self.cx >= self.c1 - p.halo).flatten() if rank < world - 1 else None
+    def __init__(self, det, xyz, plan: SlabPlan, rank: int, nccl_id: bytes | None):
+        self._L = capi.load_library()
+        self.det, self.plan, self.rank, self.world = det, plan, int(rank), plan.world
+        det._push()
+        self._h = C.c_void_p()
+        idbuf = C.create_string_buffer(nccl_id, 128) if nccl_id is not None else None
+        self._check(self._L.kpl_shard_create(det._h, C.byref(plan.c_plan), self.rank, idbuf, C.byref(self._h)))
+        self._set_slab(xyz)
 
-    # ---- step pieces (kept separate so the CPU tests can put the oracle in the middle) --------------
-    def exchange_halo(self):
-        """Send my boundary strips to the two neighbours, receive theirs (NCCL all_to_all over NVLink; gloo on
-        CPU).  Returns the (left, right) received buffers, None at the ends."""
-        p, r, w = self.plan, self.rank, self.world
-        left_sel, right_sel = self._left_sel, self._right_sel
+    def replan(self, xyz, plan: SlabPlan):
+        """kpl_shard_set_plan + kpl_shard_set_slab: a new plan for the same communicator (e.g. a wider k-NN support after
+        KPL_E_HALO)."""
+        self.plan = plan
+        self._check(self._L.kpl_shard_set_plan(self._h, C.byref(plan.c_plan)))
+        self._set_slab(xyz)
 
-        def pack(sel):
-            # one message per neighbour: xyz4 | gidx (as 2 x int32 bit patterns) | cx  -> float32 [m, 7]
-            m = len(sel)
-            buf = torch.empty((m, 7), dtype=torch.float32, device=self.device)
-            buf[:, :4] = self.xyz4[sel]
-            buf[:, 4:6] = self.gidx[sel].view(torch.int32).view(m, 2).view(torch.float32)
-            buf[:, 6] = self.cx[sel].view(torch.float32)
-            return buf
+    def _set_slab(self, xyz):
+        plan, rank = self.plan, self.rank
+        self.gidx = partition(plan, xyz, rank)
+        a = np.asarray(xyz)
+        own = np.ones((len(self.gidx), 4), np.float32)
+        own[:, :3] = a[self.gidx, :3]
+        self.host_xyz4 = own                       # callers may replace this by a pinned copy (same contents)
+        self.n_owned, self.n_total = len(self.gidx), len(a)
+        self._check(self._L.kpl_shard_set_slab(self._h, own.ctypes.data_as(C.POINTER(C.c_float)), 16,
+                                               self.gidx.ctypes.data_as(C.POINTER(C.c_int32)), len(self.gidx)))
 
-        send_l = pack(left_sel) if left_sel is not None else None
-        send_r = pack(right_sel) if right_sel is not None else None
-        # strip sizes of every rank (one tiny all_gather), then ONE all_to_all whose only non-empty
-        # splits are the two neighbours: the same collective sequence on every rank, whatever its position.
-        mine = torch.tensor([len(send_l) if send_l is not None else 0, len(send_r) if send_r is not None else 0],
-                            dtype=torch.int64, device=self.device)
-        sizes = [torch.zeros(2, dtype=torch.int64, device=self.device) for _ in range(w)]
-        dist.all_gather(sizes, mine)
-        sizes = torch.stack(sizes).cpu()
-        in_split = [0] * w
-        out_split = [0] * w
-        if r > 0:
-            in_split[r - 1] = int(sizes[r, 0]); out_split[r - 1] = int(sizes[r - 1, 1])
-        if r < w - 1:
-            in_split[r + 1] = int(sizes[r, 1]); out_split[r + 1] = int(sizes[r + 1, 0])
-        send = torch.cat([t for t in (send_l, send_r) if t is not None]) if (send_l is not None or send_r is not None) \
-            else torch.empty((0, 7), dtype=torch.float32, device=self.device)
-        recv = torch.empty((sum(out_split), 7), dtype=torch.float32, device=self.device)
-        dist.all_to_all_single(recv, send.contiguous(), output_split_sizes=out_split, input_split_sizes=in_split)
-        n_l = out_split[r - 1] if r > 0 else 0
-        recv_l = recv[:n_l] if r > 0 else None
-        recv_r = recv[n_l:] if r < w - 1 else None
-        self.halo_bytes = sum(int(t.numel()) * 4 for t in (send_l, send_r) if t is not None)
-        return recv_l, recv_r
+    def _check(self, rc):
+        if rc != 0:
+            raise capi.KplError(rc, (self._L.kpl_last_error(self.det._h) or b"").decode())
 
-    @staticmethod
-    def _unpack(buf):
-        m = buf.shape[0]
-        xyz4 = buf[:, :4].contiguous()
-        gidx = buf[:, 4:6].contiguous().view(torch.int32).view(m, 2).view(torch.int64).flatten()
-        cx = buf[:, 6].contiguous().view(torch.int32)
-        return xyz4, gidx, cx
+    def upload(self, host_xyz4=None):
+        a = self.host_xyz4 if host_xyz4 is None else host_xyz4
+        self._check(self._L.kpl_shard_upload(self._h, a.ctypes.data_as(C.POINTER(C.c_float)), a.shape[1] * 4))
 
-    def assemble(self):
-        """-> (xyz4 [n,4] float32, role [n] uint8, gidx [n] int64).  Pieces are whole cells and each is in
-        ascending global index, so inside every cell the order is the global one."""
-        recv_l, recv_r = self.exchange_halo() if self.world > 1 else (None, None)
-        parts_xyz, parts_g, parts_cx = [], [], []
-        for buf in (recv_l,):
-            if buf is not None and len(buf):
-                a, b, c = self._unpack(buf); parts_xyz.append(a); parts_g.append(b); parts_cx.append(c)
-        parts_xyz.append(self.xyz4); parts_g.append(self.gidx); parts_cx.append(self.cx)
-        for buf in (recv_r,):
-            if buf is not None and len(buf):
-                a, b, c = self._unpack(buf); parts_xyz.append(a); parts_g.append(b); parts_cx.append(c)
-        xyz4 = torch.cat(parts_xyz) if len(parts_xyz) > 1 else parts_xyz[0]
-        gidx = torch.cat(parts_g) if len(parts_g) > 1 else parts_g[0]
-        cx = torch.cat(parts_cx) if len(parts_cx) > 1 else parts_cx[0]
-        rn = self.plan.reach_nms
-        role = torch.zeros(len(cx), dtype=torch.uint8, device=self.device)
-        role[(cx >= self.c0 - rn) & (cx < self.c1 + rn)] = ROLE_SCORE
-        role[(cx >= self.c0) & (cx < self.c1)] = ROLE_OWNED
-        self._slab = (xyz4, role, gidx)
-        return xyz4, role, gidx
+    def detect(self, scores_out=None, kp_out=None):
+        """kpl_shard_detect.  Returns (global keypoint count, ascending global keypoint indices on rank 0 / None)."""
+        self.det._push()
+        n = C.c_int64(0)
+        kp = kp_out
+        if self.rank == 0 and kp is None:
+            kp = np.empty(self.n_total, np.int32)
+        self._check(self._L.kpl_shard_detect(self._h, None if scores_out is None else scores_out.ctypes.data_as(C.POINTER(C.c_float)),
+                                             None if kp is None else kp.ctypes.data_as(C.POINTER(C.c_int32)),
+                                             0 if kp is None else kp.size, C.byref(n)))
+        return n.value, (kp[:n.value] if self.rank == 0 else None)
 
-    def finish(self, kp_local: torch.Tensor):
-        """kp_local: local indices (into the assembled slab) of this rank's keypoints.  Rank 0 returns the
-        ascending global keypoint index list, the other ranks None."""
-        _, _, gidx = self._slab
-        mine = gidx[kp_local.long()]
-        if self.world == 1:
-            return torch.sort(mine).values
-        cnt = torch.tensor([len(mine)], dtype=torch.int64, device=self.device)
-        cnts = [torch.zeros(1, dtype=torch.int64, device=self.device) for _ in range(self.world)]
-        dist.all_gather(cnts, cnt)
-        cnts = torch.cat(cnts).cpu().tolist()               # one host sync for all ranks' counts
-        mx = max(cnts)
-        pad = torch.full((max(mx, 1),), -1, dtype=torch.int64, device=self.device)
-        pad[:len(mine)] = mine
-        allp = [torch.empty_like(pad) for _ in range(self.world)]
-        dist.all_gather(allp, pad)
-        if self.rank != 0:
-            return None
-        out = torch.cat([a[:c] for a, c in zip(allp, cnts)])
-        return torch.sort(out).values
+    def info(self):
+        i = capi.KplShardInfo()
+        self._check(self._L.kpl_shard_get_info(self._h, C.byref(i)))
+        d = {k: getattr(i, k) for k, _ in capi.KplShardInfo._fields_}
+        d["local_dims"] = list(i.local_dims); d["local_offset"] = list(i.local_offset)
+        return d
 
-    # ---- the GPU step --------------------------------------------------------------------------------
-    def step(self, det):
-        """One full sharded detection step on the GPU.  Returns the global keypoint count on rank 0."""
-        xyz4, role, gidx = self.assemble()
-        n = xyz4.shape[0]
-        if self._kp is None or self._kp.numel() < n:
-            self._kp = torch.empty(n + n // 8, dtype=torch.int32, device=self.device)
-            self._scores = torch.empty(n + n // 8, dtype=torch.float32, device=self.device)
-        det.setForcedGrid(self.plan.origin, self.local_dims, self.offset)
-        if self.device.type == "cuda":
-            # the slab was assembled by torch ops on the current stream: run the detection on that stream too
-            det.setStream(torch.cuda.current_stream(self.device).cuda_stream)
-        nkp = det.detectDevice(xyz4.data_ptr(), n, d_role=role.data_ptr(), d_scores=self._scores.data_ptr(), d_kp_idx=self._kp.data_ptr())
-        glob = self.finish(self._kp[:nkp])
-        self.last_global_keypoints = glob
-        self.last_slab_points = n
-        return int(len(glob)) if glob is not None else 0
+    def device_scores_ptr(self):
+        return self._L.kpl_shard_device_scores(self._h)
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._L.kpl_shard_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+KPL_E_HALO = 12
+
+
+def detect_widening(job, xyz, r_feat, r_nms, cpr, max_support=64, **kw):
+    """job.detect(); on KPL_E_HALO (a k-NN normal that matters was clipped by a slab face -- every rank reports it)
+    re-plan with twice the k-NN support and try again.  The support is thereby derived from the data."""
+    while True:
+        try:
+            return job.detect(**kw)
+        except capi.KplError as e:
+            ns = job.plan.normal_support_cells * 2
+            if e.code != KPL_E_HALO or ns > max_support:
+                raise
+            job.replan(xyz, plan_slabs(xyz, r_feat, r_nms, cpr, job.world, ns))
+
+
+def detect_group_widening(jobs, xyz, r_feat, r_nms, cpr, max_support=64, want_scores=True):
+    """detect_group() with the same widening loop for an in-process group."""
+    while True:
+        try:
+            return detect_group(jobs, want_scores)
+        except capi.KplError as e:
+            ns = jobs[0].plan.normal_support_cells * 2
+            if e.code != KPL_E_HALO or ns > max_support:
+                raise
+            plan = plan_slabs(xyz, r_feat, r_nms, cpr, len(jobs), ns)
+            for j in jobs:
+                j.replan(xyz, plan)
+
+
+def detect_group(jobs, want_scores=True):
+    """kpl_shard_detect_group: all ranks of an in-process group (created with nccl_id=None) from this thread.
+    Returns (global keypoint indices, [owned scores per rank])."""
+    L = capi.load_library()
+    world = len(jobs)
+    for j in jobs:
+        j.det._push()
+    hs = (C.c_void_p * world)(*[j._h for j in jobs])
+    scores = [np.empty(j.n_owned, np.float32) for j in jobs] if want_scores else None
+    f32p = C.POINTER(C.c_float)
+    sc_ptrs = (f32p * world)(*[s.ctypes.data_as(f32p) for s in scores]) if want_scores else None
+    kp = np.empty(jobs[0].n_total, np.int32)
+    n = C.c_int64(0)
+    rc = L.kpl_shard_detect_group(hs, world, sc_ptrs, kp.ctypes.data_as(C.POINTER(C.c_int32)), kp.size, C.byref(n))
+    if rc != 0:
+        raise capi.KplError(rc, (L.kpl_last_error(jobs[0].det._h) or b"").decode())
+    return kp[:n.value].copy(), scores
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# The schedule in numpy (transport and detection stage supplied by the caller): CPU tests only
+# ---------------------------------------------------------------------------------------------------------------
+class HostSlab:
+    """What rank `rank` of `plan` sends, holds and decides -- the host mirror of csrc/shard.cu, used by
+    tests/test_shard_cpu.py over a gloo process group with the CPU oracle as the detection stage."""
+
+    def __init__(self, xyz, plan: SlabPlan, rank: int):
+        self.plan, self.rank, self.world = plan, rank, plan.world
+        self.gidx = partition(plan, xyz, rank).astype(np.int64)
+        self.own = np.ascontiguousarray(np.asarray(xyz, np.float32)[self.gidx, :3])
+        cx = cell_coords(self.own, plan.origin, plan.cell, 0)
+        c0, c1, H = int(plan.cuts[rank]), int(plan.cuts[rank + 1]), plan.halo
+        self.sel_l = np.nonzero(cx < c0 + H)[0] if rank > 0 else np.zeros(0, np.int64)
+        self.sel_r = np.nonzero(cx >= c1 - H)[0] if rank < self.world - 1 else np.zeros(0, np.int64)
+        self.x0 = max(c0 - H, 0) if rank > 0 else 0
+        self.x1 = min(c1 + H, int(plan.dims[0])) if rank < self.world - 1 else int(plan.dims[0])
+
+    def position_strips(self):
+        """(to the left neighbour, to the right neighbour): float32 [m, 3]"""
+        return self.own[self.sel_l], self.own[self.sel_r]
+
+    def assemble(self, from_left, from_right):
+        """[left halo | owned | right halo] and the roles; from_* are the neighbours' strips (None at the ends)."""
+        parts = [p for p in (from_left, self.own, from_right) if p is not None and len(p)]
+        self.n_l = 0 if from_left is None else len(from_left)
+        self.n_r = 0 if from_right is None else len(from_right)
+        self.local = np.ascontiguousarray(np.concatenate(parts))
+        self.role = np.zeros(len(self.local), np.uint8)
+        self.role[self.n_l:self.n_l + len(self.own)] = ROLE_OWNED
+        return self.local, self.role
+
+    def score_strips(self, scores_local):
+        own = scores_local[self.n_l:self.n_l + len(self.own)]
+        return own[self.sel_l], own[self.sel_r]
+
+    def merge_scores(self, scores_local, from_left, from_right):
+        out = scores_local.copy()
+        if self.n_l:
+            out[:self.n_l] = from_left
+        if self.n_r:
+            out[self.n_l + len(self.own):] = from_right
+        return out
+
+    def owned_keypoints(self, kp_local):
+        """local keypoint indices (over the assembled cloud) -> ascending global indices of those this rank owns"""
+        kp_local = np.asarray(kp_local, np.int64)
+        mine = kp_local[(kp_local >= self.n_l) & (kp_local < self.n_l + len(self.own))]
+        return self.gidx[mine - self.n_l]
