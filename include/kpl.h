@@ -120,6 +120,7 @@ KPL_API int kpl_create(int device, kpl_ctx** out);            /* new KeypointLea
 KPL_API void kpl_destroy(kpl_ctx* ctx);                       /* ~KeypointLearningDetector   (KeypointLearning.h:93-97)    */
 KPL_API const char* kpl_last_error(const kpl_ctx* ctx);
 KPL_API const char* kpl_version(void);
+KPL_API int kpl_device_count(void);                           /* usable (compute capability 10.x) devices; 0 without one */
 /* Run on a caller-owned cudaStream_t.  NULL selects the context's own NON-BLOCKING stream, which is not ordered
  * after work on the legacy default stream: a caller working on the default stream passes cudaStreamLegacy. */
 KPL_API int kpl_set_stream(kpl_ctx* ctx, void* cuda_stream);

@@ -83,7 +83,7 @@ def build_host(force: bool = False) -> str:
         if not os.path.exists(os.path.join(HOST, main)) or (not force and not _stale(exe, deps)):
             continue
         cmd = [_host_cxx(), "-O2", "-std=c++17", "-Wall", "-Wextra", "-I", os.path.join(ROOT, "include"), "-I", HOST,
-               os.path.join(HOST, main), *common, "-o", exe, "-L", HERE, "-lkpl_b200", "-Wl,-rpath,$ORIGIN"]
+               os.path.join(HOST, main), *common, "-o", exe, "-L", HERE, "-lkpl_b200", "-lpthread", "-Wl,-rpath,$ORIGIN"]
         subprocess.check_call(cmd)
     return TEST_DETECTOR
 

@@ -24,7 +24,7 @@ EXPORTS = ["kpl_create", "kpl_destroy", "kpl_last_error", "kpl_version", "kpl_se
            "kpl_set_params", "kpl_get_params", "kpl_load_forest", "kpl_set_forest", "kpl_forest_info", "kpl_detect",
            "kpl_normals", "kpl_features", "kpl_radius_stats", "kpl_radius_neighbors", "kpl_detect_device",
            "kpl_get_timings", "kpl_get_stats", "kpl_fetch", "kpl_set_keep_intermediates", "kpl_uniform_sample", "kpl_nearest",
-           "kpl_fetch_u8", "kpl_detect_batch", "kpl_detect_batch_device",
+           "kpl_fetch_u8", "kpl_device_count", "kpl_detect_batch", "kpl_detect_batch_device",
            "kpl_slab_plan_make", "kpl_slab_partition", "kpl_nccl_unique_id", "kpl_shard_create", "kpl_shard_destroy", "kpl_shard_set_plan",
            "kpl_shard_set_slab", "kpl_shard_upload", "kpl_shard_detect", "kpl_shard_detect_group", "kpl_shard_get_info",
            "kpl_shard_device_scores"]
@@ -264,6 +264,11 @@ class KeypointLearningDetector:
             if nrm.shape[0] != n:
                 raise KplError(3, "normals given, but the number of normals does not match the number of input points")
         self._push()
+        # Non-dense clouds: the reference's kd-tree ignores NaN points and runForest skips them (hpp:277).  The finite
+        # points are compacted, detected, and indices / scores mapped back (NaN score, never a keypoint).
+        finite = np.isfinite(xyz[:, :3]).all(axis=1)
+        if not finite.all():
+            return self._compute_compacted(xyz, nrm, finite, role)
         # caller-provided result buffers (e.g. pinned host memory) are used as they are
         scores = np.empty(n, np.float32) if scores_out is None else scores_out
         kp = np.empty(max(n, 1), np.int32) if kp_out is None else kp_out
@@ -325,12 +330,33 @@ class KeypointLearningDetector:
         self._check(self._L.kpl_fetch_u8(self._h, b"fragile", _ptr(out, C.c_uint8), n))
         return out
 
+    def _compute_compacted(self, xyz, nrm, finite, role):
+        keep = np.nonzero(finite)[0]
+        sub = np.ascontiguousarray(xyz[keep])
+        saved = (self._cloud, self._normals)
+        try:
+            self._cloud = sub
+            self._normals = None if nrm is None else np.ascontiguousarray(nrm[keep])
+            kp, idx = self.compute(role=None if role is None else np.ascontiguousarray(role)[keep])
+        finally:
+            self._cloud, self._normals = saved
+        scores = np.full(xyz.shape[0], np.nan, np.float32)
+        scores[keep] = self._scores[:len(keep)]
+        self._scores = scores
+        self._kp_idx = keep[idx].astype(np.int32)
+        return kp, self._kp_idx
+
     def getKeypointsIndices(self): return self._kp_idx
     def getResponse(self): return self._scores
 
     def computeNormals(self, cloud):
         xyz, xs = _vec3(cloud, "cloud")
         self._push()
+        finite = np.isfinite(xyz[:, :3]).all(axis=1)
+        if not finite.all():                          # non-dense cloud: NaN normals for the NaN points (as PCL)
+            out = np.full((xyz.shape[0], 4), np.nan, np.float32)
+            out[finite] = self.computeNormals(np.ascontiguousarray(xyz[finite]))
+            return out
         out = np.empty((xyz.shape[0], 4), np.float32)
         self._check(self._L.kpl_normals(self._h, _ptr(xyz, C.c_float), xs, xyz.shape[0], _ptr(out, C.c_float)))
         return out

@@ -45,6 +45,17 @@ extern "C" {
 
 const char* kpl_version(void) { return "kpl-b200 0.1 (sm_100a)"; }
 
+int kpl_device_count(void)
+{
+    int count = 0, usable = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess) { (void)cudaGetLastError(); return 0; }
+    for (int d = 0; d < count; ++d) {
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, d) == cudaSuccess && prop.major == 10) usable++;
+    }
+    return usable;
+}
+
 int kpl_params_default(kpl_params* p)
 {
     if (!p) return KPL_E_INVALID;

@@ -8,6 +8,7 @@
 // message on stderr and an empty output cloud (impl/KeypointLearning.hpp:119-123,149-153,165-174).
 #pragma once
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <memory>
 #include <string>
@@ -64,9 +65,21 @@ public:
     virtual void setNonMaxRadius(double r) { p_.radius_nms = (float)r; }
     virtual void setNAnnulus(int n) { p_.n_annulus = n; }
     virtual void setNBins(int n) { p_.n_bins = n; }
-    void setRadiusSearch(double r) { p_.radius_features = (float)r; }          // pcl::Keypoint
-    void setKSearch(int) {}                                                     // pcl::Keypoint (k search is an error with a radius, see initCompute)
-    void setCellsPerRadius(int cpr) { p_.cells_per_radius = cpr; }             // B200 build only
+    // ---- inherited from pcl::Keypoint in the reference (include/KeypointLearning.h:55-56)
+    void setRadiusSearch(double r) { p_.radius_features = (float)r; }
+    // pcl::Keypoint::initCompute refuses a radius AND a k; a k alone would make computePointFeatures divide by a zero
+    // support (hpp:345 passes search_radius_): both cases fail in initCompute() below, as they do upstream
+    void setKSearch(int k) { k_ = k; }
+    // Neighbour searches of this build always run on the uniform grid inside libkpl_b200 with the radiusSearch
+    // semantics of the kd-tree the reference installs (hpp:116-124): any search object is accepted and has no effect.
+    void setSearchMethod(const typename pcl::search::KdTree<PointInT>::Ptr&) {}
+    // The reference indexes normals_, response and the kd-tree with ONE index space (hpp:203-253,334-342), which only
+    // holds when the search surface is the input cloud: another surface is refused in initCompute().
+    void setSearchSurface(const PointCloudInConstPtr& cloud) { surface_ = cloud; }
+    // ---- B200 build only
+    void setCellsPerRadius(int cpr) { p_.cells_per_radius = cpr; }
+    void setReportFragile(bool on) { p_.report_fragile = on; }                 // kpl_stats.n_fragile_points
+    const kpl_params& params() const { return p_; }
 
     // impl/KeypointLearning.hpp:159-176
     virtual bool loadForest(const std::string& path)
@@ -92,8 +105,33 @@ public:
         std::vector<int32_t> idx((size_t)std::max<int64_t>(n, 1));
         int64_t nkp = 0;
         const float* nrm = normals_ ? reinterpret_cast<const float*>(normals_->points.data()) : nullptr;
-        int rc = kpl_detect(ctx_, reinterpret_cast<const float*>(input_->points.data()), (int32_t)sizeof(PointInT), nrm, (int32_t)sizeof(NormalT),
+        // Non-dense clouds (Kinect / organized PCDs carry NaN points): the reference's kd-tree ignores them and runForest
+        // skips them (hpp:277).  Here the finite points are compacted, detected, and the results mapped back; a skipped
+        // point has a NaN response and is never a keypoint.
+        std::vector<int32_t> finite;
+        for (int64_t i = 0; i < n; ++i)
+            if (pcl::isFinite(input_->points[(size_t)i])) finite.push_back((int32_t)i);
+        int rc;
+        if ((int64_t)finite.size() == n) {
+            rc = kpl_detect(ctx_, reinterpret_cast<const float*>(input_->points.data()), (int32_t)sizeof(PointInT), nrm, (int32_t)sizeof(NormalT),
                             nullptr, n, response_.data(), idx.data(), &nkp);
+        } else {
+            const int64_t m = (int64_t)finite.size();
+            std::vector<PointInT> pts((size_t)m);
+            std::vector<NormalT> nrs(normals_ ? (size_t)m : 0);
+            for (int64_t k = 0; k < m; ++k) {
+                pts[(size_t)k] = input_->points[(size_t)finite[(size_t)k]];
+                if (normals_) nrs[(size_t)k] = normals_->points[(size_t)finite[(size_t)k]];
+            }
+            std::vector<float> sc((size_t)std::max<int64_t>(m, 1));
+            rc = kpl_detect(ctx_, reinterpret_cast<const float*>(pts.data()), (int32_t)sizeof(PointInT),
+                            normals_ ? reinterpret_cast<const float*>(nrs.data()) : nullptr, (int32_t)sizeof(NormalT), nullptr, m, sc.data(), idx.data(), &nkp);
+            if (rc == KPL_OK) {
+                response_.assign((size_t)n, std::nanf(""));
+                for (int64_t k = 0; k < m; ++k) response_[(size_t)finite[(size_t)k]] = sc[(size_t)k];
+                for (int64_t k = 0; k < nkp; ++k) idx[(size_t)k] = finite[(size_t)idx[(size_t)k]];
+            }
+        }
         if (rc != KPL_OK) {
             std::fprintf(stderr, "[pcl::%s::compute] %s\n", name_.c_str(), kpl_last_error(ctx_));
             return;
@@ -142,8 +180,21 @@ protected:
             std::fprintf(stderr, "[pcl::%s::initCompute] init failed!\n", name_.c_str());
             return false;
         }
-        if (!(p_.radius_features > 0.f)) {        // pcl::Keypoint::initCompute: neither radius nor k set
-            std::fprintf(stderr, "[pcl::%s::initCompute] Neither radius nor K defined! Set one of them to zero first and then re-run compute ().\n", name_.c_str());
+        if (surface_ && surface_ != input_) {
+            std::fprintf(stderr, "[pcl::%s::initCompute] a search surface other than the input cloud is not supported: normals, response and "
+                                 "neighbour indices share one index space (hpp:203-253,334-342)\n", name_.c_str());
+            return false;
+        }
+        if (p_.radius_features > 0.f && k_ != 0) {   // pcl::Keypoint::initCompute
+            std::fprintf(stderr, "[pcl::%s::initCompute] Both radius (%f) and K (%d) defined! Set one of them to zero first and then re-run compute ().\n",
+                         name_.c_str(), p_.radius_features, k_);
+            return false;
+        }
+        if (!(p_.radius_features > 0.f)) {
+            if (k_ != 0)
+                std::fprintf(stderr, "[pcl::%s::initCompute] a k search gives computePointFeatures a zero support (hpp:345): set a radius with setRadiusSearch\n", name_.c_str());
+            else
+                std::fprintf(stderr, "[pcl::%s::initCompute] Neither radius nor K defined! Set one of them to zero first and then re-run compute ().\n", name_.c_str());
             return false;
         }
         if (normals_ && normals_->size() != input_->size()) {
@@ -172,7 +223,8 @@ protected:
     kpl_ctx* ctx_ = nullptr;
     int create_rc_ = KPL_OK;
     kpl_params p_;
-    PointCloudInConstPtr input_;
+    int k_ = 0;
+    PointCloudInConstPtr input_, surface_;
     PointCloudNConstPtr normals_;
     pcl::PointIndicesPtr keypoints_indices_;
     std::vector<float> response_;

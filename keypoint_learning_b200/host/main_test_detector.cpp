@@ -4,7 +4,9 @@
 // annuli/bins, compile-time 5/10 in the reference (:105-106), are the run-time options --annuli/--bins.
 // Same progress lines on stdout, same exit codes (0 on --help or a parse error :112-113, -1 when the
 // forest fails to load :136-139).  The PCLVisualizer window (:190-210) has no headless equivalent and
-// is dropped; --stats prints the device-time breakdown instead.
+// is dropped; --stats prints the device-time breakdown instead.  --gpus N (B200 build only) cuts the cloud into N x
+// slabs and runs one rank per GPU of this node through kpl_shard_* (NCCL halo exchange inside libkpl_b200.so); the
+// keypoints are those of the single-GPU run, bit for bit.
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -13,6 +15,7 @@
 #include <string>
 
 #include "KeypointLearning.h"
+#include "KeypointLearningSharded.h"
 
 typedef pcl::PointXYZ PointInT;
 typedef pcl::Normal PointNormalT;
@@ -45,15 +48,16 @@ void print_help()
                  "  -t [ --threshold ] arg (=0.850000024) Threshold for random forest prediction.\n"
                  "  --annuli arg (=5)                     Number of annuli of the feature histogram.\n"
                  "  --bins arg (=10)                      Number of cosine bins of the feature histogram.\n"
-                 "  --stats                               Print device timings and counters of the detection.\n";
+                 "  --stats                               Print device timings and counters of the detection.\n"
+                 "  --gpus arg (=1)                       GPUs of this node to spread the cloud over (x slabs + halo over NCCL).\n";
 }
 
 // boost::program_options subset: --name value, --name=value, -t value, -h, boolean switches
 bool parseCommandLine(int argc, char** argv, Options& vm)
 {
     vm.values = {{"pathCloud", "../../../data/point_cloud_test/cheff001.pcd"}, {"pathRF", "../../../data/forest/SHOT-LaserScanner.yaml.gz"},
-                 {"radiusFeatures", "20"}, {"radiusNMS", "4"}, {"threshold", "0.85"}, {"annuli", "5"}, {"bins", "10"}};
-    const char* valued[] = {"leaf", "pathCloud", "pathRF", "pathKP", "radiusFeatures", "radiusNMS", "threshold", "annuli", "bins"};
+                 {"radiusFeatures", "20"}, {"radiusNMS", "4"}, {"threshold", "0.85"}, {"annuli", "5"}, {"bins", "10"}, {"gpus", "1"}};
+    const char* valued[] = {"leaf", "pathCloud", "pathRF", "pathKP", "radiusFeatures", "radiusNMS", "threshold", "annuli", "bins", "gpus"};
     const char* switches[] = {"help", "flipNormals", "subSampling", "stats"};
     for (int i = 1; i < argc; ++i) {
         std::string a = argv[i], name, val;
@@ -110,6 +114,56 @@ int main(int argc, char** argv)
     const int bins = std::atoi(vm.as_string("bins").c_str());
     const std::string path_rf = vm.as_string("pathRF");
     const std::string path_cloud = vm.as_string("pathCloud");
+    const int gpus = std::atoi(vm.as_string("gpus").c_str());
+
+    if (gpus > 1) {
+        // the same sequence as below over several GPUs; the k-NN(10) normals of :161-170 are estimated on the devices,
+        // slab by slab, with the --flipNormals re-orientation applied there
+        pcl::keypoints::ShardedKeypointLearningDetector<PointInT, KeypointT> detector(gpus);
+        detector.setNAnnulus(annuli);
+        detector.setNBins(bins);
+        detector.setNonMaxima(true);
+        detector.setNonMaxRadius(radius_nms);
+        detector.setNonMaximaDrawsRemove(false);
+        detector.setPredictionThreshold(threshold);
+        detector.setRadiusSearch(radius_features);
+        if (detector.loadForest(path_rf)) std::cout << "Detector created." << std::endl;
+        else return -1;
+        pcl::PointCloud<PointInT>::Ptr cloud(new pcl::PointCloud<PointInT>());
+        pcl::io::loadPCDFile(path_cloud, *cloud);
+        if (vm.count("subSampling")) {
+            pcl::UniformSampling<PointInT> source_uniform_sampling;
+            source_uniform_sampling.setRadiusSearch(vm.as_float("leaf"));
+            source_uniform_sampling.setInputCloud(cloud);
+            source_uniform_sampling.filter(*cloud);
+        }
+        std::cout << "Point cloud loaded" << std::endl;
+        detector.setNormalEstimation(10, vm.count("flipNormals"));
+        if (vm.count("flipNormals")) std::cout << "Flipping " << std::endl;
+        detector.setInputCloud(cloud);
+        pcl::PointCloud<KeypointT>::Ptr keypoint(new pcl::PointCloud<KeypointT>());
+        if (!detector.compute(*keypoint)) return -1;
+        std::cout << "Normals Computed" << std::endl;
+        std::cout << "Keypoint computed" << std::endl;
+        if (vm.count("stats")) {
+            const kpl_slab_plan& L = detector.plan();
+            std::printf("points %lld keypoints %zu slabs %d halo_cells %d normal_support_cells %d\n", (long long)L.n_points, keypoint->size(), L.world,
+                        L.halo, L.normal_support_cells);
+            for (int g = 0; g < gpus; ++g) {
+                kpl_timings t;
+                kpl_stats st;
+                kpl_get_timings(detector.rank(g).context(), &t);
+                kpl_get_stats(detector.rank(g).context(), &st);
+                const kpl_shard_info& I = detector.info()[(size_t)g];
+                std::printf("rank %d: columns [%d,%d) owned %lld halo %lld+%lld scored %lld pairs %lld device ms %.3f (features %.3f) exchange ms %.3f\n", g,
+                            L.cuts[g], L.cuts[g + 1], (long long)I.n_owned, (long long)I.n_left, (long long)I.n_right, (long long)st.n_scored,
+                            (long long)st.feature_pairs, t.total_ms, t.features_ms, I.exchange_ms);
+            }
+        }
+        std::cout << "DONE" << std::endl;
+        if (vm.count("pathKP")) pcl::io::savePCDFileASCII(vm.as_string("pathKP"), *keypoint);
+        return 0;
+    }
 
     // create detector (reference :123-130)
     pcl::keypoints::KeypointLearningDetector<PointInT, KeypointT>::Ptr detector(new pcl::keypoints::KeypointLearningDetector<PointInT, KeypointT>());

@@ -243,7 +243,19 @@ bool NormalEstimation<PointInT, NormalT>::compute(PointCloud<NormalT>& out, std:
     bool ok = kpl_set_params(ctx, &p) == KPL_OK;
     const size_t n = input_->size();
     std::vector<float> buf(n * 4);
-    ok = ok && kpl_normals(ctx, reinterpret_cast<const float*>(input_->points.data()), (int32_t)sizeof(PointInT), (int64_t)n, buf.data()) == KPL_OK;
+    // non-dense clouds: PCL's search ignores NaN points and gives them NaN normals; only the finite points go to the device
+    std::vector<size_t> finite;
+    for (size_t i = 0; i < n; ++i) if (isFinite(input_->points[i])) finite.push_back(i);
+    if (finite.size() == n) {
+        ok = ok && kpl_normals(ctx, reinterpret_cast<const float*>(input_->points.data()), (int32_t)sizeof(PointInT), (int64_t)n, buf.data()) == KPL_OK;
+    } else {
+        std::vector<PointInT> pts(finite.size());
+        std::vector<float> sub(finite.size() * 4);
+        for (size_t k = 0; k < finite.size(); ++k) pts[k] = input_->points[finite[k]];
+        ok = ok && kpl_normals(ctx, reinterpret_cast<const float*>(pts.data()), (int32_t)sizeof(PointInT), (int64_t)pts.size(), sub.data()) == KPL_OK;
+        std::fill(buf.begin(), buf.end(), std::nanf(""));
+        for (size_t k = 0; ok && k < finite.size(); ++k) std::copy(sub.begin() + 4 * k, sub.begin() + 4 * k + 4, buf.begin() + 4 * finite[k]);
+    }
     std::string msg = ok ? "" : kpl_last_error(ctx);
     kpl_destroy(ctx);
     if (!ok) return fail(msg);

@@ -153,3 +153,52 @@ def test_cli_end_to_end_matches_golden(tools, tmp_path, views, golden, view, dat
     assert r2.returncode == 0 and "Flipping" in r2.stdout
     r3 = subprocess.run([tools.TEST_DETECTOR, "--pathCloud", cloud, "--pathRF", forest, "--annuli", "4", "--bins", "8"], capture_output=True, text=True)
     assert r3.returncode == 0 and "annuli*bins does not match" in r3.stderr   # var_count mismatch is reported, output empty
+
+
+@pytest.mark.gpu
+def test_cli_gpus_option_matches_single_gpu(tools, tmp_path, views, golden):
+    """TestDetector --gpus N (x slabs through kpl_shard_*; with fewer devices than ranks the ranks share the devices as an
+    in-process group) writes the keypoints of the single-GPU run."""
+    cloud = str(tmp_path / "cloud.pcd")
+    xyz = np.ascontiguousarray(views["cheff001"][:, [1, 0, 2]])         # longest axis onto the slab axis
+    write_pcd(cloud, xyz, "binary")
+    forest = os.path.join(ROOT, "tests", "golden", "forests", "synthetic-T100-D15.yaml.gz")
+    out = {}
+    for gpus in (1, 3):
+        kp = str(tmp_path / ("kp%d.pcd" % gpus))
+        r = subprocess.run([tools.TEST_DETECTOR, "--pathCloud", cloud, "--pathRF", forest, "--pathKP", kp, "--stats", "--gpus", str(gpus)],
+                           capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout + r.stderr
+        assert "Keypoint computed" in r.stdout and "DONE" in r.stdout
+        if gpus > 1:
+            assert "rank 2:" in r.stdout and "slabs 3" in r.stdout
+        out[gpus] = open(kp).read().splitlines()[11:]
+    assert len(out[1]) == len(golden["cheff001"]["keypoints"])
+    assert out[1] == out[3]
+
+
+@pytest.mark.gpu
+def test_non_dense_clouds_are_compacted(kpl, views, golden):
+    """NaN points (non-dense clouds) are skipped like the reference's kd-tree / runForest do (hpp:277): the facades compact
+    the finite points, detect, and map indices and scores back."""
+    import keypoint_learning_b200 as K
+    xyz = views["cheff001"]
+    holes = np.arange(5, len(xyz), 997)
+    dirty = np.insert(xyz, holes, np.nan, axis=0).astype(np.float32)
+    keep = np.nonzero(np.isfinite(dirty).all(axis=1))[0]
+    assert len(keep) == len(xyz) and len(dirty) > len(xyz)
+    det = K.KeypointLearningDetector()
+    det.setNAnnulus(5); det.setNBins(10); det.setNonMaxima(True); det.setNonMaxRadius(4.0); det.setNonMaximaDrawsRemove(False)
+    det.setPredictionThreshold(float(np.float32(0.85))); det.setRadiusSearch(20.0); det.setNormalsMode(1, k=10)
+    assert det.loadForest(os.path.join(ROOT, "tests", "golden", "forests", "synthetic-T100-D15.yaml.gz"))
+    det.setInputCloud(dirty)
+    kp, idx = det.compute()
+    g = golden["cheff001"]
+    assert np.array_equal(idx, keep[g["keypoints"]])
+    sc = det.getResponse()
+    assert np.all(np.isnan(sc[~np.isfinite(dirty).all(axis=1)]))
+    assert np.array_equal(sc[keep].view(np.uint32), g["scores"].view(np.uint32))
+    nrm = det.computeNormals(dirty)
+    assert np.all(np.isnan(nrm[~np.isfinite(dirty).all(axis=1)]))
+    assert np.array_equal(nrm[keep].view(np.uint32), g["normals"].view(np.uint32)) if "normals" in g.files else True
+    det.close()
