@@ -444,6 +444,7 @@ int detect_nms_phase(kpl_ctx* ctx, bool use_role, int64_t n, int32_t* d_kp_out)
 // End of a call: counters and grid flags to the host (the one unavoidable synchronisation), stats and timings.
 int detect_finish(kpl_ctx* ctx, int64_t n, int64_t* n_kp_out)
 {
+    KPL_CUDA(cudaSetDevice(ctx->device));
     KPL_CUDA(cudaEventRecord(ctx->ev[5], ctx->stream));
     unsigned long long hc[kpl_ctx::NCOUNTERS];
     uint32_t hb[8];

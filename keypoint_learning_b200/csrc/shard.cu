@@ -236,6 +236,7 @@ int phase_pack(kpl_shard* s)
 int phase_score(kpl_shard* s)
 {
     kpl_ctx* c = s->ctx;
+    KS_CUDA(cudaSetDevice(c->device));
     KS_CUDA(cudaEventRecord(s->ev[1], c->stream));
     int rc = detect_begin(c);
     if (rc) return rc;
@@ -254,6 +255,7 @@ int phase_score(kpl_shard* s)
 int phase_nms(kpl_shard* s)
 {
     kpl_ctx* c = s->ctx;
+    KS_CUDA(cudaSetDevice(c->device));             // an in-process group drives ranks on several devices from one thread
     KS_CUDA(cudaEventRecord(s->ev[3], c->stream));
     if (s->n_l + s->n_r > 0)
         halo_scores_kernel<<<(unsigned)((s->n_loc + 255) / 256), 256, 0, c->stream>>>(c->s_pos.p, c->s_role.p, c->score.p, s->n_loc, c->s_score.p);
@@ -610,6 +612,7 @@ int kpl_shard_upload(kpl_shard* s, const float* xyz, int32_t stride)
 static int copy_out(kpl_shard* s, float* scores_owned_out, int32_t* kp_global_out, int64_t kp_capacity, int64_t total)
 {
     kpl_ctx* c = s->ctx;
+    KS_CUDA(cudaSetDevice(c->device));
     if (scores_owned_out)
         KS_CUDA(cudaMemcpyAsync(scores_owned_out, c->score.p + s->n_l, (size_t)s->n_own * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     if (s->rank == 0 && kp_global_out && total > 0) {

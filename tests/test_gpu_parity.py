@@ -533,13 +533,34 @@ def test_query_without_finite_normal_is_unscored(kpl, views, oracle, main_forest
 
 
 # ---------------------------------------------------------------------------------------------
-# slab sharding emulated on one GPU: union of the slabs' owned results == the unsharded run
+# per-point roles + forced grid through plain kpl_detect: a slab of a larger cloud, self-contained (the band
+# within reach(r_nms) of the owned range is scored locally with role SCORE, no exchange) -- the role semantics of
+# include/kpl.h.  The multi-rank schedule of kpl_shard_* is covered by tests/test_gpu_multi.py.
 # ---------------------------------------------------------------------------------------------
+def _role_slab(xyz, plan, rank, support=2):
+    from keypoint_learning_b200 import shard
+    world = plan.world
+    cx = shard.cell_coords(xyz, plan.origin, plan.cell, 0)
+    c0, c1 = int(plan.cuts[rank]), int(plan.cuts[rank + 1])
+    halo = plan.reach_nms + plan.reach_feat + support
+    lo = c0 - halo if rank > 0 else 0
+    hi = c1 + halo if rank < world - 1 else int(plan.dims[0])
+    lo, hi = max(lo, 0), min(hi, int(plan.dims[0]))
+    gidx = np.nonzero((cx >= lo) & (cx < hi))[0]
+    c = cx[gidx]
+    role = np.zeros(len(gidx), np.uint8)
+    role[(c >= c0 - plan.reach_nms) & (c < c1 + plan.reach_nms)] = 1
+    role[(c >= c0) & (c < c1)] = 3
+    xyz4 = np.ones((len(gidx), 4), np.float32)
+    xyz4[:, :3] = xyz[gidx]
+    return dict(xyz4=xyz4, role=role, gidx=gidx, local_dims=np.array([hi - lo, plan.dims[1], plan.dims[2]], np.int32),
+                offset=np.array([lo, 0, 0], np.int32), interior=(rank > 0, rank < world - 1))
+
+
 @pytest.mark.parametrize("world", [2, 3])
 def test_slab_results_equal_unsharded(kpl, views, golden, world):
     from keypoint_learning_b200 import shard
     xyz = views["cheff001"]
-    g = golden["cheff001"]
     # shard along the longest axis of this view (y): rotate it onto x, the slab axis
     xyz_r = np.ascontiguousarray(xyz[:, [1, 0, 2]])
     d = make_detector(kpl)
@@ -550,19 +571,29 @@ def test_slab_results_equal_unsharded(kpl, views, golden, world):
     plan = shard.plan_slabs(xyz_r, R_FEAT, R_NMS, 4, world)
     kps, seen = [], np.zeros(len(xyz), bool)
     for rank in range(world):
-        s = shard.reference_slab(xyz_r, plan, rank)
+        s = _role_slab(xyz_r, plan, rank)
         d.setForcedGrid(plan.origin, s["local_dims"], s["offset"])
         d.setInputCloud(s["xyz4"])
         _, idx = d.compute(role=s["role"])
         sc = d.getResponse()
         owned = s["role"] == 3
+        scored = (s["role"] & 1) == 1
+        assert d.stats()["n_scored"] == int(scored.sum())
+        assert np.all(np.isnan(sc[~scored]))
         assert not seen[s["gidx"][owned]].any()
         seen[s["gidx"][owned]] = True
-        assert np.array_equal(sc[owned].view(np.uint32), sc_full[s["gidx"][owned]].view(np.uint32))   # bit-identical scores
-        assert np.all(owned[idx])                                                                    # only owned points are output
+        assert np.array_equal(sc[scored].view(np.uint32), sc_full[s["gidx"][scored]].view(np.uint32))   # bit-identical scores
+        assert np.all(owned[idx])                                                                      # only owned points are output
         kps.append(s["gidx"][idx])
     assert seen.all()
     assert np.array_equal(np.sort(np.concatenate(kps)), idx_full)
+    # the same slab with the clipped-support check armed and no support columns: refused, not silently different
+    s = _role_slab(xyz_r, plan, 0, support=0)
+    d.setForcedGrid(plan.origin, s["local_dims"], s["offset"], interior=s["interior"], guard_cells=0)
+    d.setInputCloud(s["xyz4"])
+    with pytest.raises(kpl.KplError) as e:
+        d.compute(role=s["role"])
+    assert e.value.code == 12
     d.setForcedGrid(None)
     d.close()
 
