@@ -264,11 +264,6 @@ class KeypointLearningDetector:
             if nrm.shape[0] != n:
                 raise KplError(3, "normals given, but the number of normals does not match the number of input points")
         self._push()
-        # Non-dense clouds: the reference's kd-tree ignores NaN points and runForest skips them (hpp:277).  The finite
-        # points are compacted, detected, and indices / scores mapped back (NaN score, never a keypoint).
-        finite = np.isfinite(xyz[:, :3]).all(axis=1)
-        if not finite.all():
-            return self._compute_compacted(xyz, nrm, finite, role)
         # caller-provided result buffers (e.g. pinned host memory) are used as they are
         scores = np.empty(n, np.float32) if scores_out is None else scores_out
         kp = np.empty(max(n, 1), np.int32) if kp_out is None else kp_out
@@ -276,8 +271,14 @@ class KeypointLearningDetector:
             raise KplError(1, "scores_out / kp_out must be float32[n] / int32[n]")
         nkp = C.c_int64(0)
         r = None if role is None else np.ascontiguousarray(role, np.uint8)
-        self._check(self._L.kpl_detect(self._h, _ptr(xyz, C.c_float), xs, _ptr(nrm, C.c_float), ns or 0, _ptr(r, C.c_uint8), n,
-                                       _ptr(scores, C.c_float), _ptr(kp, C.c_int32), C.byref(nkp)))
+        rc = self._L.kpl_detect(self._h, _ptr(xyz, C.c_float), xs, _ptr(nrm, C.c_float), ns or 0, _ptr(r, C.c_uint8), n,
+                                _ptr(scores, C.c_float), _ptr(kp, C.c_int32), C.byref(nkp))
+        if rc == 4:
+            # KPL_E_NONFINITE (found by the device's bounding-box pass, no host scan): a non-dense cloud.  The reference's
+            # kd-tree ignores NaN points and runForest skips them (hpp:277): compact the finite points, detect, and map
+            # indices / scores back (NaN score, never a keypoint).
+            return self._compute_compacted(xyz, nrm, np.isfinite(xyz[:, :3]).all(axis=1), role)
+        self._check(rc)
         self._scores = scores
         self._kp_idx = kp[:nkp.value].copy()
         out = np.empty((nkp.value, 4), np.float32)
@@ -352,13 +353,14 @@ class KeypointLearningDetector:
     def computeNormals(self, cloud):
         xyz, xs = _vec3(cloud, "cloud")
         self._push()
-        finite = np.isfinite(xyz[:, :3]).all(axis=1)
-        if not finite.all():                          # non-dense cloud: NaN normals for the NaN points (as PCL)
+        out = np.empty((xyz.shape[0], 4), np.float32)
+        rc = self._L.kpl_normals(self._h, _ptr(xyz, C.c_float), xs, xyz.shape[0], _ptr(out, C.c_float))
+        if rc == 4:                                   # non-dense cloud: NaN normals for the NaN points (as PCL)
+            finite = np.isfinite(xyz[:, :3]).all(axis=1)
             out = np.full((xyz.shape[0], 4), np.nan, np.float32)
             out[finite] = self.computeNormals(np.ascontiguousarray(xyz[finite]))
             return out
-        out = np.empty((xyz.shape[0], 4), np.float32)
-        self._check(self._L.kpl_normals(self._h, _ptr(xyz, C.c_float), xs, xyz.shape[0], _ptr(out, C.c_float)))
+        self._check(rc)
         return out
 
     def computePointsForTrainingFeatures(self, indices=None):

@@ -114,7 +114,7 @@ void kpl_destroy(kpl_ctx* ctx)
     release(ctx->key_a); release(ctx->key_b); release(ctx->idx_a); release(ctx->idx_b); release(ctx->cub_tmp);
     release(ctx->row_warps_n); release(ctx->row_offset_n); release(ctx->fragile); release(ctx->views); release(ctx->layer_view);
     release(ctx->view_offsets); release(ctx->qlist);
-    release(ctx->cell_start); release(ctx->row_warps); release(ctx->row_offset); release(ctx->work); release(ctx->work_n); release(ctx->s_pos); release(ctx->s_nrm); release(ctx->feat);
+    release(ctx->cell_start); release(ctx->row_warps); release(ctx->row_offset); release(ctx->work); release(ctx->work_n); release(ctx->work_tmp); release(ctx->s_pos); release(ctx->s_nrm); release(ctx->feat);
     release(ctx->s_score); release(ctx->score); release(ctx->flag); release(ctx->s_state); release(ctx->kp_idx);
     release(ctx->scratch_f); release(ctx->scratch_i); release(ctx->counters);
     if (ctx->d_bbox) cudaFree(ctx->d_bbox);
@@ -357,6 +357,12 @@ static int prepare_lists(kpl_ctx* ctx, bool normals_given, bool want_features)
     ctx->nwarps_norm = ctx->nwarps_feat = 0;
     if (span_n < 0 && span_f < 0) return KPL_OK;
     KPL_CUDA(build_work_lists(ctx, span_n, span_f));
+    // A launch of few waves (a slab of a multi-GPU job, a single view) ends with a long idle tail unless the expensive
+    // warps start first; a cloud whose sorted arrays exceed the L2 keeps the spatial order of its list instead, so that
+    // concurrently running warps keep sharing candidate rows (there the tail is a percent of the launch anyway).
+    const int64_t slots = 148 * 28;
+    if (span_f >= 0 && ctx->nwarps_feat > slots && ctx->nwarps_feat < 24 * slots && ctx->last_n * 32 < (int64_t)120e6)
+        KPL_CUDA(sort_work_longest_first(ctx, ctx->nwarps_feat, P.radius_features));
     return KPL_OK;
 }
 

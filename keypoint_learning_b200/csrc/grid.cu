@@ -304,6 +304,67 @@ cudaError_t build_work_lists(kpl_ctx* c, int span_n, int span_f)
     return cudaGetLastError();
 }
 
+// ---- longest-first order of the feature kernel's work list --------------------------------------------------
+// One warp of the feature kernel runs for milliseconds (32 queries x thousands of neighbours), so a launch of only a
+// few waves -- one slab of an 8-GPU job is ~9 -- idles ~half a warp-time per SM slot at its end.  Launching the
+// expensive warps first (LPT scheduling) leaves the cheap ones for the tail.  Cost estimate = candidate points in the
+// warp's search box (the rows the kernel will stage, same culling).  Blocks retire independently, so the order of the
+// list never changes a result.
+__global__ void __launch_bounds__(128) warp_cost_kernel(const int2* __restrict__ work, int nwarps, const uint32_t* __restrict__ skey,
+                                                        const int32_t* __restrict__ cell_start, int dimx, int dimy, int dimz, int reach,
+                                                        float cellf, float rcull2, uint32_t* __restrict__ cost, uint32_t* __restrict__ order)
+{
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= nwarps) return;
+    const int2 item = __ldg(work + w);
+    const uint32_t k0 = __ldg(skey + item.x), k1 = __ldg(skey + item.x + item.y - 1);
+    const uint32_t t = k0 / (uint32_t)dimx;
+    const int minx = (int)(k0 - t * (uint32_t)dimx), maxx = (int)(k1 - (k1 / (uint32_t)dimx) * (uint32_t)dimx);
+    const int gz0 = (int)(t / (uint32_t)dimy), gy0 = (int)(t - (uint32_t)gz0 * (uint32_t)dimy);
+    unsigned c = 0;
+    for (int zz = max(gz0 - reach, 0); zz <= min(gz0 + reach, dimz - 1); ++zz)
+        for (int yy = max(gy0 - reach, 0); yy <= min(gy0 + reach, dimy - 1); ++yy) {
+            const int gy = max(abs(yy - gy0) - 1, 0), gz = max(abs(zz - gz0) - 1, 0);
+            const float gap2 = (float)(gy * gy + gz * gz) * cellf * cellf;
+            if (!(gap2 < rcull2)) continue;
+            const int rx = min((int)(sqrtf(rcull2 - gap2) / cellf) + 1, reach);
+            const int64_t base = ((int64_t)zz * dimy + yy) * dimx;
+            c += (unsigned)(__ldg(cell_start + base + min(maxx + rx, dimx - 1) + 1) - __ldg(cell_start + base + max(minx - rx, 0)));
+        }
+    cost[w] = c;
+    order[w] = (uint32_t)w;
+}
+__global__ void __launch_bounds__(256) permute_work_kernel(const int2* __restrict__ work, const uint32_t* __restrict__ order, int nwarps,
+                                                           int2* __restrict__ out)
+{
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w < nwarps) out[w] = work[order[w]];
+}
+// Reorders c->work (nwarps entries) by descending cost estimate.
+cudaError_t sort_work_longest_first(kpl_ctx* c, int nwarps, float radius)
+{
+    if (nwarps < 2) return cudaSuccess;
+    const GridDesc& g = c->grid;
+    cudaError_t e;
+    if ((e = ensure(c->scratch_i, 4 * (size_t)nwarps + 16)) || (e = ensure(c->work_tmp, (size_t)nwarps + 1))) return e;
+    uint32_t* cost_a = (uint32_t*)c->scratch_i.p;
+    uint32_t* cost_b = cost_a + nwarps;
+    uint32_t* ord_a = cost_b + nwarps;
+    uint32_t* ord_b = ord_a + nwarps;
+    size_t bytes = 0;
+    cub::DeviceRadixSort::SortPairsDescending(nullptr, bytes, cost_a, cost_b, ord_a, ord_b, nwarps, 0, 32, c->stream);
+    if ((e = ensure(c->cub_tmp, bytes))) return e;
+    const double r = (double)radius;
+    warp_cost_kernel<<<(nwarps + 127) / 128, 128, 0, c->stream>>>(c->work.p, nwarps, c->key_b.p, c->cell_start.p, g.dim[0], g.dim[1], g.dim[2],
+                                                                   g.reach_feat, (float)g.cell, (float)(r * r * (1.0 + 1e-5)), cost_a, ord_a);
+    bytes = c->cub_tmp.cap;
+    if ((e = cub::DeviceRadixSort::SortPairsDescending(c->cub_tmp.p, bytes, cost_a, cost_b, ord_a, ord_b, nwarps, 0, 32, c->stream))) return e;
+    permute_work_kernel<<<(nwarps + 255) / 256, 256, 0, c->stream>>>(c->work.p, ord_b, nwarps, c->work_tmp.p);
+    std::swap(c->work, c->work_tmp);
+    c->launches += 2 + 5;
+    return cudaGetLastError();
+}
+
 // ---- occupied cells (kpl_normals sizes its k-NN grid from the data) ---------------------------------------
 __global__ void __launch_bounds__(256) count_heads_kernel(const uint32_t* __restrict__ skey, int64_t n, unsigned long long* __restrict__ out)
 {

@@ -94,7 +94,7 @@ struct kpl_ctx {
     kpl::DevBuf<int32_t> row_warps, row_offset;   // feature-kernel work list: warps per cell row and their prefix sum
     kpl::DevBuf<int32_t> row_warps_n, row_offset_n;   // same for the normal kernels' list
     int nwarps_feat = 0, nwarps_norm = 0;         // sizes of work / work_n for the grid in place
-    kpl::DevBuf<int2> work, work_n;               // (first sorted position, count <= 32) per warp: feature / normal kernels
+    kpl::DevBuf<int2> work, work_n, work_tmp;     // (first sorted position, count <= 32) per warp: feature / normal kernels
     kpl::DevBuf<float4> s_pos, s_nrm;            // cell-sorted positions (w = original index bits) / normals
     kpl::DevBuf<float> feat;                     // n x F, sorted order
     kpl::DevBuf<float> s_score, score;           // sorted order / original order
@@ -136,6 +136,7 @@ cudaError_t launch_check_normals(kpl_ctx* c, int64_t n, bool use_role);
 bool normals_knn_uses_work_list(const kpl_params& P);
 int feature_span(const kpl_params& P);
 cudaError_t launch_bbox_init(kpl_ctx* c);
+cudaError_t sort_work_longest_first(kpl_ctx* c, int nwarps, float radius);
 cudaError_t launch_count_occupied_cells(kpl_ctx* c, int64_t n, unsigned long long* d_out);
 cudaError_t build_query_list(kpl_ctx* c, int64_t n, const int32_t* d_indices, int64_t m);
 cudaError_t launch_scatter_rows(kpl_ctx* c, const float* d_rows, int64_t m, int width, float* d_out);

@@ -105,17 +105,15 @@ public:
         std::vector<int32_t> idx((size_t)std::max<int64_t>(n, 1));
         int64_t nkp = 0;
         const float* nrm = normals_ ? reinterpret_cast<const float*>(normals_->points.data()) : nullptr;
-        // Non-dense clouds (Kinect / organized PCDs carry NaN points): the reference's kd-tree ignores them and runForest
-        // skips them (hpp:277).  Here the finite points are compacted, detected, and the results mapped back; a skipped
-        // point has a NaN response and is never a keypoint.
-        std::vector<int32_t> finite;
-        for (int64_t i = 0; i < n; ++i)
-            if (pcl::isFinite(input_->points[(size_t)i])) finite.push_back((int32_t)i);
-        int rc;
-        if ((int64_t)finite.size() == n) {
-            rc = kpl_detect(ctx_, reinterpret_cast<const float*>(input_->points.data()), (int32_t)sizeof(PointInT), nrm, (int32_t)sizeof(NormalT),
+        int rc = kpl_detect(ctx_, reinterpret_cast<const float*>(input_->points.data()), (int32_t)sizeof(PointInT), nrm, (int32_t)sizeof(NormalT),
                             nullptr, n, response_.data(), idx.data(), &nkp);
-        } else {
+        if (rc == KPL_E_NONFINITE) {
+            // Non-dense clouds (Kinect / organized PCDs carry NaN points; found by the device's bounding-box pass): the
+            // reference's kd-tree ignores them and runForest skips them (hpp:277).  The finite points are compacted,
+            // detected, and the results mapped back; a skipped point has a NaN response and is never a keypoint.
+            std::vector<int32_t> finite;
+            for (int64_t i = 0; i < n; ++i)
+                if (pcl::isFinite(input_->points[(size_t)i])) finite.push_back((int32_t)i);
             const int64_t m = (int64_t)finite.size();
             std::vector<PointInT> pts((size_t)m);
             std::vector<NormalT> nrs(normals_ ? (size_t)m : 0);

@@ -244,11 +244,11 @@ bool NormalEstimation<PointInT, NormalT>::compute(PointCloud<NormalT>& out, std:
     const size_t n = input_->size();
     std::vector<float> buf(n * 4);
     // non-dense clouds: PCL's search ignores NaN points and gives them NaN normals; only the finite points go to the device
-    std::vector<size_t> finite;
-    for (size_t i = 0; i < n; ++i) if (isFinite(input_->points[i])) finite.push_back(i);
-    if (finite.size() == n) {
-        ok = ok && kpl_normals(ctx, reinterpret_cast<const float*>(input_->points.data()), (int32_t)sizeof(PointInT), (int64_t)n, buf.data()) == KPL_OK;
-    } else {
+    int nrc = ok ? kpl_normals(ctx, reinterpret_cast<const float*>(input_->points.data()), (int32_t)sizeof(PointInT), (int64_t)n, buf.data()) : KPL_E_INVALID;
+    if (nrc != KPL_E_NONFINITE) ok = ok && nrc == KPL_OK;
+    else {
+        std::vector<size_t> finite;
+        for (size_t i = 0; i < n; ++i) if (isFinite(input_->points[i])) finite.push_back(i);
         std::vector<PointInT> pts(finite.size());
         std::vector<float> sub(finite.size() * 4);
         for (size_t k = 0; k < finite.size(); ++k) pts[k] = input_->points[finite[k]];
