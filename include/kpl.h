@@ -81,6 +81,9 @@ typedef struct kpl_params {
     int32_t slab_interior_hi; /*    local grid (a slab of a larger cloud): a k-NN normal search that would have   */
     int32_t slab_guard_cells; /*    to look beyond such a face fails with KPL_E_HALO, except for points in the    */
                               /*    outermost slab_guard_cells columns at that face (nothing kept depends on them) */
+    int32_t slab_owned_lo;    /* forced grid only: the local columns [lo, hi) hold every point with a scoring role    */
+    int32_t slab_owned_hi;    /*    (hi > lo; 0,0 = not stated).  Warps of the feature kernel are then never shared      */
+                              /*    between scored and unscored columns, and unscored columns get no warps at all         */
     int32_t report_fragile;   /* 1: flag the points with a near-split forest decision (kpl_stats.n_fragile_points,
                                  kpl_fetch_u8 "fragile"); costs ~2 % of the detection, default 0                   */
 } kpl_params;

@@ -38,7 +38,8 @@ class KplParams(C.Structure):
                 ("viewpoint", C.c_float * 3), ("flip_normals", C.c_int32), ("cells_per_radius", C.c_int32),
                 ("grid_forced", C.c_int32), ("grid_origin", C.c_double * 3), ("grid_dims", C.c_int32 * 3),
                 ("grid_offset", C.c_int32 * 3), ("slab_interior_lo", C.c_int32), ("slab_interior_hi", C.c_int32),
-                ("slab_guard_cells", C.c_int32), ("report_fragile", C.c_int32)]
+                ("slab_guard_cells", C.c_int32), ("slab_owned_lo", C.c_int32), ("slab_owned_hi", C.c_int32),
+                ("report_fragile", C.c_int32)]
 
 
 class KplTimings(C.Structure):

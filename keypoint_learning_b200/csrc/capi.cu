@@ -75,6 +75,7 @@ int kpl_params_default(kpl_params* p)
     p->grid_forced = 0;
     p->slab_interior_lo = p->slab_interior_hi = 0;
     p->slab_guard_cells = 0;
+    p->slab_owned_lo = p->slab_owned_hi = 0;
     p->report_fragile = 0;
     return KPL_OK;
 }
@@ -227,6 +228,7 @@ static void clear_batch(GridDesc& g)
 {
     g.views = nullptr; g.layer_view = nullptr; g.view_offsets = nullptr; g.nviews = 0;
     g.interior_lo = g.interior_hi = 0; g.guard_cells = 0;
+    g.owned_lo = g.owned_hi = 0;
 }
 
 static int finish_grid(kpl_ctx* ctx, int64_t n)
@@ -263,6 +265,7 @@ static int prepare_grid(kpl_ctx* ctx, const float4* d_xyz, const float4* d_nrm, 
         KPL_CUDA(launch_bbox_init(ctx));
         for (int a = 0; a < 3; ++a) { g.org[a] = P.grid_origin[a]; g.dim[a] = P.grid_dims[a]; g.off[a] = P.grid_offset[a]; }
         g.interior_lo = P.slab_interior_lo; g.interior_hi = P.slab_interior_hi; g.guard_cells = P.slab_guard_cells;
+        if (P.slab_owned_hi > P.slab_owned_lo) { g.owned_lo = std::max(P.slab_owned_lo, 0); g.owned_hi = std::min(P.slab_owned_hi, g.dim[0]); }
     } else {
         KPL_CUDA(launch_bbox(ctx, d_xyz, n, ctx->d_bbox));
         uint32_t hb[8];

@@ -590,10 +590,18 @@ cudaError_t launch_features(kpl_ctx* c, int64_t n, bool use_role, bool fuse_fore
     cudaError_t e;
     if (d_qlist && (fuse_forest || !store_rows)) return cudaErrorInvalidValue;
     if (store_rows && (e = ensure(c->feat, (size_t)(d_qlist ? m_list : n) * P.F))) return e;
+    if (store_rows && !d_qlist && c->grid.owned_hi > c->grid.owned_lo &&
+        (e = cudaMemsetAsync(c->feat.p, 0, (size_t)n * P.F * sizeof(float), c->stream))) return e;      // rows of columns without warps
     FusedForest FF = {nullptr, nullptr, 0, nullptr, nullptr, nullptr};
     if (fuse_forest) {
         if ((e = ensure(c->s_score, n)) || (e = ensure(c->score, n)) || (e = ensure(c->fragile, n))) return e;
         FF = {c->forest.d_nodes, c->forest.d_roots, c->forest.ntrees, c->s_score.p, c->score.p, c->fragile.p};
+        if (c->grid.owned_hi > c->grid.owned_lo) {
+            // columns outside the slab's owned range get no warps (grid.cu): their points are unscored = NaN (all-ones is a NaN)
+            if ((e = cudaMemsetAsync(c->s_score.p, 0xFF, (size_t)n * sizeof(float), c->stream)) ||
+                (e = cudaMemsetAsync(c->score.p, 0xFF, (size_t)n * sizeof(float), c->stream))) return e;
+            if (U.report_fragile && (e = cudaMemsetAsync(c->fragile.p, 0, (size_t)n, c->stream))) return e;
+        }
     }
     bool fast = false;
     bool try_fast = true;

@@ -231,8 +231,12 @@ cudaError_t build_grid(kpl_ctx* c, const float4* xyz, const float4* nrm, const u
 // property (a closed surface crosses a cell row in several separate places), so the queries are cut into
 // runs -- maximal stretches of one row spanning at most span + 1 cells -- and every warp gets up to 32
 // consecutive points of one run: work[w] = (first sorted position, count).  One thread walks one row.
+// Slabs of a larger cloud state the columns [own_lo, own_hi) that hold their scored points: a run then never crosses
+// one of the two faces (a warp shared between scored and unscored points would idle the unscored lanes through the
+// whole neighbourhood walk), and with skip_outside the unscored columns get no warps at all.
 template <bool FILL>
 __global__ void __launch_bounds__(128) run_list_kernel(const int32_t* __restrict__ cell_start, int dimx, int64_t nrows, int span,
+                                                       int own_lo, int own_hi, bool skip_outside,
                                                        int32_t* __restrict__ row_warps, const int32_t* __restrict__ row_offset,
                                                        int2* __restrict__ work)
 {
@@ -242,7 +246,9 @@ __global__ void __launch_bounds__(128) run_list_kernel(const int32_t* __restrict
     int warps = 0;
     int out = FILL ? row_offset[row] : 0;
     int run_x = -1, run_s = 0, run_e = 0;
+    const bool faces = own_hi > own_lo;
     auto close_run = [&]() {
+        if (skip_outside && faces && (run_x < own_lo || run_x >= own_hi)) return;
         for (int s = run_s; s < run_e; s += 32) {
             if (FILL) work[out++] = make_int2(s, min(32, run_e - s));
             ++warps;
@@ -252,7 +258,7 @@ __global__ void __launch_bounds__(128) run_list_kernel(const int32_t* __restrict
     for (int x = 0; x < dimx; ++x) {
         const int next = __ldg(cs + x + 1);
         if (next > prev) {                                   // cell x holds points [prev, next)
-            if (run_x < 0 || x - run_x > span) {
+            if (run_x < 0 || x - run_x > span || (faces && ((run_x < own_lo && x >= own_lo) || (run_x < own_hi && x >= own_hi)))) {
                 if (run_x >= 0) close_run();
                 run_x = x; run_s = prev;
             }
@@ -284,7 +290,9 @@ cudaError_t build_work_lists(kpl_ctx* c, int span_n, int span_f)
         *l.total = 0;
         if (l.span < 0) continue;
         if ((e = ensure(*l.rw, (size_t)nrows + 1)) || (e = ensure(*l.ro, (size_t)nrows + 1))) return e;
-        run_list_kernel<false><<<blocks, 128, 0, c->stream>>>(c->cell_start.p, g.dim[0], nrows, l.span, l.rw->p, nullptr, nullptr);
+        // the feature list (k == 1) honours the slab's owned columns; every point needs a normal, so the other list does not
+        const int own_lo = k == 1 ? g.owned_lo : 0, own_hi = k == 1 ? g.owned_hi : 0;
+        run_list_kernel<false><<<blocks, 128, 0, c->stream>>>(c->cell_start.p, g.dim[0], nrows, l.span, own_lo, own_hi, k == 1, l.rw->p, nullptr, nullptr);
         if ((e = cudaMemsetAsync(l.rw->p + nrows, 0, sizeof(int32_t), c->stream))) return e;
         size_t tmp = c->cub_tmp.cap;
         if ((e = cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, tmp, l.rw->p, l.ro->p, (int)nrows + 1, c->stream))) return e;
@@ -297,7 +305,8 @@ cudaError_t build_work_lists(kpl_ctx* c, int span_n, int span_f)
         L& l = lists[k];
         if (l.span < 0 || total[k] == 0) continue;
         if ((e = ensure(*l.work, (size_t)total[k] + 1))) return e;
-        run_list_kernel<true><<<blocks, 128, 0, c->stream>>>(c->cell_start.p, g.dim[0], nrows, l.span, nullptr, l.ro->p, l.work->p);
+        const int own_lo = k == 1 ? g.owned_lo : 0, own_hi = k == 1 ? g.owned_hi : 0;
+        run_list_kernel<true><<<blocks, 128, 0, c->stream>>>(c->cell_start.p, g.dim[0], nrows, l.span, own_lo, own_hi, k == 1, nullptr, l.ro->p, l.work->p);
         *l.total = total[k];
         c->launches++;
     }

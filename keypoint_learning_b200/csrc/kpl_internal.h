@@ -38,6 +38,7 @@ struct GridDesc {
     // search that would have to look beyond such a face cannot be exact (normals.cu)
     int32_t interior_lo, interior_hi;
     int32_t guard_cells;  // points in the outermost guard_cells columns next to an interior face are expected to be clipped
+    int32_t owned_lo, owned_hi;   // local columns holding every point with a scoring role (0,0: not stated)
 };
 
 // One forest node, 8 bytes: thr_or_value + packed(child_block_offset << 10 | var); var == 1023 => leaf.

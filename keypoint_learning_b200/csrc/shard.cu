@@ -211,6 +211,8 @@ int set_forced_grid(kpl_shard* s)
     P.slab_interior_lo = s->rank > 0;
     P.slab_interior_hi = s->rank < s->world - 1;
     P.slab_guard_cells = L.normal_support_cells;
+    P.slab_owned_lo = L.cuts[s->rank] - s->x0;
+    P.slab_owned_hi = L.cuts[s->rank + 1] - s->x0;
     return KPL_OK;
 }
 
