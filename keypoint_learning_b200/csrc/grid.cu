@@ -88,20 +88,21 @@ __global__ void __launch_bounds__(256) bbox_views_kernel(const float4* __restric
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const bool in = i < n;
     int v = -1;
-    uint32_t e[3] = {0u, 0u, 0u};
+    uint32_t lo[3] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu}, hi[3] = {0u, 0u, 0u};      // neutral for lanes beyond n
     bool bad = false;
     if (in) {
         v = view_of_point(view_offsets, nviews, i);
         const float4 p = __ldg(xyz + i);
         bad = !(isfinite(p.x) && isfinite(p.y) && isfinite(p.z));
-        e[0] = enc_float(p.x); e[1] = enc_float(p.y); e[2] = enc_float(p.z);
+        lo[0] = hi[0] = enc_float(p.x); lo[1] = hi[1] = enc_float(p.y); lo[2] = hi[2] = enc_float(p.z);
     }
+    const unsigned inmask = __ballot_sync(0xFFFFFFFFu, in);
+    if (!inmask) return;                                       // the whole warp lies beyond n
     // the lanes of a warp almost always share one view: one set of atomics per warp then
-    const int v0 = __shfl_sync(0xFFFFFFFFu, v, 0);
-    if (__all_sync(0xFFFFFFFFu, v == v0 && !bad)) {
-        uint32_t lo[3], hi[3];
+    const int v0 = __shfl_sync(0xFFFFFFFFu, v, __ffs(inmask) - 1);
+    if (__all_sync(0xFFFFFFFFu, !in || (v == v0 && !bad))) {
 #pragma unroll
-        for (int a = 0; a < 3; ++a) { lo[a] = __reduce_min_sync(0xFFFFFFFFu, e[a]); hi[a] = __reduce_max_sync(0xFFFFFFFFu, e[a]); }
+        for (int a = 0; a < 3; ++a) { lo[a] = __reduce_min_sync(0xFFFFFFFFu, lo[a]); hi[a] = __reduce_max_sync(0xFFFFFFFFu, hi[a]); }
         if ((threadIdx.x & 31) == 0) {
 #pragma unroll
             for (int a = 0; a < 3; ++a) { atomicMin(bbox + 8 * v0 + a, lo[a]); atomicMax(bbox + 8 * v0 + 3 + a, hi[a]); }
@@ -110,7 +111,7 @@ __global__ void __launch_bounds__(256) bbox_views_kernel(const float4* __restric
         if (bad) atomicOr(bbox + 8 * v + 6, 1u);
         else {
 #pragma unroll
-            for (int a = 0; a < 3; ++a) { atomicMin(bbox + 8 * v + a, e[a]); atomicMax(bbox + 8 * v + 3 + a, e[a]); }
+            for (int a = 0; a < 3; ++a) { atomicMin(bbox + 8 * v + a, lo[a]); atomicMax(bbox + 8 * v + 3 + a, hi[a]); }
         }
     }
 }

@@ -37,5 +37,31 @@ cnt, h = d.radiusStats(xyz, 4.0)
 role = np.full(len(xyz), 3, np.uint8); role[::5] = 0; role[1::5] = 1
 d.setInputCloud(xyz); d.setNormals(nrm)
 print("with roles", len(d.compute(role=role)[1]))
+# batch of views in one pass, fragile-split report, nearest-point snap
+views = [xyz, synth.view_25d(80, 48, seed=12)[0], np.ascontiguousarray(xyz[:9] + np.float32(200.0))]
+d.setNormals(None); d.setReportFragile(True)
+sc_b, kp_b = d.computeBatch(views)
+print("batch keypoints", [len(k) for k in kp_b], "fragile", d.stats()["n_fragile_points"])
+d.setReportFragile(False)
+d.nearest(xyz, xyz[:100] + np.float32(0.3))
 d.close()
+# slab sharding: three ranks of an in-process group on this device (pack / halo-score / to-global / record kernels,
+# runs cut at the ownership faces, longest-first work list)
+from keypoint_learning_b200 import shard  # noqa: E402
+big, vp2 = synth.view_25d(400, 96, seed=13)
+dets = []
+for _ in range(3):
+    t = K.KeypointLearningDetector()
+    t.setNAnnulus(5); t.setNBins(10); t.setNonMaxima(True); t.setNonMaxRadius(4.0); t.setNonMaximaDrawsRemove(False)
+    t.setPredictionThreshold(float(np.float32(0.5))); t.setRadiusSearch(20.0); t.setNormalsMode(1, k=10, viewpoint=vp2)
+    assert t.loadForest(forest)
+    dets.append(t)
+plan = shard.plan_slabs(big, 20.0, 4.0, 4, 3)
+jobs = [shard.SlabJob(t, big, plan, r, None) for r, t in enumerate(dets)]
+kp, scores = shard.detect_group_widening(jobs, big, 20.0, 4.0, 4)
+print("sharded keypoints", len(kp))
+for j in jobs:
+    j.close()
+for t in dets:
+    t.close()
 print("sanitize run complete")
