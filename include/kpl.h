@@ -155,6 +155,14 @@ KPL_API int kpl_detect(kpl_ctx* ctx, const float* xyz, int32_t xyz_stride, const
  * normals_out = n x (nx, ny, nz, curvature). Mode / k / viewpoint / flip come from the params. */
 KPL_API int kpl_normals(kpl_ctx* ctx, const float* xyz, int32_t xyz_stride, int64_t n, float* normals_out);
 
+/* The normals KeypointLearningDetector::initCompute estimates itself for an ORGANIZED surface when none were set
+ * (impl/KeypointLearning.hpp:138-145): pcl::IntegralImageNormalEstimation, SIMPLE_3D_GRADIENT, setNormalSmoothingSize
+ * (smoothing_size; the reference passes 5.0).  xyz: height x width points in row-major order, NaN = no measurement.
+ * normals_out = n x (nx, ny, nz, curvature = NaN), NaN where PCL leaves the normal undefined (image border, depth
+ * discontinuities, NaN points).  Viewpoint from the params. */
+KPL_API int kpl_normals_organized(kpl_ctx* ctx, const float* xyz, int32_t xyz_stride, int32_t width, int32_t height,
+                                  float smoothing_size, float* normals_out);
+
 /* pcl::UniformSampling as TestDetector's --subSampling uses it (main_test_detector.cpp:145-157): one point
  * per leaf-sized voxel, the one closest to the voxel centre (ties: lower index).  idx_out (capacity n)
  * receives the ascending original indices of the survivors, *m_out their number. */

@@ -18,7 +18,7 @@ LIB = os.path.join(HERE, "libkpl_b200.so")
 TEST_DETECTOR = os.path.join(HERE, "TestDetector")
 PCD_TOOL = os.path.join(HERE, "pcd_tool")
 
-CU_SOURCES = ["capi.cu", "grid.cu", "normals.cu", "features.cu", "forest.cu", "nms.cu", "shard.cu", "forest_yaml.cpp"]
+CU_SOURCES = ["capi.cu", "grid.cu", "normals.cu", "features.cu", "forest.cu", "nms.cu", "shard.cu", "organized.cu", "forest_yaml.cpp"]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-fmad=false",
     "-Xcompiler", "-fPIC,-fvisibility=hidden,-O2", "--expt-relaxed-constexpr", "-cudart", "static",

@@ -24,7 +24,7 @@ EXPORTS = ["kpl_create", "kpl_destroy", "kpl_last_error", "kpl_version", "kpl_se
            "kpl_set_params", "kpl_get_params", "kpl_load_forest", "kpl_set_forest", "kpl_forest_info", "kpl_detect",
            "kpl_normals", "kpl_features", "kpl_radius_stats", "kpl_radius_neighbors", "kpl_detect_device",
            "kpl_get_timings", "kpl_get_stats", "kpl_fetch", "kpl_set_keep_intermediates", "kpl_uniform_sample", "kpl_nearest",
-           "kpl_fetch_u8", "kpl_device_count", "kpl_detect_batch", "kpl_detect_batch_device",
+           "kpl_fetch_u8", "kpl_device_count", "kpl_normals_organized", "kpl_detect_batch", "kpl_detect_batch_device",
            "kpl_slab_plan_make", "kpl_slab_partition", "kpl_nccl_unique_id", "kpl_shard_create", "kpl_shard_destroy", "kpl_shard_set_plan",
            "kpl_shard_set_slab", "kpl_shard_upload", "kpl_shard_detect", "kpl_shard_detect_group", "kpl_shard_get_info",
            "kpl_shard_device_scores"]
@@ -109,6 +109,7 @@ def load_library():
     L.kpl_uniform_sample.argtypes = [vp, f32p, C.c_int32, C.c_int64, C.c_float, i32p, i64p]
     L.kpl_nearest.argtypes = [vp, f32p, C.c_int32, C.c_int64, f32p, C.c_int32, C.c_int64, i32p, f32p]
     L.kpl_fetch_u8.argtypes = [vp, C.c_char_p, u8p, C.c_int64]
+    L.kpl_normals_organized.argtypes = [vp, f32p, C.c_int32, C.c_int32, C.c_int32, C.c_float, f32p]
     L.kpl_slab_plan_make.argtypes = [f32p, C.c_int32, C.c_int64, C.POINTER(KplParams), C.c_int32, C.c_int32, C.POINTER(KplSlabPlan)]
     L.kpl_slab_partition.argtypes = [C.POINTER(KplSlabPlan), f32p, C.c_int32, C.c_int64, C.c_int32, i32p, i64p]
     L.kpl_nccl_unique_id.argtypes = [vp]
@@ -363,6 +364,31 @@ class KeypointLearningDetector:
             return out
         self._check(rc)
         return out
+
+    def computeNormalsOrganized(self, cloud_hw, smoothing=5.0):
+        """kpl_normals_organized: pcl::IntegralImageNormalEstimation(SIMPLE_3D_GRADIENT, smoothing) on a (height, width, >=3)
+        organized cloud (NaN = no measurement).  Returns (height*width, 4)."""
+        a = np.ascontiguousarray(cloud_hw, np.float32)
+        if a.ndim != 3 or a.shape[2] < 3:
+            raise ValueError("organized cloud must be (height, width, >=3) float32")
+        h, w = a.shape[:2]
+        self._push()
+        out = np.empty((h * w, 4), np.float32)
+        self._check(self._L.kpl_normals_organized(self._h, _ptr(a, C.c_float), a.shape[2] * 4, w, h, float(smoothing), _ptr(out, C.c_float)))
+        return out
+
+    def computeOrganized(self, cloud_hw, smoothing=5.0):
+        """compute() for an organized cloud without normals, as initCompute does it (hpp:138-145): integral-image normals,
+        then the detection over the finite points (NaN points and points without a normal get no score)."""
+        a = np.ascontiguousarray(cloud_hw, np.float32)
+        nrm = self.computeNormalsOrganized(a, smoothing)
+        flat = np.ascontiguousarray(a.reshape(-1, a.shape[2]))
+        saved = (self._cloud, self._normals)
+        try:
+            self._cloud, self._normals = flat, nrm
+            return self.compute()
+        finally:
+            self._cloud, self._normals = saved
 
     def computePointsForTrainingFeatures(self, indices=None):
         xyz, xs = _vec3(self._cloud, "cloud")

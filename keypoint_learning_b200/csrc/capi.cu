@@ -721,6 +721,25 @@ int kpl_normals(kpl_ctx* ctx, const float* xyz, int32_t xyz_stride, int64_t n, f
     return KPL_OK;
 }
 
+// Organized clouds: pcl::IntegralImageNormalEstimation(SIMPLE_3D_GRADIENT, smoothing 5.0) (hpp:138-145), csrc/organized.cu.
+int kpl_normals_organized(kpl_ctx* ctx, const float* xyz, int32_t xyz_stride, int32_t width, int32_t height, float smoothing_size, float* normals_out)
+{
+    if (!ctx || width < 1 || height < 1 || !xyz || !normals_out) return KPL_E_INVALID;
+    begin_call(ctx);
+    if (!(smoothing_size > 0.f) || !std::isfinite(smoothing_size)) return fail(ctx, KPL_E_INVALID, "normal smoothing size must be > 0");
+    const int64_t n = (int64_t)width * height;
+    if (n > 2147483000ll) return fail(ctx, KPL_E_INVALID, "point count out of range");
+    int rc = upload_inputs(ctx, xyz, xyz_stride, nullptr, 0, nullptr, n);
+    if (rc) return rc;
+    KPL_CUDA(ensure(ctx->in_nrm, (size_t)n));
+    KPL_CUDA(launch_normals_integral_image(ctx, ctx->in_xyz.p, width, height, smoothing_size, ctx->in_nrm.p));
+    KPL_CUDA(cudaMemcpyAsync(normals_out, ctx->in_nrm.p, (size_t)n * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    KPL_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->syncs++;
+    ctx->stats.n_points = n; ctx->stats.kernel_launches = ctx->launches; ctx->stats.host_syncs = ctx->syncs;
+    return KPL_OK;
+}
+
 // computePointsForTrainingFeatures (hpp:299-318).  With an index subset (TrainDetector's pattern: a few thousand
 // samples of a large cloud, main_train_detector.cpp:419-439) only the listed queries are evaluated and only m x F
 // floats are ever materialised.

@@ -204,8 +204,26 @@ protected:
             // hpp:125-148: unorganized -> NormalEstimation.setRadiusSearch(search_radius_); organized -> integral images (unsupported)
             std::printf("Computing normals for KPL\n");
             if (input_->isOrganized()) {
-                std::fprintf(stderr, "[pcl::%s::initCompute] organized clouds (IntegralImageNormalEstimation) are not supported by the B200 build\n", name_.c_str());
-                return false;
+                // hpp:138-145: IntegralImageNormalEstimation, SIMPLE_3D_GRADIENT, setNormalSmoothingSize(5.0); like the
+                // reference the result becomes this->normals_ and stays for later calls on the same cloud
+                q.viewpoint[0] = input_->sensor_origin_[0]; q.viewpoint[1] = input_->sensor_origin_[1]; q.viewpoint[2] = input_->sensor_origin_[2];
+                const size_t n = input_->size();
+                std::vector<float> buf(n * 4);
+                if (kpl_set_params(ctx_, &q) != KPL_OK ||
+                    kpl_normals_organized(ctx_, reinterpret_cast<const float*>(input_->points.data()), (int32_t)sizeof(PointInT), (int32_t)input_->width,
+                                          (int32_t)input_->height, 5.0f, buf.data()) != KPL_OK) {
+                    std::fprintf(stderr, "[pcl::%s::initCompute] %s\n", name_.c_str(), kpl_last_error(ctx_));
+                    return false;
+                }
+                PointCloudNPtr normals(new PointCloudN());
+                normals->points.resize(n);
+                for (size_t i = 0; i < n; ++i) {
+                    NormalT& o = normals->points[i];
+                    o.normal_x = buf[4 * i]; o.normal_y = buf[4 * i + 1]; o.normal_z = buf[4 * i + 2]; o.curvature = buf[4 * i + 3];
+                }
+                normals->width = input_->width; normals->height = input_->height; normals->is_dense = false;
+                normals_ = normals;
+                return true;
             }
             q.normals_mode = KPL_NORMALS_RADIUS;
             q.viewpoint[0] = input_->sensor_origin_[0]; q.viewpoint[1] = input_->sensor_origin_[1]; q.viewpoint[2] = input_->sensor_origin_[2];

@@ -2,10 +2,15 @@
 // for converting clouds):   pcd_tool dump in.pcd        -> "n width height dense vx vy vz" + one "x y z" line per point (%.9g)
 //                           pcd_tool ascii|binary in.pcd out.pcd
 //                           pcd_tool subsample leaf in.pcd out.pcd   (pcl::UniformSampling stand-in)
+//                           pcd_tool detect forest in.pcd r_feat r_nms threshold
+//                               the detector WITHOUT setNormals(): initCompute estimates them itself (hpp:125-148: radius-mode
+//                               NormalEstimation for an unorganized cloud, IntegralImageNormalEstimation for an organized one);
+//                               prints "n_keypoints" and one "index score" line per keypoint (%.9g)
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include "pcl_shim.h"
+#include "KeypointLearning.h"
 
 int main(int argc, char** argv)
 {
@@ -30,6 +35,19 @@ int main(int argc, char** argv)
         us.setInputCloud(cloud);
         us.filter(*cloud);
         return pcl::io::savePCDFileASCII(argv[4], *cloud);
+    }
+    if (cmd == "detect" && argc == 7) {
+        if (pcl::io::loadPCDFile(argv[3], *cloud)) return 1;
+        pcl::keypoints::KeypointLearningDetector<pcl::PointXYZ, pcl::PointXYZI> det;
+        det.setNAnnulus(5); det.setNBins(10); det.setNonMaxima(true); det.setNonMaximaDrawsRemove(false);
+        det.setRadiusSearch(std::atof(argv[4])); det.setNonMaxRadius(std::atof(argv[5])); det.setPredictionThreshold((float)std::atof(argv[6]));
+        if (!det.loadForest(argv[2])) return 1;
+        det.setInputCloud(cloud);
+        pcl::PointCloud<pcl::PointXYZI> kp;
+        det.compute(kp);
+        std::printf("%zu\n", kp.size());
+        for (size_t k = 0; k < kp.size(); ++k) std::printf("%d %.9g\n", det.getKeypointsIndices()->indices[k], kp.points[k].intensity);
+        return 0;
     }
     std::fprintf(stderr, "bad arguments\n");
     return 2;

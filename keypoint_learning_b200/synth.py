@@ -125,6 +125,29 @@ def cube_crop(xyz, m):
     return np.ascontiguousarray(xyz[np.sort(sel)])
 
 
+def organized_range_image(width=320, height=240, focal=525.0, seed=7, holes=True, dtype=np.float32):
+    """An ORGANIZED cloud (height, width, 3) as a depth camera delivers it: pinhole projection of a smooth relief with two
+    depth steps, sensor noise, NaN holes (no measurement) -- the input of the reference's organized branch
+    (impl/KeypointLearning.hpp:138-145).  Depth ~0.5-0.8 m in millimetres."""
+    rng = np.random.default_rng(seed)
+    v, u = np.mgrid[0:height, 0:width].astype(np.float64)
+    z = 620.0 + 35.0 * np.sin(u / 23.0 + 0.3) * np.cos(v / 17.0) + 20.0 * np.cos(u / 9.0) + rng.normal(0.0, 0.15, u.shape)
+    z[:, (2 * width) // 3:] += 70.0                               # a vertical depth step
+    z[height // 2:, : width // 4] -= 55.0                         # and a second one
+    for _ in range(6):
+        cx, cy, s = rng.uniform(0, width), rng.uniform(0, height), rng.uniform(8, 25)
+        z += rng.uniform(-25, 25) * np.exp(-((u - cx) ** 2 + (v - cy) ** 2) / (2 * s * s))
+    x = (u - (width - 1) / 2.0) * z / focal
+    y = (v - (height - 1) / 2.0) * z / focal
+    xyz = np.stack([x, y, z], axis=2).astype(dtype)
+    if holes:
+        for _ in range(5):
+            r0, c0 = int(rng.integers(0, max(1, height - 12))), int(rng.integers(0, max(1, width - 20)))
+            xyz[r0:r0 + int(rng.integers(2, 12)), c0:c0 + int(rng.integers(2, 20))] = np.nan
+        xyz[rng.uniform(size=(height, width)) < 0.002] = np.nan      # isolated drop-outs
+    return np.ascontiguousarray(xyz), (0.0, 0.0, 0.0)
+
+
 def small_patch(n_side=64, pitch=0.64, seed=0):
     """Tiny 2.5D patch for unit tests (n_side^2 points)."""
     return view_25d(n_side, n_side, pitch, seed)

@@ -686,6 +686,101 @@ KPLO_API int kplo_features(const float* xyz, const float* normals4, int64_t n, d
 }
 
 /* ------------------------------------------------------------------------------------------ */
+/* F2' (organized clouds): pcl::IntegralImageNormalEstimation with SIMPLE_3D_GRADIENT and          */
+/* setNormalSmoothingSize(5.0), the branch KeypointLearningDetector::initCompute takes for an        */
+/* organized surface (impl/KeypointLearning.hpp:138-145).  [3P-recalled] PCL 1.8.0                   */
+/* features/impl/integral_image_normal.hpp (computeFeature, computeFeatureFull with                  */
+/* BORDER_POLICY_IGNORE and no depth-dependent smoothing, computePointNormal) and                    */
+/* features/impl/integral_image2D.hpp (IntegralImage2D<float,3>: double sums, NaN elements skipped). */
+/* xyz: height x width points (row-major, 3 floats each, NaN = no measurement).                      */
+/* normals4: (nx, ny, nz, curvature = NaN) per pixel, NaN where PCL leaves the normal undefined.     */
+/* The out-of-row reads of PCL's two distance-map passes (previous_row[ci + 1] at the last column,   */
+/* next_row[ci - 1] at the first) are kept: they are reads of the neighbouring row inside the array. */
+/* ------------------------------------------------------------------------------------------ */
+KPLO_API int kplo_normals_integral_image(const float* xyz, int width, int height, float smoothing_size, const float vp[3], float* normals4)
+{
+    if (width < 1 || height < 1) return -1;
+    const int64_t n = (int64_t)width * height;
+    const int W = width, H = height;
+    const float max_depth_change_factor = 20.0f * 0.001f;                 /* constructor default, never changed by the reference */
+    unsigned char* change = (unsigned char*)malloc((size_t)n);
+    float* dist = (float*)malloc((size_t)n * sizeof(float));
+    double* I = (double*)calloc((size_t)(W + 1) * (H + 1) * 3, sizeof(double));
+    if (!change || !dist || !I) { free(change); free(dist); free(I); return -3; }
+    memset(change, 255, (size_t)n);
+    for (int ri = 0; ri < H - 1; ++ri)
+        for (int ci = 0; ci < W - 1; ++ci) {
+            const int64_t index = (int64_t)ri * W + ci;
+            const float depth = xyz[3 * index + 2], depthR = xyz[3 * (index + 1) + 2], depthD = xyz[3 * (index + W) + 2];
+            const float lim = (max_depth_change_factor * (fabsf(depth) + 1.0f) * 2.0f);
+            if (fabsf(depth - depthR) > lim || !isfinite(depth) || !isfinite(depthR)) { change[index] = 0; change[index + 1] = 0; }
+            if (fabsf(depth - depthD) > lim || !isfinite(depth) || !isfinite(depthD)) { change[index] = 0; change[index + W] = 0; }
+        }
+    for (int64_t i = 0; i < n; ++i) dist[i] = change[i] == 0 ? 0.0f : (float)(W + H);
+    for (int ri = 1; ri < H; ++ri) {                                       /* first pass */
+        const float* prev = dist + (int64_t)(ri - 1) * W;
+        float* cur = dist + (int64_t)ri * W;
+        for (int ci = 1; ci < W; ++ci) {
+            const float upLeft = prev[ci - 1] + 1.4f, up = prev[ci] + 1.0f, upRight = prev[ci + 1] + 1.4f, left = cur[ci - 1] + 1.0f;
+            const float a = upLeft < up ? upLeft : up, b = left < upRight ? left : upRight;   /* std::min(std::min(upLeft, up), std::min(left, upRight)) */
+            const float m = a < b ? a : b;
+            if (m < cur[ci]) cur[ci] = m;
+        }
+    }
+    for (int ri = H - 2; ri >= 0; --ri) {                                  /* second pass */
+        const float* next = dist + (int64_t)(ri + 1) * W;
+        float* cur = dist + (int64_t)ri * W;
+        for (int ci = W - 2; ci >= 0; --ci) {
+            const float lowerLeft = next[ci - 1] + 1.4f, lower = next[ci] + 1.0f, lowerRight = next[ci + 1] + 1.4f, right = cur[ci + 1] + 1.0f;
+            const float a = lowerLeft < lower ? lowerLeft : lower, b = right < lowerRight ? right : lowerRight;
+            const float m = a < b ? a : b;
+            if (m < cur[ci]) cur[ci] = m;
+        }
+    }
+    /* IntegralImage2D<float,3>::computeIntegralImages, first order only */
+    const int S = W + 1;
+    for (int r = 0; r < H; ++r)
+        for (int c = 0; c < W; ++c) {
+            const float* e = xyz + 3 * ((int64_t)r * W + c);
+            const int fin = isfinite(e[0] + (e[1] + e[2]));                /* pcl_isfinite(element->sum()) */
+            for (int a = 0; a < 3; ++a) {
+                double v = I[((int64_t)r * S + (c + 1)) * 3 + a] + I[((int64_t)(r + 1) * S + c) * 3 + a] - I[((int64_t)r * S + c) * 3 + a];
+                if (fin) v += (double)e[a];
+                I[((int64_t)(r + 1) * S + (c + 1)) * 3 + a] = v;
+            }
+        }
+    for (int64_t i = 0; i < 4 * n; ++i) normals4[i] = NAN;
+    const int border = (int)smoothing_size;
+    for (int ri = border; ri < H - border; ++ri)
+        for (int ci = border; ci < W - border; ++ci) {
+            const int64_t index = (int64_t)ri * W + ci;
+            if (!isfinite(xyz[3 * index + 2])) continue;
+            const float smoothing = dist[index] < smoothing_size ? dist[index] : smoothing_size;
+            if (!(smoothing > 2.0f)) continue;
+            const int rw = (int)smoothing, rh = (int)smoothing, rw2 = rw / 2, rh2 = rh / 2;
+            double gx[3], gy[3];
+#define KPLO_II_SUM(sx, sy, w, h, a) (I[((int64_t)((sy) + (h)) * S + (sx) + (w)) * 3 + (a)] + I[((int64_t)(sy) * S + (sx)) * 3 + (a)] - \
+                                      I[((int64_t)(sy) * S + (sx) + (w)) * 3 + (a)] - I[((int64_t)((sy) + (h)) * S + (sx)) * 3 + (a)])
+            for (int a = 0; a < 3; ++a) {
+                gx[a] = KPLO_II_SUM(ci + rw2, ri - rh2, 1, rh, a) - KPLO_II_SUM(ci - rw2, ri - rh2, 1, rh, a);
+                gy[a] = KPLO_II_SUM(ci - rw2, ri + rh2, rw, 1, a) - KPLO_II_SUM(ci - rw2, ri - rh2, rw, 1, a);
+            }
+#undef KPLO_II_SUM
+            double nv[3] = { gy[1] * gx[2] - gy[2] * gx[1], gy[2] * gx[0] - gy[0] * gx[2], gy[0] * gx[1] - gy[1] * gx[0] };   /* gradient_y.cross(gradient_x) */
+            const double len = nv[0] * nv[0] + (nv[1] * nv[1] + nv[2] * nv[2]);
+            if (len == 0.0) continue;
+            const double s = sqrt(len);
+            float nx = (float)(nv[0] / s), ny = (float)(nv[1] / s), nz = (float)(nv[2] / s);
+            const float vx = vp[0] - xyz[3 * index], vy = vp[1] - xyz[3 * index + 1], vz = vp[2] - xyz[3 * index + 2];
+            const float cos_theta = (vx * nx + vy * ny + vz * nz);
+            if (cos_theta < 0) { nx *= -1; ny *= -1; nz *= -1; }
+            normals4[4 * index] = nx; normals4[4 * index + 1] = ny; normals4[4 * index + 2] = nz;   /* curvature stays NaN (bad_point) */
+        }
+    free(change); free(dist); free(I);
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------ */
 /* F7: OpenCV DTreesImpl::predictTrees(PREDICT_SUM) on flat arrays + KeypointLearning.hpp:287    */
 /* var[i] < 0 => leaf.  go left iff x[var] <= thr.  sum in double, returned as float.            */
 /* ------------------------------------------------------------------------------------------ */

@@ -283,6 +283,18 @@ def normals_radius(xyz, radius, viewpoint=(0.0, 0.0, 0.0), order=0, cpr=4):
     return out
 
 
+def normals_integral_image(xyz_hw3, smoothing=5.0, viewpoint=(0.0, 0.0, 0.0)):
+    """pcl::IntegralImageNormalEstimation(SIMPLE_3D_GRADIENT, smoothing) on an organized cloud (height, width, 3)."""
+    a = np.ascontiguousarray(xyz_hw3, np.float32)
+    assert a.ndim == 3 and a.shape[2] == 3
+    h, w = a.shape[:2]
+    out = np.empty((h * w, 4), np.float32)
+    vp = np.asarray(viewpoint, np.float32)
+    rc = lib().kplo_normals_integral_image(_p(a, C.c_float), int(w), int(h), C.c_float(smoothing), _p(vp, C.c_float), _p(out, C.c_float))
+    assert rc == 0, rc
+    return out
+
+
 def uniform_sample(xyz, leaf):
     """pcl::UniformSampling (PCL 1.8 filters/uniform_sampling, call site src/main_test_detector.cpp:145-157),
     restated in FP32 numpy: ijk = floor(p * (1/leaf)), centre = (ijk + 0.5) * leaf, keep the point closest to

@@ -815,3 +815,40 @@ def test_forest_guards(kpl, views, tmp_path):
     p.write_text(bad)
     assert not d.loadForest(str(p))
     d.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# organized clouds: initCompute's IntegralImageNormalEstimation branch (impl/KeypointLearning.hpp:138-145)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape", [(320, 240), (97, 61), (640, 13), (7, 300)])
+def test_integral_image_normals_bit_exact(kpl, oracle, shape):
+    from keypoint_learning_b200 import synth
+    w, h = shape
+    xyz, vp = synth.organized_range_image(w, h, seed=w + h)
+    d = kpl.KeypointLearningDetector()
+    d.setNormalsMode(1, k=10, viewpoint=vp)
+    for smoothing in (5.0, 3.0, 10.0):
+        got = d.computeNormalsOrganized(xyz, smoothing)
+        ref = oracle.normals_integral_image(xyz, smoothing, vp)
+        assert same_bits(got, ref), (shape, smoothing)
+    d.close()
+
+
+def test_organized_cloud_detection(kpl, oracle, main_forest):
+    """The whole organized path through the Python facade: integral-image normals, NaN points compacted, detection over the
+    finite points with those normals == the oracle fed with the same normals."""
+    from keypoint_learning_b200 import synth
+    xyz, vp = synth.organized_range_image(320, 240, seed=11)
+    d = make_detector(kpl, th=0.5)
+    d.setNormalsMode(1, k=10, viewpoint=vp)
+    kp, idx = d.computeOrganized(xyz, 5.0)
+    sc = d.getResponse()
+    flat = xyz.reshape(-1, 3)
+    nrm = oracle.normals_integral_image(xyz, 5.0, vp)
+    keep = np.nonzero(np.isfinite(flat).all(axis=1))[0]
+    ref = oracle.detect(np.ascontiguousarray(flat[keep]), main_forest, R_FEAT, R_NMS, 0.5, 5, 10, normals4=nrm[keep], order=1)
+    assert same_bits(sc[keep], ref["scores"])
+    assert np.all(np.isnan(sc[np.setdiff1d(np.arange(len(flat)), keep)]))
+    assert np.array_equal(idx, keep[ref["keypoints"]])
+    assert len(idx) > 0
+    d.close()

@@ -202,3 +202,32 @@ def test_non_dense_clouds_are_compacted(kpl, views, golden):
     assert np.all(np.isnan(nrm[~np.isfinite(dirty).all(axis=1)]))
     assert np.array_equal(nrm[keep].view(np.uint32), g["normals"].view(np.uint32)) if "normals" in g.files else True
     det.close()
+
+
+@pytest.mark.gpu
+def test_facade_estimates_missing_normals_like_initcompute(tools, tmp_path, oracle):
+    """The C++ detector without setNormals() (pcd_tool detect): an ORGANIZED PCD takes the IntegralImageNormalEstimation
+    branch of initCompute (hpp:138-145), an unorganized one the radius-mode NormalEstimation (hpp:130-137)."""
+    from keypoint_learning_b200 import synth
+    forest_file = os.path.join(ROOT, "tests", "golden", "forests", "synthetic-T100-D15.yaml.gz")
+    forest = oracle.load_forest_yaml(forest_file)
+    xyz, vp = synth.organized_range_image(240, 180, seed=5)
+    h, w = xyz.shape[:2]
+    flat = np.ascontiguousarray(xyz.reshape(-1, 3))
+    p = str(tmp_path / "organized.pcd")
+    hdr = ("# .PCD v0.7 - Point Cloud Data file format\nVERSION 0.7\nFIELDS x y z\nSIZE 4 4 4\nTYPE F F F\nCOUNT 1 1 1\nWIDTH %d\nHEIGHT %d\n"
+           "VIEWPOINT 0 0 0 1 0 0 0\nPOINTS %d\nDATA binary\n" % (w, h, w * h))
+    with open(p, "wb") as f:
+        f.write(hdr.encode()); f.write(flat.tobytes())
+    r = subprocess.run([tools.PCD_TOOL, "detect", forest_file, p, "20", "4", "0.5"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    lines = r.stdout.splitlines()
+    assert "Computing normals for KPL" in lines[0]
+    nkp = int(lines[1])
+    got = np.array([[float(v) for v in l.split()] for l in lines[2:2 + nkp]])
+    nrm = oracle.normals_integral_image(xyz, 5.0, vp)
+    keep = np.nonzero(np.isfinite(flat).all(axis=1))[0]
+    ref = oracle.detect(np.ascontiguousarray(flat[keep]), forest, 20.0, 4.0, 0.5, 5, 10, normals4=nrm[keep], order=1)
+    assert nkp == len(ref["keypoints"]) and nkp > 0
+    assert np.array_equal(got[:, 0].astype(np.int64), keep[ref["keypoints"]])
+    assert np.allclose(got[:, 1], ref["scores"][ref["keypoints"]], rtol=1e-7, atol=0)

@@ -441,3 +441,42 @@ def test_detect_one_call_equals_stages(oracle, views, golden, main_forest):
     res = oracle.detect(xyz, main_forest, order=1)
     assert np.array_equal(res["scores"].view(np.uint32), g["scores"].view(np.uint32))
     assert np.array_equal(res["keypoints"], g["keypoints"])
+
+
+def test_integral_image_normals_restatement(oracle):
+    """pcl::IntegralImageNormalEstimation(SIMPLE_3D_GRADIENT, 5.0) as restated by the oracle (hpp:138-145) against a
+    direct float64 evaluation of its definition: gradient_x / gradient_y are differences of column / row sums over the
+    smoothing rectangle, the normal their cross product turned towards the viewpoint; undefined on the image border,
+    next to depth discontinuities and at NaN points."""
+    from keypoint_learning_b200 import synth
+    xyz, vp = synth.organized_range_image(200, 150, seed=3)
+    h, w = xyz.shape[:2]
+    n = oracle.normals_integral_image(xyz, 5.0, vp).reshape(h, w, 4)
+    fin = np.isfinite(n[..., 0])
+    assert 0.5 < fin.mean() < 0.97
+    assert not fin[:5].any() and not fin[-5:].any() and not fin[:, :5].any() and not fin[:, -5:].any()      # BORDER_POLICY_IGNORE
+    assert not fin[~np.isfinite(xyz[..., 2])].any()
+    assert np.all(np.isnan(n[..., 3]))                                                                    # curvature = bad_point
+    assert np.allclose(np.linalg.norm(n[fin][:, :3], axis=1), 1.0, atol=1e-6)
+    assert np.all(np.einsum("ij,ij->i", n[fin][:, :3], -xyz[fin].astype(np.float64)) >= -1e-3)           # towards the viewpoint
+    step = (2 * w) // 3
+    assert not fin[20:-20, step - 2:step + 2].any()                                                      # nothing across the depth step
+    # full 5 x 5 rectangle away from every discontinuity: compare with the definition
+    P = np.nan_to_num(xyz.astype(np.float64))
+    rng = np.random.default_rng(1)
+    checked = 0
+    for _ in range(4000):
+        ri, ci = int(rng.integers(12, h - 12)), int(rng.integers(12, w - 12))
+        if not np.isfinite(xyz[ri - 8:ri + 9, ci - 8:ci + 9]).all() or abs(ci - step) < 9 or (ri > h // 2 - 9 and ci < w // 4 + 9):
+            continue
+        gx = P[ri - 2:ri + 3, ci + 2].sum(0) - P[ri - 2:ri + 3, ci - 2].sum(0)
+        gy = P[ri + 2, ci - 2:ci + 3].sum(0) - P[ri - 2, ci - 2:ci + 3].sum(0)
+        nv = np.cross(gy, gx)
+        nv /= np.linalg.norm(nv)
+        if np.dot(-P[ri, ci], nv) < 0:
+            nv = -nv
+        if not fin[ri, ci]:
+            continue                                  # a noise spike tripped the depth-change test nearby
+        assert np.abs(n[ri, ci, :3] - nv).max() < 2e-6, (ri, ci)
+        checked += 1
+    assert checked > 300
