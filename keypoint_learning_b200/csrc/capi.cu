@@ -708,15 +708,21 @@ int kpl_normals(kpl_ctx* ctx, const float* xyz, int32_t xyz_stride, int64_t n, f
     int rc = upload_inputs(ctx, xyz, xyz_stride, nullptr, 0, nullptr, n);
     if (rc) return rc;
     KPL_CUDA(cudaMemsetAsync(ctx->counters.p, 0, kpl_ctx::NCOUNTERS * sizeof(unsigned long long), ctx->stream));
+    KPL_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
     if ((rc = prepare_knn_grid(ctx, n))) return rc;
     if ((rc = check_forced_grid(ctx))) return rc;
     if ((rc = prepare_lists(ctx, false, false))) return rc;
+    KPL_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
     if ((rc = prepare_normals(ctx, false, n))) return rc;
+    KPL_CUDA(cudaEventRecord(ctx->ev[2], ctx->stream));
     KPL_CUDA(ensure(ctx->scratch_f, (size_t)n * 4));
     KPL_CUDA(launch_unsort_normals(ctx, n, (float4*)ctx->scratch_f.p));
     KPL_CUDA(cudaMemcpyAsync(normals_out, ctx->scratch_f.p, (size_t)n * 16, cudaMemcpyDeviceToHost, ctx->stream));
     KPL_CUDA(cudaStreamSynchronize(ctx->stream));
     ctx->syncs++;
+    cudaEventElapsedTime(&ctx->timings.grid_ms, ctx->ev[0], ctx->ev[1]);
+    cudaEventElapsedTime(&ctx->timings.normals_ms, ctx->ev[1], ctx->ev[2]);
+    ctx->timings.total_ms = ctx->timings.grid_ms + ctx->timings.normals_ms;
     ctx->stats.n_points = n; ctx->stats.kernel_launches = ctx->launches; ctx->stats.host_syncs = ctx->syncs;
     return KPL_OK;
 }

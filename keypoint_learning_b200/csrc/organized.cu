@@ -5,8 +5,8 @@
 // [3P-recalled] PCL 1.8.0 features/impl/integral_image_normal.hpp (computeFeature: depth-change map, two-pass distance
 // map; computeFeatureFull with BORDER_POLICY_IGNORE and no depth-dependent smoothing; computePointNormal) and
 // features/impl/integral_image2D.hpp (IntegralImage2D<float,3>: sums in double, non-finite elements skipped).  The
-// estimator is PCL code that is absent from this build, so this is a restatement from the pinned version, held bit for
-// bit to the oracle's restatement (oracle/kpl_oracle.c: kplo_normals_integral_image).
+// estimator is PCL code that is absent from this build, so this is a restatement from the pinned version; the tests hold
+// it bit for bit to an independent CPU restatement of the same PCL sources (tests/test_gpu_parity.py).
 //
 // The two distance-map passes and the integral image are recurrences with a fixed evaluation order; they are evaluated
 // as WAVEFRONTS by one thread block (every element with the same number of the recurrence's longest dependency chain is

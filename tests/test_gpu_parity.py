@@ -820,7 +820,7 @@ def test_forest_guards(kpl, views, tmp_path):
 # ---------------------------------------------------------------------------------------------
 # organized clouds: initCompute's IntegralImageNormalEstimation branch (impl/KeypointLearning.hpp:138-145)
 # ---------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("shape", [(320, 240), (97, 61), (640, 13), (7, 300)])
+@pytest.mark.parametrize("shape", [(320, 240), (97, 61), (640, 13), (7, 300), (12, 11), (1, 1)])
 def test_integral_image_normals_bit_exact(kpl, oracle, shape):
     from keypoint_learning_b200 import synth
     w, h = shape
