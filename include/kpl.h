@@ -84,6 +84,8 @@ typedef struct kpl_params {
     int32_t slab_owned_lo;    /* forced grid only: the local columns [lo, hi) hold every point with a scoring role    */
     int32_t slab_owned_hi;    /*    (hi > lo; 0,0 = not stated).  Warps of the feature kernel are then never shared      */
                               /*    between scored and unscored columns, and unscored columns get no warps at all         */
+    int32_t eigen32_normalize;/* per-annulus row.normalize() (hpp:360-365): 0 = divide by the norm (Eigen >= 3.3, default),   */
+                              /*    1 = multiply by 1/norm (Eigen 3.2.x DenseBase::operator/=); <= 1 ulp per feature       */
     int32_t report_fragile;   /* 1: flag the points with a near-split forest decision (kpl_stats.n_fragile_points,
                                  kpl_fetch_u8 "fragile"); costs ~2 % of the detection, default 0                   */
 } kpl_params;

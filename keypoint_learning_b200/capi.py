@@ -39,7 +39,7 @@ class KplParams(C.Structure):
                 ("grid_forced", C.c_int32), ("grid_origin", C.c_double * 3), ("grid_dims", C.c_int32 * 3),
                 ("grid_offset", C.c_int32 * 3), ("slab_interior_lo", C.c_int32), ("slab_interior_hi", C.c_int32),
                 ("slab_guard_cells", C.c_int32), ("slab_owned_lo", C.c_int32), ("slab_owned_hi", C.c_int32),
-                ("report_fragile", C.c_int32)]
+                ("eigen32_normalize", C.c_int32), ("report_fragile", C.c_int32)]
 
 
 class KplTimings(C.Structure):
@@ -215,6 +215,10 @@ class KeypointLearningDetector:
         self._p.flip_normals = int(bool(flip))
 
     def setCellsPerRadius(self, cpr): self._p.cells_per_radius = int(cpr)
+
+    def setEigen32Normalize(self, on=True):
+        """row.normalize() as Eigen 3.2.x evaluates it (multiply by 1/norm) instead of the default division (Eigen >= 3.3)."""
+        self._p.eigen32_normalize = int(bool(on))
 
     def setReportFragile(self, on=True):
         """Flag the points whose forest walk decided a split within 1e-5 (stats()["n_fragile_points"], fetchFragile())."""

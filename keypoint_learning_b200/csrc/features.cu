@@ -42,6 +42,7 @@ static constexpr int FEAT_WARPS = 1;
 
 struct FeatParams {
     int n, A, B, F, reach, span;
+    int recip_normalize;   // row.normalize() as Eigen 3.2.x: multiply by 1/norm instead of dividing (kpl_params.eigen32_normalize)
     float r2, support, adim, ahalf, ainv, bdim, bhalf, binv, cellf, rcull2;
     uint64_t one2;   // (1.0f, 1.0f), opaque to the compiler: see dist2_x2
     // packed (v, v) copies of the run constants for the two-votes-per-iteration loop; n* = negated
@@ -490,8 +491,13 @@ feature_kernel(const float4* __restrict__ s_pos, const float4* __restrict__ s_nr
             float ss = 0.0f;
             for (int b = 0; b < P.B; ++b) ss = __fadd_rn(ss, __fmul_rn(h[b * 32], h[b * 32]));
             const float norm = __fsqrt_rn(ss);
-            if (norm > 0.0f)
-                for (int b = 0; b < P.B; ++b) h[b * 32] = __fdiv_rn(h[b * 32], norm);
+            if (norm > 0.0f) {
+                if (P.recip_normalize) {
+                    const float inv = __fdiv_rn(1.0f, norm);
+                    for (int b = 0; b < P.B; ++b) h[b * 32] = __fmul_rn(h[b * 32], inv);
+                } else
+                    for (int b = 0; b < P.B; ++b) h[b * 32] = __fdiv_rn(h[b * 32], norm);
+            }
         }
     }
     __syncwarp();
@@ -572,6 +578,7 @@ cudaError_t launch_features(kpl_ctx* c, int64_t n, bool use_role, bool fuse_fore
     FeatParams P;
     P.n = (int)n; P.A = U.n_annulus; P.B = U.n_bins; P.F = P.A * P.B; P.reach = c->grid.reach_feat;
     P.span = feature_span(U);
+    P.recip_normalize = U.eigen32_normalize != 0;
     const double r = (double)U.radius_features;
     P.r2 = (float)(r * r);                       // static_cast<float>(radius*radius), KdTreeFLANN::radiusSearch
     P.support = (float)r;                        // findAnnulusPair(.., (float)search_radius_, ..) hpp:345

@@ -79,6 +79,7 @@ public:
     // ---- B200 build only
     void setCellsPerRadius(int cpr) { p_.cells_per_radius = cpr; }
     void setReportFragile(bool on) { p_.report_fragile = on; }                 // kpl_stats.n_fragile_points
+    void setEigen32Normalize(bool on) { p_.eigen32_normalize = on; }           // row.normalize() as Eigen 3.2.x (x * 1/norm)
     const kpl_params& params() const { return p_; }
 
     // impl/KeypointLearning.hpp:159-176

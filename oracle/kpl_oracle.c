@@ -607,6 +607,10 @@ KPLO_API void kplo_canon_keys(const float* xyz, int64_t n, const double org[3], 
 /* non-finite are skipped (:338).  Output m x (A*B), index a*B + b (:366-369).                   */
 /* canon_* may be NULL when order != 1 (then derived from the cloud when order == 1).            */
 /* ------------------------------------------------------------------------------------------ */
+/* Eigen's `row.normalize()` (hpp:360-365): Eigen >= 3.3 divides by the norm, Eigen 3.2.x multiplies by 1/norm. */
+static int g_normalize_reciprocal = 0;
+KPLO_API void kplo_set_normalize_mode(int reciprocal) { g_normalize_reciprocal = reciprocal; }
+
 static void feature_row(const float* xyz, const float* normals4, int64_t q, nb_t* nb, int64_t cnt,
                         float support, int A, int B, float* hist /* A*B */, float* out)
 {
@@ -637,7 +641,9 @@ static void feature_row(const float* xyz, const float* normals4, int64_t q, nb_t
         float ss = 0.0f;
         for (int b = 0; b < B; ++b) ss += hist[a * B + b] * hist[a * B + b];
         float norm = sqrtf(ss);
-        for (int b = 0; b < B; ++b) out[a * B + b] = (norm > 0) ? hist[a * B + b] / norm : hist[a * B + b];
+        const float inv = 1.0f / norm;
+        for (int b = 0; b < B; ++b)
+            out[a * B + b] = (norm > 0) ? (g_normalize_reciprocal ? hist[a * B + b] * inv : hist[a * B + b] / norm) : hist[a * B + b];
     }
 }
 

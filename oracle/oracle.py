@@ -350,6 +350,14 @@ def features(xyz, normals4, r_feat, A=5, B=10, order=1, cpr=4, qidx=None, canon=
     return out
 
 
+def set_normalize_mode(reciprocal):
+    """Eigen version of the per-annulus row.normalize(): False = divide (Eigen >= 3.3), True = multiply by 1/norm (3.2.x)."""
+    lib().kplo_set_normalize_mode(int(bool(reciprocal)))
+    r = ref_lib()
+    if r is not None:
+        r.kplref_set_normalize_mode(int(bool(reciprocal)))
+
+
 def forest_sum(forest, feat):
     feat = np.ascontiguousarray(feat, np.float32)
     m, F = feat.shape

@@ -53,12 +53,20 @@ struct Vector3f {
     Vector3f operator-(const Vector3f& o) const { return Vector3f{{v[0] - o.v[0], v[1] - o.v[1], v[2] - o.v[2]}}; }
     float norm() const { return std::sqrt(v[0] * v[0] + (v[1] * v[1] + v[2] * v[2])); }
 };
+// Eigen's `row /= norm` differs between versions: 3.3+ divides every coefficient, 3.2.x (DenseBase::operator/=) multiplies
+// by Scalar(1)/norm.  The reference pins PCL 1.8.0 but no Eigen version; the wrapper selects the variant under test.
+inline int& kplref_normalize_reciprocal() { static int flag = 0; return flag; }
 class MatrixXf {
 public:
     struct Row {
         MatrixXf* m; int r;
         float norm() const { float s = 0.0f; for (int c = 0; c < m->cols_; ++c) s += (*m)(r, c) * (*m)(r, c); return std::sqrt(s); }
-        void normalize() { const float n = norm(); for (int c = 0; c < m->cols_; ++c) (*m)(r, c) /= n; }
+        void normalize()
+        {
+            const float n = norm();
+            if (kplref_normalize_reciprocal()) { const float inv = 1.0f / n; for (int c = 0; c < m->cols_; ++c) (*m)(r, c) *= inv; }
+            else for (int c = 0; c < m->cols_; ++c) (*m)(r, c) /= n;
+        }
     };
     static MatrixXf Zero(int rows, int cols) { MatrixXf z; z.rows_ = rows; z.cols_ = cols; z.d.assign((size_t)rows * cols, 0.0f); return z; }
     float& operator()(int r, int c) { return d[(size_t)c * rows_ + r]; }          // column-major like Eigen

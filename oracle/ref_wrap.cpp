@@ -12,6 +12,8 @@
 typedef pcl::keypoints::KeypointLearningDetector<pcl::PointXYZ, pcl::PointXYZI> Detector;
 #define KPLREF_API extern "C" __attribute__((visibility("default")))
 
+KPLREF_API void kplref_set_normalize_mode(int reciprocal) { Eigen::kplref_normalize_reciprocal() = reciprocal; }
+
 KPLREF_API void kplref_find_annulus_pair(int n_annulus, float distance, float support, int* index, int* pair, float* weight)
 {
     findAnnulusPair(n_annulus, distance, support, *index, *pair, *weight);

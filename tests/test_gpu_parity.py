@@ -852,3 +852,30 @@ def test_organized_cloud_detection(kpl, oracle, main_forest):
     assert np.array_equal(idx, keep[ref["keypoints"]])
     assert len(idx) > 0
     d.close()
+
+
+def test_eigen32_normalize_variant(kpl, views, oracle, main_forest):
+    """kpl_params.eigen32_normalize: the per-annulus normalisation as Eigen 3.2.x evaluates it, bit-identical to the oracle
+    in the same mode; the default (division, Eigen >= 3.3) is untouched."""
+    xyz = views["cheff002"]
+    nrm = oracle.normals_knn(xyz, 10)
+    d = make_detector(kpl)
+    d.keepIntermediates(True)
+    d.setInputCloud(xyz); d.setNormals(nrm)
+    d.setEigen32Normalize(True)
+    _, idx = d.compute()
+    try:
+        oracle.set_normalize_mode(True)
+        ref = oracle.detect(xyz, main_forest, R_FEAT, R_NMS, TH, 5, 10, normals4=nrm, order=1)
+    finally:
+        oracle.set_normalize_mode(False)
+    assert np.array_equal(d.fetch("features", len(xyz), 50).view(np.uint32), ref["features"].view(np.uint32))
+    assert same_bits(d.getResponse(), ref["scores"])
+    assert np.array_equal(idx, ref["keypoints"])
+    sc1 = d.getResponse().copy()
+    d.setEigen32Normalize(False)
+    d.setReportFragile(True)
+    d.compute()
+    differs = sc1 != d.getResponse()
+    assert not np.any(differs & (d.fetchFragile(len(xyz)) == 0))      # only fragile decisions can tell the two Eigen versions apart
+    d.close()

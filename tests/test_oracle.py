@@ -480,3 +480,27 @@ def test_integral_image_normals_restatement(oracle):
         assert np.abs(n[ri, ci, :3] - nv).max() < 2e-6, (ri, ci)
         checked += 1
     assert checked > 300
+
+
+def test_eigen_normalize_variants_against_the_reference_templates(oracle, views):
+    """`row.normalize()` (hpp:360-365) is Eigen code whose arithmetic changed between versions: >= 3.3 divides by the norm,
+    3.2.x multiplies by 1/norm.  The reference pins no Eigen version, so both are restated; the reference's own
+    computePointFeatures (oracle/_ref) run over either stub variant must equal the oracle in that mode, and the two
+    variants differ by at most one ulp per feature."""
+    if oracle.ref_lib() is None:
+        pytest.skip("oracle/_ref was not built (reference tree not mounted)")
+    xyz = np.ascontiguousarray(views["cheff000"][:2500])
+    nrm = oracle.normals_knn(xyz, 10)
+    lf = oracle.ref_neighbour_lists(xyz, 20.0, 1)
+    rows = {}
+    try:
+        for recip in (False, True):
+            oracle.set_normalize_mode(recip)
+            f = oracle.features(xyz, nrm, 20.0, 5, 10, order=1)
+            r = oracle.ref_features(xyz, nrm, 20.0, 5, 10, lf)
+            assert np.array_equal(f.view(np.uint32), r.view(np.uint32)), recip
+            rows[recip] = f
+    finally:
+        oracle.set_normalize_mode(False)
+    ulps = np.abs(rows[False].view(np.int32).astype(np.int64) - rows[True].view(np.int32).astype(np.int64))
+    assert ulps.max() == 1 and 0.01 < (ulps != 0).mean() < 0.5
