@@ -84,6 +84,8 @@ typedef struct kpl_params {
     int32_t slab_owned_lo;    /* forced grid only: the local columns [lo, hi) hold every point with a scoring role    */
     int32_t slab_owned_hi;    /*    (hi > lo; 0,0 = not stated).  Warps of the feature kernel are then never shared      */
                               /*    between scored and unscored columns, and unscored columns get no warps at all         */
+    int32_t uniform_sampling_centre; /* kpl_uniform_sample: 0 = PCL 1.8.0's literal rule (closest to the voxel INDEX vector taken as
+                                        a point), 1 = closest to the voxel centre                                        */
     int32_t eigen32_normalize;/* per-annulus row.normalize() (hpp:360-365): 0 = divide by the norm (Eigen >= 3.3, default),   */
                               /*    1 = multiply by 1/norm (Eigen 3.2.x DenseBase::operator/=); <= 1 ulp per feature       */
     int32_t report_fragile;   /* 1: flag the points with a near-split forest decision (kpl_stats.n_fragile_points,
@@ -166,8 +168,9 @@ KPL_API int kpl_normals_organized(kpl_ctx* ctx, const float* xyz, int32_t xyz_st
                                   float smoothing_size, float* normals_out);
 
 /* pcl::UniformSampling as TestDetector's --subSampling uses it (main_test_detector.cpp:145-157): one point
- * per leaf-sized voxel, the one closest to the voxel centre (ties: lower index).  idx_out (capacity n)
- * receives the ascending original indices of the survivors, *m_out their number. */
+ * per leaf-sized voxel -- PCL 1.8.0 keeps the one closest to the voxel's integer index vector (sic; see
+ * kpl_params.uniform_sampling_centre), ties: lower index.  idx_out (capacity n) receives the ascending original
+ * indices of the survivors, *m_out their number. */
 KPL_API int kpl_uniform_sample(kpl_ctx* ctx, const float* xyz, int32_t xyz_stride, int64_t n, float leaf,
                                int32_t* idx_out, int64_t* m_out);
 

@@ -39,7 +39,7 @@ class KplParams(C.Structure):
                 ("grid_forced", C.c_int32), ("grid_origin", C.c_double * 3), ("grid_dims", C.c_int32 * 3),
                 ("grid_offset", C.c_int32 * 3), ("slab_interior_lo", C.c_int32), ("slab_interior_hi", C.c_int32),
                 ("slab_guard_cells", C.c_int32), ("slab_owned_lo", C.c_int32), ("slab_owned_hi", C.c_int32),
-                ("eigen32_normalize", C.c_int32), ("report_fragile", C.c_int32)]
+                ("uniform_sampling_centre", C.c_int32), ("eigen32_normalize", C.c_int32), ("report_fragile", C.c_int32)]
 
 
 class KplTimings(C.Structure):
@@ -444,9 +444,12 @@ class KeypointLearningDetector:
                                         _ptr(idx, C.c_int32), _ptr(d2, C.c_float)))
         return idx[:q.shape[0]].copy(), d2[:q.shape[0]].copy()
 
-    def uniformSample(self, cloud, leaf):
-        """pcl::UniformSampling(leaf) on the device: ascending indices of the surviving points."""
+    def uniformSample(self, cloud, leaf, centre=False):
+        """pcl::UniformSampling(leaf) on the device: ascending indices of the surviving points.  centre=False is PCL 1.8.0's
+        literal rule (closest to the voxel index vector), True the voxel centre."""
         xyz, xs = _vec3(cloud, "cloud")
+        self._p.uniform_sampling_centre = int(bool(centre))
+        self._push()
         idx = np.empty(max(1, xyz.shape[0]), np.int32)
         m = C.c_int64(0)
         self._check(self._L.kpl_uniform_sample(self._h, _ptr(xyz, C.c_float), xs, xyz.shape[0], float(leaf), _ptr(idx, C.c_int32), C.byref(m)))

@@ -76,6 +76,7 @@ int kpl_params_default(kpl_params* p)
     p->slab_interior_lo = p->slab_interior_hi = 0;
     p->slab_guard_cells = 0;
     p->slab_owned_lo = p->slab_owned_hi = 0;
+    p->uniform_sampling_centre = 0;
     p->eigen32_normalize = 0;
     p->report_fragile = 0;
     return KPL_OK;

@@ -492,11 +492,16 @@ cudaError_t launch_compact(kpl_ctx* c, int64_t n, int32_t* d_kp_idx_out)
 }
 
 // ---- pcl::UniformSampling (src/main_test_detector.cpp:145-157) ----------------------------------
-// One survivor per leaf-sized voxel: the point closest to the voxel centre (PCL 1.8 filters/uniform_sampling:
-// ijk = floor(p * (1/leaf)) in FP32, centre = (ijk + 0.5) * leaf), ties to the lower index; survivors are
-// reported in ascending original index (PCL emits them in unordered_map order, which is platform dependent).
+// One survivor per leaf-sized voxel, ijk = floor(p * (1/leaf)) in FP32.  [3P-recalled] PCL 1.8.0
+// filters/impl/uniform_sampling.hpp keeps the point with the smaller
+//     (p.getVector4fMap() - ijk.cast<float>()).squaredNorm()
+// i.e. it measures the distance to the voxel INDEX vector taken as a point (not to the voxel centre), over the four
+// floats (x, y, z, 1) - (i, j, k, 0), summed as an SSE2 packet reduction (d0 + d2) + (d1 + d3); a later point wins only
+// if strictly closer, so ties go to the lower index.  centre = true selects the voxel centre (ijk + 0.5) * leaf instead
+// (kpl_params.uniform_sampling_centre).  Survivors are reported in ascending original index (PCL emits them in
+// unordered_map order, which is platform dependent).
 // Same machinery as the neighbour grid: voxel keys, a stable radix sort, one scan of each run of equal keys.
-__global__ void __launch_bounds__(256) voxel_key_kernel(const float4* __restrict__ xyz, int64_t n, float inv_leaf, float leaf,
+__global__ void __launch_bounds__(256) voxel_key_kernel(const float4* __restrict__ xyz, int64_t n, float inv_leaf, float leaf, bool centre,
                                                         int mbx, int mby, int mbz, unsigned long long dx, unsigned long long dy,
                                                         unsigned long long* __restrict__ keys, uint32_t* __restrict__ idx, float* __restrict__ dist)
 {
@@ -508,9 +513,14 @@ __global__ void __launch_bounds__(256) voxel_key_kernel(const float4* __restrict
                              iz = (unsigned long long)((long long)fz - mbz);
     keys[i] = (iz * dy + iy) * dx + ix;
     idx[i] = (uint32_t)i;
-    const float cx = __fmul_rn(__fadd_rn(fx, 0.5f), leaf), cy = __fmul_rn(__fadd_rn(fy, 0.5f), leaf), cz = __fmul_rn(__fadd_rn(fz, 0.5f), leaf);
-    const float ex = __fsub_rn(cx, p.x), ey = __fsub_rn(cy, p.y), ez = __fsub_rn(cz, p.z);
-    dist[i] = __fadd_rn(__fmul_rn(ex, ex), __fadd_rn(__fmul_rn(ey, ey), __fmul_rn(ez, ez)));
+    if (centre) {
+        const float cx = __fmul_rn(__fadd_rn(fx, 0.5f), leaf), cy = __fmul_rn(__fadd_rn(fy, 0.5f), leaf), cz = __fmul_rn(__fadd_rn(fz, 0.5f), leaf);
+        const float ex = __fsub_rn(cx, p.x), ey = __fsub_rn(cy, p.y), ez = __fsub_rn(cz, p.z);
+        dist[i] = __fadd_rn(__fmul_rn(ex, ex), __fadd_rn(__fmul_rn(ey, ey), __fmul_rn(ez, ez)));
+    } else {
+        const float ex = __fsub_rn(p.x, fx), ey = __fsub_rn(p.y, fy), ez = __fsub_rn(p.z, fz);      // fourth component: 1 - 0
+        dist[i] = __fadd_rn(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ez, ez)), __fadd_rn(__fmul_rn(ey, ey), 1.0f));
+    }
 }
 
 __global__ void __launch_bounds__(256) voxel_pick_kernel(const unsigned long long* __restrict__ skeys, const uint32_t* __restrict__ sidx,
@@ -560,7 +570,7 @@ cudaError_t uniform_sample(kpl_ctx* c, const float4* xyz, int64_t n, float leaf,
     cub::DeviceSelect::Flagged(nullptr, sel_bytes, it, c->flag.p, d_idx_out, d_cnt, (int)n, c->stream);
     if ((e = ensure(tmp, std::max(sort_bytes, sel_bytes)))) return e;
     const unsigned blocks = (unsigned)((n + 255) / 256);
-    voxel_key_kernel<<<blocks, 256, 0, c->stream>>>(xyz, n, inv_leaf, leaf, (int)mb[0], (int)mb[1], (int)mb[2],
+    voxel_key_kernel<<<blocks, 256, 0, c->stream>>>(xyz, n, inv_leaf, leaf, c->params.uniform_sampling_centre != 0, (int)mb[0], (int)mb[1], (int)mb[2],
                                                     (unsigned long long)db[0], (unsigned long long)db[1], key_a, idx_a, dist);
     size_t bytes = tmp.cap;
     if ((e = cub::DeviceRadixSort::SortPairs(tmp.p, bytes, key_a, key_b, idx_a, idx_b, (int)n, 0, end_bit, c->stream))) return e;

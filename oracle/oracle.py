@@ -295,10 +295,13 @@ def normals_integral_image(xyz_hw3, smoothing=5.0, viewpoint=(0.0, 0.0, 0.0)):
     return out
 
 
-def uniform_sample(xyz, leaf):
-    """pcl::UniformSampling (PCL 1.8 filters/uniform_sampling, call site src/main_test_detector.cpp:145-157),
-    restated in FP32 numpy: ijk = floor(p * (1/leaf)), centre = (ijk + 0.5) * leaf, keep the point closest to
-    the centre (squared distance dx^2 + (dy^2 + dz^2)), ties to the lower index; ascending indices."""
+def uniform_sample(xyz, leaf, centre=False):
+    """pcl::UniformSampling (call site src/main_test_detector.cpp:145-157), restated in FP32 numpy [3P-recalled, PCL 1.8.0
+    filters/impl/uniform_sampling.hpp]: ijk = floor(p * (1/leaf)); per voxel keep the point with the smallest
+    (p.getVector4fMap() - ijk.cast<float>()).squaredNorm() -- the distance to the voxel INDEX vector taken as a point, over
+    (x, y, z, 1) - (i, j, k, 0), SSE2 packet sum (d0 + d2) + (d1 + d3) -- a later point replacing the kept one only when
+    strictly closer (ties: lower index).  centre=True: closest to the voxel centre (ijk + 0.5) * leaf instead.
+    Ascending indices (PCL's own output order is that of an unordered_map)."""
     x = _xyz(xyz)
     leaf = np.float32(leaf)
     inv = np.float32(1.0) / leaf
@@ -307,8 +310,12 @@ def uniform_sample(xyz, leaf):
     db = (np.floor(x.max(axis=0) * inv) - mb + 1).astype(np.int64)
     ijk = (f - mb).astype(np.int64)
     key = (ijk[:, 2] * db[1] + ijk[:, 1]) * db[0] + ijk[:, 0]
-    e = (f + np.float32(0.5)) * leaf - x
-    d = e[:, 0] * e[:, 0] + (e[:, 1] * e[:, 1] + e[:, 2] * e[:, 2])
+    if centre:
+        e = (f + np.float32(0.5)) * leaf - x
+        d = e[:, 0] * e[:, 0] + (e[:, 1] * e[:, 1] + e[:, 2] * e[:, 2])
+    else:
+        e = x - f
+        d = (e[:, 0] * e[:, 0] + e[:, 2] * e[:, 2]) + (e[:, 1] * e[:, 1] + np.float32(1.0))
     order = np.lexsort((np.arange(len(x)), d, key))
     first = np.ones(len(x), bool)
     first[1:] = key[order][1:] != key[order][:-1]

@@ -326,6 +326,10 @@ def test_uniform_sampling_matches_restatement(kpl, views, oracle):
         keep = d.uniformSample(xyz, leaf)
         ref = oracle.uniform_sample(xyz, leaf)
         assert np.array_equal(keep, ref), (view, leaf, len(keep), len(ref))
+        keep_c = d.uniformSample(xyz, leaf, centre=True)                       # the voxel-centre variant
+        assert np.array_equal(keep_c, oracle.uniform_sample(xyz, leaf, centre=True))
+        assert len(keep_c) == len(keep) and (leaf > 100 or not np.array_equal(keep_c, keep))
+        d.uniformSample(xyz, leaf)                                              # back to PCL 1.8.0's rule
         vox = np.floor(xyz[keep] * (np.float32(1.0) / np.float32(leaf)))
         assert len(np.unique(vox, axis=0)) == len(keep)                  # one survivor per voxel
     assert len(d.uniformSample(views["cheff000"], 500.0)) <= 8
