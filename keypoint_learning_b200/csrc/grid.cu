@@ -612,21 +612,4 @@ cudaError_t launch_unsort_normals(kpl_ctx* c, int64_t n, float4* out)
     c->launches++;
     return cudaGetLastError();
 }
-__global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restrict__ rows, const int32_t* __restrict__ indices,
-                                                          int64_t m, int width, float* __restrict__ out)
-{
-    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (t >= m * width) return;
-    int64_t k = t / width;
-    int f = (int)(t - k * width);
-    out[t] = rows[(int64_t)indices[k] * width + f];
-}
-cudaError_t launch_gather_rows(kpl_ctx* c, const float* rows, const int32_t* indices, int64_t m, int width, float* out)
-{
-    int64_t total = m * width;
-    gather_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(rows, indices, m, width, out);
-    c->launches++;
-    return cudaGetLastError();
-}
-
 }  // namespace kpl

@@ -163,7 +163,6 @@ cudaError_t launch_radius_lists(kpl_ctx* c, int64_t n, double radius, const int3
                                 const int64_t* d_offsets, int32_t* d_indices);
 cudaError_t launch_unsort_rows(kpl_ctx* c, const float* d_sorted_rows, int64_t n, int width, float* d_out_orig_order);
 cudaError_t launch_unsort_normals(kpl_ctx* c, int64_t n, float4* d_out_orig_order);
-cudaError_t launch_gather_rows(kpl_ctx* c, const float* d_rows_orig_order, const int32_t* d_indices, int64_t m, int width, float* d_out);
 
 // detection phases (capi.cu), shared with the slab-sharded driver (shard.cu); all return kpl_status
 int detect_check(kpl_ctx* ctx, int64_t n, bool sharded);

@@ -311,6 +311,10 @@ int check_ready(kpl_shard* s)
 {
     if (!s || !s->ctx) return KPL_E_INVALID;
     if (!s->has_slab) return sfail(s, KPL_E_INVALID, "kpl_shard_set_slab was not called");
+    // radius-mode normals (hpp:130-137) need every neighbour within r_feat of a point whose normal matters: the halo must
+    // then be two search reaches wide, which no device check can verify after the fact
+    if (s->world > 1 && s->ctx->params.normals_mode == KPL_NORMALS_RADIUS && s->plan.normal_support_cells < s->plan.reach_feat)
+        return sfail(s, KPL_E_HALO, "radius-mode normals need normal_support_cells >= reach_feat (the whole r_feat ball of every halo point that matters)");
     return detect_check(s->ctx, s->n_loc, true);
 }
 
