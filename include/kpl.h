@@ -155,6 +155,12 @@ KPL_API int kpl_forest_info(const kpl_ctx* ctx, int32_t* ntrees, int32_t* nnodes
 KPL_API int kpl_detect(kpl_ctx* ctx, const float* xyz, int32_t xyz_stride, const float* normals, int32_t normals_stride,
                        const uint8_t* role, int64_t n, float* scores_out, int32_t* kp_idx_out, int64_t* n_kp_out);
 
+/* The same, also filling the keypoint CLOUD detectKeypoints returns (hpp:246-253): kp_xyzi_out (NULL or capacity 4*n floats)
+ * receives x, y, z of each keypoint and its response as the fourth float, in the order of kp_idx_out. */
+KPL_API int kpl_detect_xyzi(kpl_ctx* ctx, const float* xyz, int32_t xyz_stride, const float* normals, int32_t normals_stride,
+                            const uint8_t* role, int64_t n, float* scores_out, int32_t* kp_idx_out, float* kp_xyzi_out,
+                            int64_t* n_kp_out);
+
 /* pcl::NormalEstimation::compute as TestDetector uses it (main_test_detector.cpp:162-169):
  * normals_out = n x (nx, ny, nz, curvature). Mode / k / viewpoint / flip come from the params. */
 KPL_API int kpl_normals(kpl_ctx* ctx, const float* xyz, int32_t xyz_stride, int64_t n, float* normals_out);

@@ -21,7 +21,7 @@ NORMALS_GIVEN, NORMALS_KNN, NORMALS_RADIUS = 0, 1, 2
 ROLE_HALO, ROLE_SCORE, ROLE_OWNED = 0, 1, 3
 
 EXPORTS = ["kpl_create", "kpl_destroy", "kpl_last_error", "kpl_version", "kpl_set_stream", "kpl_params_default",
-           "kpl_set_params", "kpl_get_params", "kpl_load_forest", "kpl_set_forest", "kpl_forest_info", "kpl_detect",
+           "kpl_set_params", "kpl_get_params", "kpl_load_forest", "kpl_set_forest", "kpl_forest_info", "kpl_detect", "kpl_detect_xyzi",
            "kpl_normals", "kpl_features", "kpl_radius_stats", "kpl_radius_neighbors", "kpl_detect_device",
            "kpl_get_timings", "kpl_get_stats", "kpl_fetch", "kpl_set_keep_intermediates", "kpl_uniform_sample", "kpl_nearest",
            "kpl_fetch_u8", "kpl_device_count", "kpl_normals_organized", "kpl_detect_batch", "kpl_detect_batch_device",
@@ -97,6 +97,7 @@ def load_library():
     L.kpl_set_forest.argtypes = [vp, C.c_int32, C.c_int32, i32p, i32p, f32p, i32p, i32p, f32p, C.c_int32]
     L.kpl_forest_info.argtypes = [vp, i32p, i32p, i32p, i32p]
     L.kpl_detect.argtypes = [vp, f32p, C.c_int32, f32p, C.c_int32, u8p, C.c_int64, f32p, i32p, i64p]
+    L.kpl_detect_xyzi.argtypes = [vp, f32p, C.c_int32, f32p, C.c_int32, u8p, C.c_int64, f32p, i32p, f32p, i64p]
     L.kpl_normals.argtypes = [vp, f32p, C.c_int32, C.c_int64, f32p]
     L.kpl_features.argtypes = [vp, f32p, C.c_int32, f32p, C.c_int32, C.c_int64, i32p, C.c_int64, f32p]
     L.kpl_radius_stats.argtypes = [vp, f32p, C.c_int32, C.c_int64, C.c_double, i32p, u64p]
@@ -167,6 +168,7 @@ class KeypointLearningDetector:
         self._normals = None
         self._kp_idx = np.empty(0, np.int32)
         self._scores = None
+        self._xyzi = None
 
     # ---- lifetime
     def close(self):
@@ -277,8 +279,10 @@ class KeypointLearningDetector:
             raise KplError(1, "scores_out / kp_out must be float32[n] / int32[n]")
         nkp = C.c_int64(0)
         r = None if role is None else np.ascontiguousarray(role, np.uint8)
-        rc = self._L.kpl_detect(self._h, _ptr(xyz, C.c_float), xs, _ptr(nrm, C.c_float), ns or 0, _ptr(r, C.c_uint8), n,
-                                _ptr(scores, C.c_float), _ptr(kp, C.c_int32), C.byref(nkp))
+        if self._xyzi is None or self._xyzi.shape[0] < max(n, 1):
+            self._xyzi = np.empty((max(n, 1), 4), np.float32)          # virtual memory only: the library writes n_kp rows
+        rc = self._L.kpl_detect_xyzi(self._h, _ptr(xyz, C.c_float), xs, _ptr(nrm, C.c_float), ns or 0, _ptr(r, C.c_uint8), n,
+                                     _ptr(scores, C.c_float), _ptr(kp, C.c_int32), _ptr(self._xyzi, C.c_float), C.byref(nkp))
         if rc == 4:
             # KPL_E_NONFINITE (found by the device's bounding-box pass, no host scan): a non-dense cloud.  The reference's
             # kd-tree ignores NaN points and runForest skips them (hpp:277): compact the finite points, detect, and map
@@ -287,10 +291,7 @@ class KeypointLearningDetector:
         self._check(rc)
         self._scores = scores
         self._kp_idx = kp[:nkp.value].copy()
-        out = np.empty((nkp.value, 4), np.float32)
-        out[:, :3] = xyz[self._kp_idx, :3]
-        out[:, 3] = scores[self._kp_idx]
-        return out, self._kp_idx
+        return self._xyzi[:nkp.value].copy(), self._kp_idx          # the keypoint cloud was gathered on the device
 
     def computeBatch(self, clouds, normals=None):
         """kpl_detect_batch: `clouds` is a list of (n_v, >=3) float32 views.  Returns (scores list, keypoint index list),

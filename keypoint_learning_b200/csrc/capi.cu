@@ -572,8 +572,8 @@ static int upload_inputs(kpl_ctx* ctx, const float* xyz, int32_t xs, const float
 
 extern "C" {
 
-int kpl_detect(kpl_ctx* ctx, const float* xyz, int32_t xyz_stride, const float* normals, int32_t normals_stride,
-               const uint8_t* role, int64_t n, float* scores_out, int32_t* kp_idx_out, int64_t* n_kp_out)
+int kpl_detect_xyzi(kpl_ctx* ctx, const float* xyz, int32_t xyz_stride, const float* normals, int32_t normals_stride,
+                    const uint8_t* role, int64_t n, float* scores_out, int32_t* kp_idx_out, float* kp_xyzi_out, int64_t* n_kp_out)
 {
     if (!ctx) return KPL_E_INVALID;
     if (n > 0 && !kp_idx_out) return fail(ctx, KPL_E_INVALID, "kp_idx_out is NULL");
@@ -586,10 +586,24 @@ int kpl_detect(kpl_ctx* ctx, const float* xyz, int32_t xyz_stride, const float* 
     if (n > 0) {
         if (scores_out) KPL_CUDA(cudaMemcpyAsync(scores_out, ctx->score.p, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
         if (nkp > 0) KPL_CUDA(cudaMemcpyAsync(kp_idx_out, ctx->kp_idx.p, (size_t)nkp * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        if (nkp > 0 && kp_xyzi_out) {
+            // the keypoint cloud of hpp:246-253 (x, y, z of the input point, intensity = its response), gathered on the
+            // device: a host-side gather of ~1e5 scattered rows out of a 160 MB array costs milliseconds of cache misses
+            KPL_CUDA(ensure(ctx->scratch_f, (size_t)nkp * 4));
+            KPL_CUDA(launch_gather_keypoints(ctx, ctx->in_xyz.p, ctx->kp_idx.p, nkp, (float4*)ctx->scratch_f.p));
+            KPL_CUDA(cudaMemcpyAsync(kp_xyzi_out, ctx->scratch_f.p, (size_t)nkp * 16, cudaMemcpyDeviceToHost, ctx->stream));
+        }
         KPL_CUDA(cudaStreamSynchronize(ctx->stream));
+        ctx->syncs++; ctx->stats.host_syncs = ctx->syncs; ctx->stats.kernel_launches = ctx->launches;
     }
     if (n_kp_out) *n_kp_out = nkp;
     return KPL_OK;
+}
+
+int kpl_detect(kpl_ctx* ctx, const float* xyz, int32_t xyz_stride, const float* normals, int32_t normals_stride,
+               const uint8_t* role, int64_t n, float* scores_out, int32_t* kp_idx_out, int64_t* n_kp_out)
+{
+    return kpl_detect_xyzi(ctx, xyz, xyz_stride, normals, normals_stride, role, n, scores_out, kp_idx_out, nullptr, n_kp_out);
 }
 
 int kpl_detect_device(kpl_ctx* ctx, const void* d_xyz4, const void* d_normals4, const void* d_role, int64_t n,

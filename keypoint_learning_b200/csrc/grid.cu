@@ -476,6 +476,24 @@ cudaError_t launch_view_ranges(kpl_ctx* c, int64_t n, int32_t* d_kp_idx, const i
     return cudaGetLastError();
 }
 
+// ---- the keypoint cloud: (x, y, z, response) of every keypoint (PointXYZI of hpp:246-253) --------------------
+__global__ void __launch_bounds__(256) gather_keypoints_kernel(const float4* __restrict__ xyz, const float* __restrict__ score,
+                                                               const int32_t* __restrict__ kp_idx, int64_t nkp, float4* __restrict__ out)
+{
+    const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (k >= nkp) return;
+    const int32_t i = kp_idx[k];
+    float4 p = __ldg(xyz + i);
+    p.w = score[i];
+    out[k] = p;
+}
+cudaError_t launch_gather_keypoints(kpl_ctx* c, const float4* d_xyz, const int32_t* d_kp_idx, int64_t nkp, float4* d_out)
+{
+    gather_keypoints_kernel<<<(unsigned)((nkp + 255) / 256), 256, 0, c->stream>>>(d_xyz, c->score.p, d_kp_idx, nkp, d_out);
+    c->launches++;
+    return cudaGetLastError();
+}
+
 // ---- keypoint compaction: ascending original index (keypoints_indices_, hpp:252-253) ----------
 cudaError_t launch_compact(kpl_ctx* c, int64_t n, int32_t* d_kp_idx_out)
 {

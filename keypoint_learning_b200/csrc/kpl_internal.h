@@ -137,6 +137,7 @@ cudaError_t launch_check_normals(kpl_ctx* c, int64_t n, bool use_role);
 bool normals_knn_uses_work_list(const kpl_params& P);
 int feature_span(const kpl_params& P);
 cudaError_t launch_bbox_init(kpl_ctx* c);
+cudaError_t launch_gather_keypoints(kpl_ctx* c, const float4* d_xyz, const int32_t* d_kp_idx, int64_t nkp, float4* d_out);
 cudaError_t launch_normals_integral_image(kpl_ctx* c, const float4* d_xyz, int W, int H, float smoothing_size, float4* d_out);
 cudaError_t sort_work_longest_first(kpl_ctx* c, int nwarps, float radius);
 cudaError_t launch_count_occupied_cells(kpl_ctx* c, int64_t n, unsigned long long* d_out);

@@ -102,12 +102,14 @@ public:
         keypoints_indices_.reset(new pcl::PointIndices);
         if (!initCompute()) return;
         const int64_t n = (int64_t)input_->size();
-        response_.assign((size_t)n, 0.f);
-        std::vector<int32_t> idx((size_t)std::max<int64_t>(n, 1));
+        // result buffers are written by the library: sized, not cleared (clearing 10 M-point buffers costs milliseconds)
+        if (response_.size() != (size_t)n) response_.resize((size_t)n);
+        std::unique_ptr<int32_t[]> idx(new int32_t[(size_t)std::max<int64_t>(n, 1)]);
         int64_t nkp = 0;
         const float* nrm = normals_ ? reinterpret_cast<const float*>(normals_->points.data()) : nullptr;
-        int rc = kpl_detect(ctx_, reinterpret_cast<const float*>(input_->points.data()), (int32_t)sizeof(PointInT), nrm, (int32_t)sizeof(NormalT),
-                            nullptr, n, response_.data(), idx.data(), &nkp);
+        std::unique_ptr<float[]> xyzi(new float[(size_t)std::max<int64_t>(n, 1) * 4]);   // keypoint cloud, gathered on the device
+        int rc = kpl_detect_xyzi(ctx_, reinterpret_cast<const float*>(input_->points.data()), (int32_t)sizeof(PointInT), nrm, (int32_t)sizeof(NormalT),
+                                 nullptr, n, response_.data(), idx.get(), xyzi.get(), &nkp);
         if (rc == KPL_E_NONFINITE) {
             // Non-dense clouds (Kinect / organized PCDs carry NaN points; found by the device's bounding-box pass): the
             // reference's kd-tree ignores them and runForest skips them (hpp:277).  The finite points are compacted,
@@ -123,8 +125,9 @@ public:
                 if (normals_) nrs[(size_t)k] = normals_->points[(size_t)finite[(size_t)k]];
             }
             std::vector<float> sc((size_t)std::max<int64_t>(m, 1));
-            rc = kpl_detect(ctx_, reinterpret_cast<const float*>(pts.data()), (int32_t)sizeof(PointInT),
-                            normals_ ? reinterpret_cast<const float*>(nrs.data()) : nullptr, (int32_t)sizeof(NormalT), nullptr, m, sc.data(), idx.data(), &nkp);
+            rc = kpl_detect_xyzi(ctx_, reinterpret_cast<const float*>(pts.data()), (int32_t)sizeof(PointInT),
+                                 normals_ ? reinterpret_cast<const float*>(nrs.data()) : nullptr, (int32_t)sizeof(NormalT), nullptr, m, sc.data(), idx.get(),
+                                 xyzi.get(), &nkp);
             if (rc == KPL_OK) {
                 response_.assign((size_t)n, std::nanf(""));
                 for (int64_t k = 0; k < m; ++k) response_[(size_t)finite[(size_t)k]] = sc[(size_t)k];
@@ -136,11 +139,10 @@ public:
             return;
         }
         output.points.reserve((size_t)nkp);
-        for (int64_t k = 0; k < nkp; ++k) {
-            const PointInT& in = input_->points[(size_t)idx[(size_t)k]];
+        for (int64_t k = 0; k < nkp; ++k) {                                       // hpp:246-253
             PointOutT o;
-            o.x = in.x; o.y = in.y; o.z = in.z;
-            o.intensity = response_[(size_t)idx[(size_t)k]];
+            o.x = xyzi[(size_t)k * 4]; o.y = xyzi[(size_t)k * 4 + 1]; o.z = xyzi[(size_t)k * 4 + 2];
+            o.intensity = xyzi[(size_t)k * 4 + 3];
             output.points.push_back(o);
             keypoints_indices_->indices.push_back(idx[(size_t)k]);
         }
