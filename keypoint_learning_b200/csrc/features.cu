@@ -28,6 +28,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <type_traits>
 #include "kpl_internal.h"
 #include "kpl_math.cuh"
 #include "forest.cuh"
@@ -42,10 +43,12 @@ static constexpr int FEAT_WARPS = 1;
 
 struct FeatParams {
     int n, A, B, F, reach, span;
+    int unbias;            // 1 - bits(2^23): see soft_bin_x2
     int recip_normalize;   // row.normalize() as Eigen 3.2.x: multiply by 1/norm instead of dividing (kpl_params.eigen32_normalize)
-    float r2, support, adim, ahalf, ainv, bdim, bhalf, binv, cellf, rcull2;
+    float r2, support, adim, ahalf, ainv, bdim, bhalf, binv, cellf, rcull2, mhalf;
     uint64_t one2;   // (1.0f, 1.0f), opaque to the compiler: see dist2_x2
-    // packed (v, v) copies of the run constants for the two-votes-per-iteration loop; n* = negated
+    // packed (v, v) copies of the run constants for the two-votes-per-iteration loop; n* = negated.  The bin constants
+    // of that loop are those of the HALF cosine (bdim/2, bhalf/2, 2*binv: exact scalings, see vote_pair)
     uint64_t adim2, nadim2, ainv2, ahalf2, bdim2, nbdim2, binv2, bhalf2;
 };
 
@@ -136,21 +139,56 @@ __device__ __forceinline__ uint64_t fast_sqrt_x2(uint64_t x, float x0, float x1)
     const uint64_t e = fma2(neg2(s), s, x);
     return fma2(e, h, s);
 }
-// soft_bin_k for two values at once (FAST arithmetic only): same expressions, packed where they are FP32
-__device__ __forceinline__ void soft_bin_x2(uint64_t v, uint64_t dim2, uint64_t ndim2, uint64_t inv2, uint64_t half2, uint64_t one2,
-                                            int nm1, int& i0, int& i1, int& p0, int& p1, uint64_t& w, uint64_t& u)
+// floor of two non-negative quotients without conversions: RD(q + 2^23) = 2^23 + floor(q) for 0 <= q < 2^22, so the low
+// mantissa bits of the sum ARE the integer and (sum - 2^23) is its float (FADD2.RM + FADD2 instead of 2 F2I + 2 I2F)
+static constexpr uint32_t FLOOR_MAGIC_BITS = 0x4B000000u;                    // 2^23
+static constexpr uint64_t FLOOR_MAGIC2 = 0x4B0000004B000000ull;
+__device__ __forceinline__ uint64_t add_rm2(uint64_t a, uint64_t b)
 {
-    float q0, q1, w0, w1;
-    unpack2(fast_div_x2(v, ndim2, inv2), q0, q1);
-    i0 = min(__float2int_rd(q0), nm1);
-    i1 = min(__float2int_rd(q1), nm1);
-    const uint64_t center = fma2(mul2(pack2((float)i0, (float)i1), dim2), one2, half2);   // RN(RN(i*dim) + half)
-    const uint64_t ww = fast_div_x2(sub2(v, center), ndim2, inv2);
-    unpack2(ww, w0, w1);
-    p0 = min(max(i0 + ((w0 > 0.0f) ? 1 : -1), 0), nm1);
-    p1 = min(max(i1 + ((w1 > 0.0f) ? 1 : -1), 0), nm1);
-    w = abs2(ww);
-    u = sub2(0x3F8000003F800000ull, w);
+    uint64_t r;
+    asm("add.rm.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t pack2u(uint32_t lo, uint32_t hi)
+{
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2u(uint64_t v, uint32_t& lo, uint32_t& hi)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v));
+}
+// soft_bin_k for two values at once (FAST arithmetic only): same expressions, packed where they are FP32.
+// Returns i + 1 (j0, j1) and the clamped pair index (p0, p1); ww keeps its SIGN (|ww| is the weight: the callers fold the
+// absolute value into the operand modifiers of the consuming FADDs, products of weights commute with it) and
+// u = 1 - |ww|.  When ww == 0 the pair cell receives an exact +0, so its index is arbitrary (i + 1 here, i - 1 in
+// soft_bin_k).
+__device__ __forceinline__ void soft_bin_x2(uint64_t v, uint64_t dim2, uint64_t ndim2, uint64_t inv2, uint64_t half2, uint64_t one2,
+                                            int nm1, int unbias, int& j0, int& j1, int& p0, int& p1, uint64_t& ww, uint64_t& u)
+{
+    uint32_t t0, t1;
+    unpack2u(add_rm2(fast_div_x2(v, ndim2, inv2), FLOOR_MAGIC2), t0, t1);
+    t0 = min(t0, FLOOR_MAGIC_BITS + (uint32_t)nm1);                                        // if (i == n) i--
+    t1 = min(t1, FLOOR_MAGIC_BITS + (uint32_t)nm1);
+    const uint64_t fi = sub2(pack2u(t0, t1), FLOOR_MAGIC2);                                // (float)i
+    const uint64_t center = fma2(mul2(fi, dim2), one2, half2);                             // RN(RN(i*dim) + half)
+    ww = fast_div_x2(sub2(v, center), ndim2, inv2);
+    uint32_t w0, w1;
+    unpack2u(ww, w0, w1);
+    j0 = (int)t0 + unbias;        // unbias = 1 - FLOOR_MAGIC_BITS, passed at run time: a compile-time constant would be
+    j1 = (int)t1 + unbias;        // re-associated into every cell address (two extra adds per read-modify-write)
+    p0 = __vimin_s32_relu(j0 + 2 * ((int)w0 >> 31), nm1);                                   // clamp(i +- 1, 0, n - 1)
+    p1 = __vimin_s32_relu(j1 + 2 * ((int)w1 >> 31), nm1);
+    u = pack2(__fsub_rn(1.0f, fabsf(__uint_as_float(w0))), __fsub_rn(1.0f, fabsf(__uint_as_float(w1))));
+}
+// clamp(RN(1 - dot), 0, 2) / 2 in one instruction: RN(0.5 - 0.5*dot) is RN(1 - dot) / 2 (scaling by two commutes with
+// rounding; 1 - dot is 0 or >= 2^-24, no underflow) and .sat clamps it to [0, 1]
+__device__ __forceinline__ float half_cosine(float dot, float minus_half)
+{
+    float h;
+    asm("fma.rn.sat.f32 %0, %1, %2, 0f3F000000;" : "=f"(h) : "f"(dot), "f"(minus_half));   // (one immediate per instruction)
+    return h;
 }
 
 // One thread per (binade, mantissa): result[0] counts sqrt mismatches over [2^-40, 2^40), result[1]
@@ -193,15 +231,26 @@ __global__ void __launch_bounds__(256) selftest_kernel(float adim, float ainv, f
         unpack2(fast_div_x2(pack2(v[4], x1), pack2(-adim, -adim), pack2(ainv, ainv)), r0, r1);
         bad_p += (__float_as_uint(r0) != __float_as_uint(fast_div_core(v[4], adim, ainv))) + (__float_as_uint(r1) != __float_as_uint(fast_div_core(x1, adim, ainv)));
         {
+            // the packed soft binning of the HALF cosine (floor by round-down addition, signed weights) against the scalar
+            // soft binning of the cosine itself, and the saturating half cosine against the reference's clamp
             const float c0 = fminf(fabsf(v[5]), 2.0f), c1 = __fsub_rn(x1, 1.0f) * 2.0f;    // cosines in [0, 2]
-            int i0, i1, p0, p1, si, sp; uint64_t w, u; float sw, w0, w1, u0, u1;
-            soft_bin_x2(pack2(c0, c1), pack2(bdim, bdim), pack2(-bdim, -bdim), pack2(binv, binv), pack2(bdim / 2.0f, bdim / 2.0f), one2,
-                        (int)(2.0f / bdim + 0.5f) - 1, i0, i1, p0, p1, w, u);
-            unpack2(w, w0, w1); unpack2(u, u0, u1);
-            soft_bin_k<true>(c0, bdim, bdim / 2.0f, binv, (int)(2.0f / bdim + 0.5f) - 1, si, sp, sw);
-            bad_p += (si != i0) + (sw != 0.0f && sp != p0) + (__float_as_uint(sw) != __float_as_uint(w0)) + (__float_as_uint(__fsub_rn(1.0f, sw)) != __float_as_uint(u0));
-            soft_bin_k<true>(c1, bdim, bdim / 2.0f, binv, (int)(2.0f / bdim + 0.5f) - 1, si, sp, sw);
-            bad_p += (si != i1) + (sw != 0.0f && sp != p1) + (__float_as_uint(sw) != __float_as_uint(w1)) + (__float_as_uint(__fsub_rn(1.0f, sw)) != __float_as_uint(u1));
+            const int Bm1 = (int)(2.0f / bdim + 0.5f) - 1;
+            const float hb = bdim * 0.5f;
+            int j0, j1, p0, p1, si, sp; uint64_t ww, u; float sw, w0, w1, u0, u1;
+            soft_bin_x2(pack2(c0 * 0.5f, c1 * 0.5f), pack2(hb, hb), pack2(-hb, -hb), pack2(binv * 2.0f, binv * 2.0f),
+                        pack2(hb * 0.5f, hb * 0.5f), one2, Bm1, 1 - (int)FLOOR_MAGIC_BITS, j0, j1, p0, p1, ww, u);
+            unpack2(ww, w0, w1); unpack2(u, u0, u1);
+            soft_bin_k<true>(c0, bdim, bdim / 2.0f, binv, Bm1, si, sp, sw);
+            bad_p += (si != j0 - 1) + (sw != 0.0f && sp != p0) + (__float_as_uint(sw) != __float_as_uint(fabsf(w0))) + (__float_as_uint(__fsub_rn(1.0f, sw)) != __float_as_uint(u0));
+            soft_bin_k<true>(c1, bdim, bdim / 2.0f, binv, Bm1, si, sp, sw);
+            bad_p += (si != j1 - 1) + (sw != 0.0f && sp != p1) + (__float_as_uint(sw) != __float_as_uint(fabsf(w1))) + (__float_as_uint(__fsub_rn(1.0f, sw)) != __float_as_uint(u1));
+            // dots in (-4, 4) (beyond [-1, 1] the clamp acts), and the exact ends
+            const float dots[4] = {__fsub_rn(x1, 1.5f) * 8.0f, v[6] * 0.03125f, m == 0 ? 1.0f : -1.0f, __fsub_rn(1.0f, v[7] * 1.52587890625e-05f)};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const float ref = fminf(fmaxf(__fsub_rn(1.0f, dots[t]), 0.0f), 2.0f) * 0.5f;
+                bad_p += (__float_as_uint(half_cosine(dots[t], -0.5f)) != __float_as_uint(ref));
+            }
         }
     }
     bad_s = __reduce_add_sync(0xFFFFFFFFu, bad_s);
@@ -218,37 +267,56 @@ __global__ void __launch_bounds__(256) selftest_kernel(float adim, float ainv, f
 
 // shared-memory accesses of the vote loop by 32-bit shared address (keeps the address arithmetic to one
 // add per cell and the four read-modify-writes in source order)
+template <int OFF = 0>
 __device__ __forceinline__ float lds_f32(unsigned a)
 {
     float v;
-    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+    asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(a), "n"(OFF));
     return v;
 }
+template <int OFF = 0>
 __device__ __forceinline__ void sts_f32(unsigned a, float v)
 {
-    asm volatile("st.shared.f32 [%0], %1;" :: "r"(a), "f"(v));
+    asm volatile("st.shared.f32 [%0+%2], %1;" :: "r"(a), "f"(v), "n"(OFF));
 }
 
-// index of the most significant set bit (FLO); mask != 0
-__device__ __forceinline__ int msb_index(uint32_t mask)
+// bit walking without constants in registers: FLO and BMSK
+__device__ __forceinline__ unsigned top_bit(uint32_t mask)           // index of the most significant set bit; 0xFFFFFFFF for 0
 {
-    int r;
+    unsigned r;
     asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(mask));
     return r;
+}
+__device__ __forceinline__ uint32_t bits_below(unsigned b)           // (1 << b) - 1 for b in [0, 32]
+{
+    uint32_t r;
+    asm("bmsk.clamp.b32 %0, 0, %1;" : "=r"(r) : "r"(b));
+    return r;
+}
+// one float of the candidate tile: OFF = 128 * component (x, y, z, nx, ny, nz rows of the SoA tile)
+template <int OFF>
+__device__ __forceinline__ float lds_tile(unsigned a)
+{
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(a), "n"(OFF));
+    return v;
 }
 
 // The four `+=` of hpp:350-355 for one neighbour, in source order (cells may coincide when a pair index
 // was clamped onto the primary one, so the read-modify-writes must stay sequential).  Loading the four
 // cells together and forwarding coinciding values was measured slower (more issue slots than it saves
 // in shared-memory latency at 28 resident warps: 211 ms vs 204 ms on the 10 M-point scene).
-__device__ __forceinline__ void vote4(unsigned hb, unsigned row_bytes, int a, int ap, int b, int bp, float v00, float v01, float v10, float v11)
+// ja / jb = primary annulus / bin index + 1 (hbm = this lane's column one annulus row BELOW the histogram), ap / bp = pair
+// indices; the votes carry the signs of the soft-binning quotients, |v| is the weight.
+__device__ __forceinline__ void vote4(unsigned hbm, unsigned hb, unsigned row_bytes, int ja, int ap, int jb, int bp, float v00, float v01, float v10, float v11)
 {
-    const unsigned ra = hb + (unsigned)a * row_bytes, rp = hb + (unsigned)ap * row_bytes;
-    const unsigned ob = (unsigned)b << 7, op = (unsigned)bp << 7;
-    sts_f32(ra + ob, __fadd_rn(lds_f32(ra + ob), v00));
-    sts_f32(ra + op, __fadd_rn(lds_f32(ra + op), v01));
-    sts_f32(rp + ob, __fadd_rn(lds_f32(rp + ob), v10));
-    sts_f32(rp + op, __fadd_rn(lds_f32(rp + op), v11));
+    const unsigned ra = hbm + (unsigned)ja * row_bytes, rp = hb + (unsigned)ap * row_bytes;
+    const unsigned c00 = ra + ((unsigned)jb << 7), c01 = ra + ((unsigned)bp << 7);      // c00 / c10 lie one bin too high: OFF = -128
+    const unsigned c10 = rp + ((unsigned)jb << 7), c11 = rp + ((unsigned)bp << 7);
+    sts_f32<-128>(c00, __fadd_rn(lds_f32<-128>(c00), fabsf(v00)));
+    sts_f32<0>(c01, __fadd_rn(lds_f32<0>(c01), fabsf(v01)));
+    sts_f32<-128>(c10, __fadd_rn(lds_f32<-128>(c10), fabsf(v10)));
+    sts_f32<0>(c11, __fadd_rn(lds_f32<0>(c11), fabsf(v11)));
 }
 
 template <bool FAST, bool FRAGILE>
@@ -302,8 +370,9 @@ feature_kernel(const float4* __restrict__ s_pos, const float4* __restrict__ s_nr
     unsigned npairs = 0, ncand = 0;
     const unsigned hb = (unsigned)__cvta_generic_to_shared(hist) + (unsigned)lane * 4u;   // this lane's histogram column
     const unsigned row_bytes = (unsigned)P.B * 128u;
+    const unsigned hbm = hb - row_bytes;                   // vote4 adds (annulus + 1) rows to it
+    const unsigned tile0 = (unsigned)__cvta_generic_to_shared(sx);     // slot 0 of the candidate tile's x row
     const int Am1 = P.A - 1, Bm1 = P.B - 1;
-    const float* sx31 = sx + 31;
     const uint64_t QY = pack2(qp.y, qp.y), QZ = pack2(qp.z, qp.z);
     const uint64_t QNX = pack2(qn.x, qn.x), QNY = pack2(qn.y, qn.y), QNZ = pack2(qn.z, qn.z);
 
@@ -370,8 +439,10 @@ feature_kernel(const float4* __restrict__ s_pos, const float4* __restrict__ s_nr
             // neighbours with a non-finite normal never vote (hpp:338): poison the position
             if (!(isfinite(cn.x) && isfinite(cn.y) && isfinite(cn.z))) cp.x = CUDART_NAN_F;
             __syncwarp();                          // previous tile fully consumed
-            sx[lane] = cp.x; sy[lane] = cp.y; sz[lane] = cp.z;
-            snx[lane] = cn.x; sny[lane] = cn.y; snz[lane] = cn.z;
+            // candidate k of the tile goes to SLOT 31 - k, the number of its mask bit: the vote loop finds a set bit with
+            // FLO and that is the slot's index
+            sx[31 - lane] = cp.x; sy[31 - lane] = cp.y; sz[31 - lane] = cp.z;
+            snx[31 - lane] = cn.x; sny[31 - lane] = cn.y; snz[31 - lane] = cn.z;
             const int cnt = min(32, te - tb);
             const unsigned self = (unsigned)(q - tb);   // slot of the query itself when it lies in this tile
             have = next_tile(tb, te);
@@ -380,24 +451,24 @@ feature_kernel(const float4* __restrict__ s_pos, const float4* __restrict__ s_nr
             __syncwarp();
             ncand += cnt;
 
-            // phase 1: membership mask, candidate k -> bit 31-k (slots >= cnt hold NaN positions and never
+            // phase 1: membership mask, candidate k -> bit 31-k (candidates >= cnt hold NaN positions and never
             // pass).  Four candidates per step: broadcast 128-bit loads of the SoA tile, packed FP32 math.
             uint32_t mask = 0;
 #pragma unroll
-            for (int k0 = 0; k0 < 32; k0 += 8) {
-                if (k0 < cnt) {
+            for (int s0 = 24; s0 >= 0; s0 -= 8) {                 // slots [s0, s0 + 8) = candidates [24 - s0, 32 - s0)
+                if (24 - s0 < cnt) {
 #pragma unroll
                     for (int u = 0; u < 8; u += 4) {
-                        const ulonglong2 X = *reinterpret_cast<const ulonglong2*>(sx + k0 + u);
-                        const ulonglong2 Y = *reinterpret_cast<const ulonglong2*>(sy + k0 + u);
-                        const ulonglong2 Z = *reinterpret_cast<const ulonglong2*>(sz + k0 + u);
+                        const ulonglong2 X = *reinterpret_cast<const ulonglong2*>(sx + s0 + u);
+                        const ulonglong2 Y = *reinterpret_cast<const ulonglong2*>(sy + s0 + u);
+                        const ulonglong2 Z = *reinterpret_cast<const ulonglong2*>(sz + s0 + u);
                         float d0, d1, d2, d3;
                         unpack2(dist2_x2(QX, QY, QZ, X.x, Y.x, Z.x, P.one2), d0, d1);
                         unpack2(dist2_x2(QX, QY, QZ, X.y, Y.y, Z.y, P.one2), d2, d3);
-                        if (d0 < P.r2) mask |= 0x80000000u >> (k0 + u);
-                        if (d1 < P.r2) mask |= 0x80000000u >> (k0 + u + 1);
-                        if (d2 < P.r2) mask |= 0x80000000u >> (k0 + u + 2);
-                        if (d3 < P.r2) mask |= 0x80000000u >> (k0 + u + 3);
+                        if (d0 < P.r2) mask |= 1u << (s0 + u);
+                        if (d1 < P.r2) mask |= 1u << (s0 + u + 1);
+                        if (d2 < P.r2) mask |= 1u << (s0 + u + 2);
+                        if (d3 < P.r2) mask |= 1u << (s0 + u + 3);
                     }
                 }
             }
@@ -412,28 +483,36 @@ feature_kernel(const float4* __restrict__ s_pos, const float4* __restrict__ s_nr
                 // its second set of updates is skipped.  (Software-pipelining the loop -- computing the next
                 // pair while the current eight read-modify-writes drain -- was measured slower: 80 registers,
                 // 211 ms vs 204 ms on the 10 M-point scene; capped at 72 registers 215 ms.)
+                // hi_first: the candidate in the HIGH half of the packed operands is the earlier one (64-bit loads of the
+                // reversed tile); both halves vote then
                 auto vote_pair = [&](const uint64_t X, const uint64_t Y, const uint64_t Z, const uint64_t NX, const uint64_t NY,
-                                     const uint64_t NZ, const bool two, const bool lane_counts) {
+                                     const uint64_t NZ, const bool two, const bool lane_counts, auto hi_first) {
                     const uint64_t D = dist2_x2(QX, QY, QZ, X, Y, Z, P.one2);
-                    // 1 - (n0*m0 + (n1*m1 + n2*m2)), hpp:341-342 with Eigen's reduction order
+                    // 1 - (n0*m0 + (n1*m1 + n2*m2)), hpp:341-342 with Eigen's reduction order, clamped to [0, 2]
+                    // (src/KeypointLearning.cpp:70-73) -- carried as its exact half
                     const uint64_t dot = fma2(mul2(QNX, NX), P.one2, fma2(mul2(QNY, NY), P.one2, mul2(QNZ, NZ)));
-                    float c0, c1, d0, d1;
-                    unpack2(sub2(0x3F8000003F800000ull, dot), c0, c1);
+                    float t0, t1, d0, d1;
+                    unpack2(dot, t0, t1);
                     unpack2(D, d0, d1);
                     uint64_t DIST = fast_sqrt_x2(D, d0, d1);                                           // hpp:345 sqrt(distances[..])
                     if (lane_counts && !(fminf(d0, d1) >= FAST_SQRT_LO)) DIST = pack2(__fsqrt_rn(d0), __fsqrt_rn(d1));   // zero / denormal-range d2: rare
-                    const uint64_t COS = pack2(fminf(fmaxf(c0, 0.0f), 2.0f), fminf(fmaxf(c1, 0.0f), 2.0f));   // src/KeypointLearning.cpp:70-73
+                    const uint64_t HCOS = pack2(half_cosine(t0, P.mhalf), half_cosine(t1, P.mhalf));
                     int a0, a1, ap0, ap1, b0, b1, bp0, bp1;
                     uint64_t WA, UA, WB, UB;
-                    soft_bin_x2(DIST, P.adim2, P.nadim2, P.ainv2, P.ahalf2, P.one2, Am1, a0, a1, ap0, ap1, WA, UA);
-                    soft_bin_x2(COS, P.bdim2, P.nbdim2, P.binv2, P.bhalf2, P.one2, Bm1, b0, b1, bp0, bp1, WB, UB);
+                    soft_bin_x2(DIST, P.adim2, P.nadim2, P.ainv2, P.ahalf2, P.one2, Am1, P.unbias, a0, a1, ap0, ap1, WA, UA);
+                    soft_bin_x2(HCOS, P.bdim2, P.nbdim2, P.binv2, P.bhalf2, P.one2, Bm1, P.unbias, b0, b1, bp0, bp1, WB, UB);
                     float v00a, v00b, v01a, v01b, v10a, v10b, v11a, v11b;
                     unpack2(mul2(UB, UA), v00a, v00b);
                     unpack2(mul2(WB, UA), v01a, v01b);
                     unpack2(mul2(UB, WA), v10a, v10b);
                     unpack2(mul2(WB, WA), v11a, v11b);
-                    vote4(hb, row_bytes, a0, ap0, b0, bp0, v00a, v01a, v10a, v11a);
-                    if (two) vote4(hb, row_bytes, a1, ap1, b1, bp1, v00b, v01b, v10b, v11b);
+                    if constexpr (decltype(hi_first)::value) {
+                        vote4(hbm, hb, row_bytes, a1, ap1, b1, bp1, v00b, v01b, v10b, v11b);
+                        vote4(hbm, hb, row_bytes, a0, ap0, b0, bp0, v00a, v01a, v10a, v11a);
+                    } else {
+                        vote4(hbm, hb, row_bytes, a0, ap0, b0, bp0, v00a, v01a, v10a, v11a);
+                        if (two) vote4(hbm, hb, row_bytes, a1, ap1, b1, bp1, v00b, v01b, v10b, v11b);
+                    }
                 };
                 // Interior tiles -- every query of the warp takes every one of the 32 candidates, about a third of
                 // all vote iterations -- need no bit walking: the warp steps through the tile in order and the
@@ -441,28 +520,30 @@ feature_kernel(const float4* __restrict__ s_pos, const float4* __restrict__ s_nr
                 // (lane >= nvalid) tag along on NaN queries; their histogram columns are never read.
                 if (__all_sync(0xFFFFFFFFu, valid ? (mask == 0xFFFFFFFFu) : true)) {
 #pragma unroll 2
-                    for (int k = 0; k < 32; k += 2)
-                        vote_pair(*reinterpret_cast<const uint64_t*>(sx + k), *reinterpret_cast<const uint64_t*>(sy + k),
-                                  *reinterpret_cast<const uint64_t*>(sz + k), *reinterpret_cast<const uint64_t*>(snx + k),
-                                  *reinterpret_cast<const uint64_t*>(sny + k), *reinterpret_cast<const uint64_t*>(snz + k), true, valid);
+                    for (int sl = 30; sl >= 0; sl -= 2)            // candidates 31 - sl - 1 (high half) and 31 - sl (low half)
+                        vote_pair(*reinterpret_cast<const uint64_t*>(sx + sl), *reinterpret_cast<const uint64_t*>(sy + sl),
+                                  *reinterpret_cast<const uint64_t*>(sz + sl), *reinterpret_cast<const uint64_t*>(snx + sl),
+                                  *reinterpret_cast<const uint64_t*>(sny + sl), *reinterpret_cast<const uint64_t*>(snz + sl), true, valid,
+                                  std::true_type());
                     mask = 0;
                 }
                 while (mask) {
-                    const int m0 = msb_index(mask);                // candidate k sits at bit 31-k: highest bit = smallest k
-                    mask ^= 1u << m0;
+                    const unsigned m0 = top_bit(mask);             // highest bit = smallest candidate index; the bit number is the slot
+                    mask &= bits_below(m0);
                     const bool two = mask != 0;
-                    const int m1 = two ? msb_index(mask) : m0;
-                    mask &= ~(1u << m1);
-                    const float* t0 = sx31 - m0;
-                    const float* t1 = sx31 - m1;
-                    vote_pair(pack2(t0[0], t1[0]), pack2(t0[32], t1[32]), pack2(t0[64], t1[64]),
-                              pack2(t0[96], t1[96]), pack2(t0[128], t1[128]), pack2(t0[160], t1[160]), two, true);
+                    const unsigned m1 = min(top_bit(mask), m0);     // an odd last vote is paired with itself (FLO of 0 is 0xFFFFFFFF)
+                    mask &= bits_below(m1);                          // (already empty when the last vote is odd)
+                    const unsigned t0 = tile0 + 4u * m0, t1 = tile0 + 4u * m1;
+                    vote_pair(pack2(lds_tile<0>(t0), lds_tile<0>(t1)), pack2(lds_tile<128>(t0), lds_tile<128>(t1)),
+                              pack2(lds_tile<256>(t0), lds_tile<256>(t1)), pack2(lds_tile<384>(t0), lds_tile<384>(t1)),
+                              pack2(lds_tile<512>(t0), lds_tile<512>(t1)), pack2(lds_tile<640>(t0), lds_tile<640>(t1)), two, true,
+                              std::false_type());
                 }
             } else {
                 while (mask) {
                     const int msb = 31 - __clz(mask);              // candidate k sits at bit 31-k: highest bit = smallest k
                     mask &= ~(1u << msb);
-                    const float* t = sx + 31 - msb;
+                    const float* t = sx + msb;                       // slot number = bit number
                     const float d2 = dist2(qp.x, qp.y, qp.z, t[0], t[32], t[64]);
                     float cosine = __fsub_rn(1.0f, dot3_eigen(qn.x, qn.y, qn.z, t[96], t[128], t[160]));   // hpp:341-342
                     const float dist = ksqrt<FAST>(d2);                                                    // hpp:345 sqrt(distances[..])
@@ -591,9 +672,12 @@ cudaError_t launch_features(kpl_ctx* c, int64_t n, bool use_role, bool fuse_fore
     P.cellf = (float)c->grid.cell;
     P.rcull2 = (float)(r * r * (1.0 + 1e-5));
     P.one2 = 0x3F8000003F800000ull;
+    P.mhalf = -0.5f;
+    P.unbias = 1 - (int)FLOOR_MAGIC_BITS;
     auto dup = [](float v) { uint32_t b; memcpy(&b, &v, 4); return ((uint64_t)b << 32) | b; };
     P.adim2 = dup(P.adim); P.nadim2 = dup(-P.adim); P.ainv2 = dup(P.ainv); P.ahalf2 = dup(P.ahalf);
-    P.bdim2 = dup(P.bdim); P.nbdim2 = dup(-P.bdim); P.binv2 = dup(P.binv); P.bhalf2 = dup(P.bhalf);
+    // the packed loop bins the HALF cosine: bin width, half width and reciprocal scaled by exact powers of two
+    P.bdim2 = dup(P.bdim * 0.5f); P.nbdim2 = dup(-P.bdim * 0.5f); P.binv2 = dup(P.binv * 2.0f); P.bhalf2 = dup(P.bhalf * 0.5f);
     cudaError_t e;
     if (d_qlist && (fuse_forest || !store_rows)) return cudaErrorInvalidValue;
     if (store_rows && (e = ensure(c->feat, (size_t)(d_qlist ? m_list : n) * P.F))) return e;
