@@ -117,7 +117,8 @@ void kpl_destroy(kpl_ctx* ctx)
     release(ctx->key_a); release(ctx->key_b); release(ctx->idx_a); release(ctx->idx_b); release(ctx->cub_tmp);
     release(ctx->row_warps_n); release(ctx->row_offset_n); release(ctx->fragile); release(ctx->views); release(ctx->layer_view);
     release(ctx->view_offsets); release(ctx->qlist);
-    release(ctx->cell_start); release(ctx->row_warps); release(ctx->row_offset); release(ctx->work); release(ctx->work_n); release(ctx->work_tmp); release(ctx->s_pos); release(ctx->s_nrm); release(ctx->feat);
+    release(ctx->cell_start); release(ctx->work_n); release(ctx->ckey_a); release(ctx->ckey_b); release(ctx->qorder_a); release(ctx->qorder);
+    release(ctx->warp_order); release(ctx->s_pos); release(ctx->s_nrm); release(ctx->feat);
     release(ctx->s_score); release(ctx->score); release(ctx->flag); release(ctx->s_state); release(ctx->kp_idx);
     release(ctx->scratch_f); release(ctx->scratch_i); release(ctx->counters);
     if (ctx->d_bbox) cudaFree(ctx->d_bbox);
@@ -349,8 +350,8 @@ static int prepare_grid_batch(kpl_ctx* ctx, const float4* d_xyz, const float4* d
     return KPL_OK;
 }
 
-// Warp work lists of the normal / feature kernels for the grid in place: ONE host synchronisation for both.
-static int prepare_lists(kpl_ctx* ctx, bool normals_given, bool want_features)
+// Work list of the normal kernel and query order of the feature kernel for the grid in place.
+static int prepare_lists(kpl_ctx* ctx, bool normals_given, bool want_features, bool use_role)
 {
     const kpl_params& P = ctx->params;
     int span_n = -1;
@@ -358,16 +359,16 @@ static int prepare_lists(kpl_ctx* ctx, bool normals_given, bool want_features)
         if (P.normals_mode == KPL_NORMALS_KNN) span_n = normals_knn_uses_work_list(P) ? 1 : -1;
         else if (P.normals_mode == KPL_NORMALS_RADIUS) span_n = P.cells_per_radius;
     }
-    const int span_f = want_features ? feature_span(P) : -1;
-    ctx->nwarps_norm = ctx->nwarps_feat = 0;
-    if (span_n < 0 && span_f < 0) return KPL_OK;
-    KPL_CUDA(build_work_lists(ctx, span_n, span_f));
-    // A launch of few waves (a slab of a multi-GPU job, a single view) ends with a long idle tail unless the expensive
-    // warps start first; a cloud whose sorted arrays exceed the L2 keeps the spatial order of its list instead, so that
-    // concurrently running warps keep sharing candidate rows (there the tail is a percent of the launch anyway).
-    const int64_t slots = 148 * 28;
-    if (span_f >= 0 && ctx->nwarps_feat > slots && ctx->nwarps_feat < 24 * slots && ctx->last_n * 32 < (int64_t)120e6)
-        KPL_CUDA(sort_work_longest_first(ctx, ctx->nwarps_feat, P.radius_features));
+    ctx->nwarps_norm = 0;
+    if (span_n >= 0) KPL_CUDA(build_work_list(ctx, span_n));
+    if (want_features) {
+        // A launch of few waves (a slab of a multi-GPU job, a single view) ends with a long idle tail unless the expensive
+        // warps start first; a cloud whose sorted arrays exceed the L2 keeps the spatial order of its queries instead, so
+        // that concurrently running warps keep sharing candidate rows (there the tail is a percent of the launch anyway).
+        const int64_t slots = 148 * 28, warps = (ctx->last_n + 31) / 32;
+        const bool longest_first = warps > slots && warps < 24 * slots && ctx->last_n * 32 < (int64_t)120e6;
+        KPL_CUDA(build_query_order(ctx, ctx->last_n, use_role, longest_first));
+    }
     return KPL_OK;
 }
 
@@ -418,7 +419,7 @@ int detect_score_phase(kpl_ctx* ctx, bool normals_given, bool use_role, int64_t 
 {
     const kpl_params& P = ctx->params;
     const int F = P.n_annulus * P.n_bins;
-    int rc = prepare_lists(ctx, normals_given, true);
+    int rc = prepare_lists(ctx, normals_given, true, use_role);
     if (rc) return rc;
     KPL_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
     rc = prepare_normals(ctx, normals_given, n);
@@ -727,7 +728,7 @@ int kpl_normals(kpl_ctx* ctx, const float* xyz, int32_t xyz_stride, int64_t n, f
     KPL_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
     if ((rc = prepare_knn_grid(ctx, n))) return rc;
     if ((rc = check_forced_grid(ctx))) return rc;
-    if ((rc = prepare_lists(ctx, false, false))) return rc;
+    if ((rc = prepare_lists(ctx, false, false, false))) return rc;
     KPL_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
     if ((rc = prepare_normals(ctx, false, n))) return rc;
     KPL_CUDA(cudaEventRecord(ctx->ev[2], ctx->stream));
@@ -782,7 +783,7 @@ int kpl_features(kpl_ctx* ctx, const float* xyz, int32_t xyz_stride, const float
     KPL_CUDA(cudaMemsetAsync(ctx->counters.p, 0, kpl_ctx::NCOUNTERS * sizeof(unsigned long long), ctx->stream));
     if ((rc = prepare_grid(ctx, ctx->in_xyz.p, normals ? ctx->in_nrm.p : nullptr, nullptr, n))) return rc;
     if ((rc = check_forced_grid(ctx))) return rc;
-    if ((rc = prepare_lists(ctx, normals != nullptr, indices == nullptr))) return rc;
+    if ((rc = prepare_lists(ctx, normals != nullptr, indices == nullptr, false))) return rc;
     if ((rc = prepare_normals(ctx, normals != nullptr, n))) return rc;
     const float* d_src = nullptr;
     if (indices) {

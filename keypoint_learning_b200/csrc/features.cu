@@ -3,8 +3,8 @@
 // its helpers findAnnulusPair / findBinPair (src/KeypointLearning.cpp:41-92) and the FLANN radius
 // search behind searchForNeighbors (hpp:334).
 //
-// Mapping: one warp (= one block) owns up to 32 consecutive cell-sorted query points of ONE run of the
-// work list (grid.cu: a stretch of one cell row spanning at most span + 1 cells), one lane per query, so
+// Mapping: one warp (= one block) owns 32 consecutive queries of the query order (grid.cu: build_query_order, a
+// Hilbert curve over sub-cells, so the 32 queries are a compact patch of the surface), one lane per query, and
 // the warp's queries share a tight candidate box.  The warp walks the cell rows that can hold neighbours
 // of any of its queries; each row is ONE contiguous range of the sorted arrays, staged 32 candidates at a
 // time into a shared SoA tile with coalesced float4 loads (the next tile's loads are in flight while the
@@ -42,7 +42,7 @@ namespace kpl {
 static constexpr int FEAT_WARPS = 1;
 
 struct FeatParams {
-    int n, A, B, F, reach, span;
+    int n, A, B, F, reach;
     int unbias;            // 1 - bits(2^23): see soft_bin_x2
     int recip_normalize;   // row.normalize() as Eigen 3.2.x: multiply by 1/norm instead of dividing (kpl_params.eigen32_normalize)
     float r2, support, adim, ahalf, ainv, bdim, bhalf, binv, cellf, rcull2, mhalf;
@@ -322,9 +322,9 @@ __device__ __forceinline__ void vote4(unsigned hbm, unsigned hb, unsigned row_by
 template <bool FAST, bool FRAGILE>
 __global__ void __launch_bounds__(FEAT_WARPS * 32)
 feature_kernel(const float4* __restrict__ s_pos, const float4* __restrict__ s_nrm, const uint32_t* __restrict__ skey,
-               const int32_t* __restrict__ cell_start, const uint8_t* __restrict__ s_role, const int2* __restrict__ work, int nwarps,
-               const int32_t* __restrict__ qlist, int nlist,
-               int dimx, int dimy, int dimz, FeatParams P, FusedForest FF, float* __restrict__ feat,
+               const int32_t* __restrict__ cell_start,
+               const int32_t* __restrict__ qlist, const unsigned long long* __restrict__ d_nq, int nlist, const uint32_t* __restrict__ warp_order,
+               int rows_by_list, int dimx, int dimy, int dimz, FeatParams P, FusedForest FF, float* __restrict__ feat,
                unsigned long long* __restrict__ counters)
 {
     extern __shared__ __align__(16) float smem[];
@@ -334,28 +334,18 @@ feature_kernel(const float4* __restrict__ s_pos, const float4* __restrict__ s_nr
     float* sx = hist + P.F * 32;                                  // SoA candidate tile: x, y, z, nx, ny, nz
     float* sy = sx + 32; float* sz = sy + 32; float* snx = sz + 32; float* sny = snx + 32; float* snz = sny + 32;
 
-    const int w = blockIdx.x * (blockDim.x >> 5) + warp;
-    if (w >= nwarps) return;
-    // work list: up to 32 consecutive sorted points of one run.  Query list (computePointsForTrainingFeatures on an
-    // index subset, hpp:299-318): 32 consecutive entries of the ascending list of sorted positions; the group loop
-    // below copes with lanes that lie in different cell rows.  q0 is also the first output row of the warp.
-    const int2 item = qlist ? make_int2(w * 32, min(32, nlist - w * 32)) : __ldg(work + w);
-    const int q0 = item.x, nvalid = item.y;
+    // Warp w takes entries [32 w, 32 w + 32) of the query list (sorted positions): the Hilbert order of every point with
+    // a scoring role (kpl_detect*, kpl_features of a whole cloud: the count is on the device) or the ascending list of an
+    // index subset (computePointsForTrainingFeatures, hpp:299-318: rows_by_list, output row = list entry).
+    int w = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (warp_order) w = (int)__ldg(warp_order + w);
+    const int nq = d_nq ? (int)*d_nq : nlist;
+    const int q0 = w * 32;
+    if (q0 >= nq) return;
+    const int nvalid = min(32, nq - q0);
     const bool valid = lane < nvalid;
-    const int q = qlist ? (valid ? __ldg(qlist + q0 + lane) : 0) : q0 + lane;
+    const int q = valid ? __ldg(qlist + q0 + lane) : 0;
     bool active = valid;
-    if (active && s_role) active = (s_role[q] & 1) != 0;
-    if (!__any_sync(0xFFFFFFFFu, active)) {
-        if (feat)
-            for (int e = lane; e < nvalid * P.F; e += 32) feat[(int64_t)q0 * P.F + e] = 0.0f;
-        if (FF.nodes && valid) {
-            const uint32_t orig = __float_as_uint(__ldg(&s_pos[q].w));
-            FF.s_score[q] = CUDART_NAN_F;
-            FF.score[orig] = CUDART_NAN_F;
-            if (FRAGILE) FF.fragile[orig] = 0;
-        }
-        return;
-    }
     float4 qp = make_float4(CUDART_NAN_F, 0.f, 0.f, 0.f), qn = make_float4(0.f, 0.f, 0.f, 0.f);
     int cx = 0, cy = 0, cz = 0;
     if (active) {
@@ -376,23 +366,25 @@ feature_kernel(const float4* __restrict__ s_pos, const float4* __restrict__ s_nr
     const uint64_t QY = pack2(qp.y, qp.y), QZ = pack2(qp.z, qp.z);
     const uint64_t QNX = pack2(qn.x, qn.x), QNY = pack2(qn.y, qn.y), QNZ = pack2(qn.z, qn.z);
 
-    // The 32 queries are consecutive in (z, y, x) cell order but may straddle the end of a cell row
-    // (or sit in far-apart cells of a sparse row).  They are processed in groups of lanes that share
-    // one cell row and span at most P.span + 1 cells in x, so the candidate region of a pass is always
-    // a tight box around the group; lanes outside the group idle for that pass (their px is NaN).
+    // The 32 queries are neighbours on the curve, almost always within a cell or two of each other.  They are processed
+    // in groups of lanes that lie within one cell of the first remaining lane in every axis, so the candidate region of a
+    // pass is a tight box around the group (at most 3 cells wider than the search reach); the rare lanes outside the group
+    // (a jump of the curve, the end of a surface, another view of a batch) idle for that pass (their px is NaN).
     unsigned remaining = __ballot_sync(0xFFFFFFFFu, active);
     while (remaining) {
         const int leader = __ffs(remaining) - 1;
-        const int minx = __shfl_sync(0xFFFFFFFFu, cx, leader);
-        const int gy0 = __shfl_sync(0xFFFFFFFFu, cy, leader), gz0 = __shfl_sync(0xFFFFFFFFu, cz, leader);
-        const bool member = active && ((remaining >> lane) & 1u) && cy == gy0 && cz == gz0 && (unsigned)(cx - minx) <= (unsigned)P.span;
+        const int lx = __shfl_sync(0xFFFFFFFFu, cx, leader), ly = __shfl_sync(0xFFFFFFFFu, cy, leader), lz = __shfl_sync(0xFFFFFFFFu, cz, leader);
+        const bool member = active && ((remaining >> lane) & 1u) && (unsigned)(cx - lx + 1) <= 2u && (unsigned)(cy - ly + 1) <= 2u &&
+                            (unsigned)(cz - lz + 1) <= 2u;
         remaining &= ~__ballot_sync(0xFFFFFFFFu, member);
-        const int maxx = __reduce_max_sync(0xFFFFFFFFu, member ? cx : minx);
+        const int minx = __reduce_min_sync(0xFFFFFFFFu, member ? cx : lx), maxx = __reduce_max_sync(0xFFFFFFFFu, member ? cx : lx);
+        const int gy0 = __reduce_min_sync(0xFFFFFFFFu, member ? cy : ly), gy1 = __reduce_max_sync(0xFFFFFFFFu, member ? cy : ly);
+        const int gz0 = __reduce_min_sync(0xFFFFFFFFu, member ? cz : lz), gz1 = __reduce_max_sync(0xFFFFFFFFu, member ? cz : lz);
         const float px = member ? qp.x : CUDART_NAN_F;
         const uint64_t QX = pack2(px, px);
 
-        const int y0 = max(gy0 - P.reach, 0), y1 = min(gy0 + P.reach, dimy - 1);
-        const int z0 = max(gz0 - P.reach, 0), z1 = min(gz0 + P.reach, dimz - 1);
+        const int y0 = max(gy0 - P.reach, 0), y1 = min(gy1 + P.reach, dimy - 1);
+        const int z0 = max(gz0 - P.reach, 0), z1 = min(gz1 + P.reach, dimz - 1);
         const int ny = y1 - y0 + 1, nrows = ny * (z1 - z0 + 1);
 
         // ---- warp-uniform iterator over the candidate tiles: rows in ascending (z, y), 32 points per tile
@@ -406,7 +398,8 @@ feature_kernel(const float4* __restrict__ s_pos, const float4* __restrict__ s_nr
                     const int r = rb + lane;
                     if (r < nrows) {
                         const int zz = z0 + r / ny, yy = y0 + r % ny;
-                        const int gy = max(abs(yy - gy0) - 1, 0), gz = max(abs(zz - gz0) - 1, 0);
+                        // whole empty cells between the row and the group's cells: a lower bound of the distance
+                        const int gy = max(max(gy0 - yy, yy - gy1) - 1, 0), gz = max(max(gz0 - zz, zz - gz1) - 1, 0);
                         const float gap2 = (float)(gy * gy + gz * gz) * P.cellf * P.cellf;
                         if (gap2 < P.rcull2) {
                             int rx = (int)(sqrtf(P.rcull2 - gap2) / P.cellf) + 1;
@@ -595,13 +588,16 @@ feature_kernel(const float4* __restrict__ s_pos, const float4* __restrict__ s_nr
         }
         if (FRAGILE) nfragile = __popc(__ballot_sync(0xFFFFFFFFu, active && fragile));
     }
-    // coalesced store of the warp's 32 rows (row-major, sorted order)
+    // store of the warp's rows: row of the list entry (index subsets) or of the query's sorted position
     if (feat) {
+        int* sq = reinterpret_cast<int*>(sx);            // the candidate tile is free now
+        __syncwarp();
+        sq[lane] = rows_by_list ? q0 + lane : q;
+        __syncwarp();
         const int total = nvalid * P.F;
-        float* dst = feat + (int64_t)q0 * P.F;
         for (int e = lane; e < total; e += 32) {
             const int row = e / P.F, f = e - row * P.F;
-            dst[e] = hist[f * 32 + row];
+            feat[(int64_t)sq[row] * P.F + f] = hist[f * 32 + row];
         }
     }
     npairs = __reduce_add_sync(0xFFFFFFFFu, npairs);
@@ -644,21 +640,11 @@ static cudaError_t fast_math_verdict(kpl_ctx* c, const FeatParams& P, bool& fast
     return cudaGetLastError();
 }
 
-// cells a warp's run may span in x beyond its first: 1/2/3/4 measured 197/192/190/189 ms (10 M points, 4 cells per radius)
-int feature_span(const kpl_params& U)
-{
-#ifdef KPL_EXPERIMENTS
-    if (const char* e = getenv("KPL_FEAT_SPAN")) return atoi(e);
-#endif
-    return U.cells_per_radius;
-}
-
 cudaError_t launch_features(kpl_ctx* c, int64_t n, bool use_role, bool fuse_forest, bool store_rows, const int32_t* d_qlist, int64_t m_list)
 {
     const kpl_params& U = c->params;
     FeatParams P;
     P.n = (int)n; P.A = U.n_annulus; P.B = U.n_bins; P.F = P.A * P.B; P.reach = c->grid.reach_feat;
-    P.span = feature_span(U);
     P.recip_normalize = U.eigen32_normalize != 0;
     const double r = (double)U.radius_features;
     P.r2 = (float)(r * r);                       // static_cast<float>(radius*radius), KdTreeFLANN::radiusSearch
@@ -681,14 +667,14 @@ cudaError_t launch_features(kpl_ctx* c, int64_t n, bool use_role, bool fuse_fore
     cudaError_t e;
     if (d_qlist && (fuse_forest || !store_rows)) return cudaErrorInvalidValue;
     if (store_rows && (e = ensure(c->feat, (size_t)(d_qlist ? m_list : n) * P.F))) return e;
-    if (store_rows && !d_qlist && c->grid.owned_hi > c->grid.owned_lo &&
-        (e = cudaMemsetAsync(c->feat.p, 0, (size_t)n * P.F * sizeof(float), c->stream))) return e;      // rows of columns without warps
+    if (store_rows && !d_qlist && use_role &&
+        (e = cudaMemsetAsync(c->feat.p, 0, (size_t)n * P.F * sizeof(float), c->stream))) return e;      // rows of points that are no queries
     FusedForest FF = {nullptr, nullptr, 0, nullptr, nullptr, nullptr};
     if (fuse_forest) {
         if ((e = ensure(c->s_score, n)) || (e = ensure(c->score, n)) || (e = ensure(c->fragile, n))) return e;
         FF = {c->forest.d_nodes, c->forest.d_roots, c->forest.ntrees, c->s_score.p, c->score.p, c->fragile.p};
-        if (c->grid.owned_hi > c->grid.owned_lo) {
-            // columns outside the slab's owned range get no warps (grid.cu): their points are unscored = NaN (all-ones is a NaN)
+        if (use_role) {
+            // points without a scoring role are not in the query order (grid.cu): unscored = NaN (all-ones is a NaN)
             if ((e = cudaMemsetAsync(c->s_score.p, 0xFF, (size_t)n * sizeof(float), c->stream)) ||
                 (e = cudaMemsetAsync(c->score.p, 0xFF, (size_t)n * sizeof(float), c->stream))) return e;
             if (U.report_fragile && (e = cudaMemsetAsync(c->fragile.p, 0, (size_t)n, c->stream))) return e;
@@ -710,15 +696,16 @@ cudaError_t launch_features(kpl_ctx* c, int64_t n, bool use_role, bool fuse_fore
                      : (frag ? feature_kernel<false, true> : feature_kernel<false, false>);
     // per device and per process state of the runtime: set it on every launch that needs it (a host-side call)
     if (smem > 48 * 1024 && (e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return e;
-    // the work list was built by the caller (build_work_lists: one host synchronisation for all lists of the call)
-    const int warps = d_qlist ? (int)((m_list + 31) / 32) : c->nwarps_feat;
+    // the query order was built by the caller (build_query_order); an index subset brings its own list
+    const int64_t nq_max = d_qlist ? m_list : n;
+    const int warps = (int)((nq_max + 31) / 32);
     if (warps == 0) return cudaSuccess;
     int blocks = (warps + wpb - 1) / wpb;
     kern<<<blocks, wpb * 32, smem, c->stream>>>(c->s_pos.p, c->s_nrm.p, c->key_b.p, c->cell_start.p,
-                                                       use_role ? c->s_role.p : nullptr, c->work.p, warps,
-                                                       d_qlist, (int)m_list,
-                                                       c->grid.dim[0], c->grid.dim[1], c->grid.dim[2], P, FF,
-                                                       store_rows ? c->feat.p : nullptr, c->counters.p);
+                                                d_qlist ? d_qlist : c->qorder.p, d_qlist ? nullptr : c->counters.p + 11, (int)m_list,
+                                                (!d_qlist && c->have_warp_order) ? c->warp_order.p : nullptr, d_qlist ? 1 : 0,
+                                                c->grid.dim[0], c->grid.dim[1], c->grid.dim[2], P, FF,
+                                                store_rows ? c->feat.p : nullptr, c->counters.p);
     c->launches++;
     return cudaGetLastError();
 }

@@ -225,19 +225,14 @@ cudaError_t build_grid(kpl_ctx* c, const float4* xyz, const float4* nrm, const u
     return cudaGetLastError();
 }
 
-// ---- warp work list --------------------------------------------------------------------------------
-// (used by the feature kernel and the normal kernels)
+// ---- warp work list of the normal kernels ---------------------------------------------------------------
 // A warp works best when its 32 queries share one cell row and span few cells in x: then they form ONE
 // group and no lane idles while another group is processed.  Consecutive sorted points do not have that
 // property (a closed surface crosses a cell row in several separate places), so the queries are cut into
 // runs -- maximal stretches of one row spanning at most span + 1 cells -- and every warp gets up to 32
 // consecutive points of one run: work[w] = (first sorted position, count).  One thread walks one row.
-// Slabs of a larger cloud state the columns [own_lo, own_hi) that hold their scored points: a run then never crosses
-// one of the two faces (a warp shared between scored and unscored points would idle the unscored lanes through the
-// whole neighbourhood walk), and with skip_outside the unscored columns get no warps at all.
 template <bool FILL>
 __global__ void __launch_bounds__(128) run_list_kernel(const int32_t* __restrict__ cell_start, int dimx, int64_t nrows, int span,
-                                                       int own_lo, int own_hi, bool skip_outside,
                                                        int32_t* __restrict__ row_warps, const int32_t* __restrict__ row_offset,
                                                        int2* __restrict__ work)
 {
@@ -247,9 +242,7 @@ __global__ void __launch_bounds__(128) run_list_kernel(const int32_t* __restrict
     int warps = 0;
     int out = FILL ? row_offset[row] : 0;
     int run_x = -1, run_s = 0, run_e = 0;
-    const bool faces = own_hi > own_lo;
     auto close_run = [&]() {
-        if (skip_outside && faces && (run_x < own_lo || run_x >= own_hi)) return;
         for (int s = run_s; s < run_e; s += 32) {
             if (FILL) work[out++] = make_int2(s, min(32, run_e - s));
             ++warps;
@@ -259,7 +252,7 @@ __global__ void __launch_bounds__(128) run_list_kernel(const int32_t* __restrict
     for (int x = 0; x < dimx; ++x) {
         const int next = __ldg(cs + x + 1);
         if (next > prev) {                                   // cell x holds points [prev, next)
-            if (run_x < 0 || x - run_x > span || (faces && ((run_x < own_lo && x >= own_lo) || (run_x < own_hi && x >= own_hi)))) {
+            if (run_x < 0 || x - run_x > span) {
                 if (run_x >= 0) close_run();
                 run_x = x; run_s = prev;
             }
@@ -271,107 +264,194 @@ __global__ void __launch_bounds__(128) run_list_kernel(const int32_t* __restrict
     if (!FILL) row_warps[row] = warps;
 }
 
-// Builds the work lists of the normal kernels (span_n) and the feature kernel (span_f) for the grid in place;
-// a negative span skips that list.  Both totals come back with ONE host synchronisation.
-cudaError_t build_work_lists(kpl_ctx* c, int span_n, int span_f)
+// Builds the work list of the normal kernels for the grid in place (one host synchronisation: its size).
+cudaError_t build_work_list(kpl_ctx* c, int span)
 {
     const GridDesc& g = c->grid;
     const int64_t nrows = (int64_t)g.dim[1] * g.dim[2];
     const unsigned blocks = (unsigned)((nrows + 127) / 128);
     cudaError_t e;
-    struct L { int span; DevBuf<int32_t>* rw; DevBuf<int32_t>* ro; DevBuf<int2>* work; int* total; };
-    L lists[2] = {{span_n, &c->row_warps_n, &c->row_offset_n, &c->work_n, &c->nwarps_norm},
-                  {span_f, &c->row_warps, &c->row_offset, &c->work, &c->nwarps_feat}};
     size_t bytes = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, bytes, (int32_t*)nullptr, (int32_t*)nullptr, (int)nrows + 1, c->stream);
     if ((e = ensure(c->cub_tmp, bytes))) return e;
-    int32_t total[2] = {0, 0};
-    for (int k = 0; k < 2; ++k) {
-        L& l = lists[k];
-        *l.total = 0;
-        if (l.span < 0) continue;
-        if ((e = ensure(*l.rw, (size_t)nrows + 1)) || (e = ensure(*l.ro, (size_t)nrows + 1))) return e;
-        // the feature list (k == 1) honours the slab's owned columns; every point needs a normal, so the other list does not
-        const int own_lo = k == 1 ? g.owned_lo : 0, own_hi = k == 1 ? g.owned_hi : 0;
-        run_list_kernel<false><<<blocks, 128, 0, c->stream>>>(c->cell_start.p, g.dim[0], nrows, l.span, own_lo, own_hi, k == 1, l.rw->p, nullptr, nullptr);
-        if ((e = cudaMemsetAsync(l.rw->p + nrows, 0, sizeof(int32_t), c->stream))) return e;
-        size_t tmp = c->cub_tmp.cap;
-        if ((e = cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, tmp, l.rw->p, l.ro->p, (int)nrows + 1, c->stream))) return e;
-        if ((e = cudaMemcpyAsync(&total[k], l.ro->p + nrows, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream))) return e;
-        c->launches += 3;
-    }
+    int32_t total = 0;
+    c->nwarps_norm = 0;
+    if ((e = ensure(c->row_warps_n, (size_t)nrows + 1)) || (e = ensure(c->row_offset_n, (size_t)nrows + 1))) return e;
+    run_list_kernel<false><<<blocks, 128, 0, c->stream>>>(c->cell_start.p, g.dim[0], nrows, span, c->row_warps_n.p, nullptr, nullptr);
+    if ((e = cudaMemsetAsync(c->row_warps_n.p + nrows, 0, sizeof(int32_t), c->stream))) return e;
+    size_t tmp = c->cub_tmp.cap;
+    if ((e = cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, tmp, c->row_warps_n.p, c->row_offset_n.p, (int)nrows + 1, c->stream))) return e;
+    if ((e = cudaMemcpyAsync(&total, c->row_offset_n.p + nrows, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream))) return e;
+    c->launches += 3;
     if ((e = cudaStreamSynchronize(c->stream))) return e;
     c->syncs++;
-    for (int k = 0; k < 2; ++k) {
-        L& l = lists[k];
-        if (l.span < 0 || total[k] == 0) continue;
-        if ((e = ensure(*l.work, (size_t)total[k] + 1))) return e;
-        const int own_lo = k == 1 ? g.owned_lo : 0, own_hi = k == 1 ? g.owned_hi : 0;
-        run_list_kernel<true><<<blocks, 128, 0, c->stream>>>(c->cell_start.p, g.dim[0], nrows, l.span, own_lo, own_hi, k == 1, nullptr, l.ro->p, l.work->p);
-        *l.total = total[k];
-        c->launches++;
-    }
+    if (total == 0) return cudaGetLastError();
+    if ((e = ensure(c->work_n, (size_t)total + 1))) return e;
+    run_list_kernel<true><<<blocks, 128, 0, c->stream>>>(c->cell_start.p, g.dim[0], nrows, span, nullptr, c->row_offset_n.p, c->work_n.p);
+    c->nwarps_norm = total;
+    c->launches++;
     return cudaGetLastError();
 }
 
-// ---- longest-first order of the feature kernel's work list --------------------------------------------------
-// One warp of the feature kernel runs for milliseconds (32 queries x thousands of neighbours), so a launch of only a
-// few waves -- one slab of an 8-GPU job is ~9 -- idles ~half a warp-time per SM slot at its end.  Launching the
-// expensive warps first (LPT scheduling) leaves the cheap ones for the tail.  Cost estimate = candidate points in the
-// warp's search box (the rows the kernel will stage, same culling).  Blocks retire independently, so the order of the
-// list never changes a result.
-__global__ void __launch_bounds__(128) warp_cost_kernel(const int2* __restrict__ work, int nwarps, const uint32_t* __restrict__ skey,
-                                                        const int32_t* __restrict__ cell_start, int dimx, int dimy, int dimz, int reach,
-                                                        float cellf, float rcull2, uint32_t* __restrict__ cost, uint32_t* __restrict__ order)
+// ---- query order of the feature kernel -----------------------------------------------------------------------
+// A warp of the feature kernel takes 32 queries and walks the union of their neighbourhoods; every lane idles while
+// the others vote for candidates it does not take.  The tighter the 32 queries sit together, the more alike their
+// neighbour sets are -- and ANY assignment of queries to warps gives the same results, because each query accumulates
+// its own votes in canonical candidate order.  So the queries are ordered along a Hilbert curve over a lattice of
+// cell / 2^sub sub-cells (sub = 2: 4 x 4 x 4 per grid cell) and every warp takes 32 CONSECUTIVE queries of that order:
+// all warps but the last are full (runs of a cell row filled 0.90 of the lanes), and the 32 queries of a warp are a
+// compact patch of the surface (model on the 10 M-point scene, tools/sim_query_order.py: 0.69 -> 0.78 of the vote
+// slots used).  Points without a scoring role are left out of the list.
+__device__ __forceinline__ uint64_t hilbert3(uint32_t x, uint32_t y, uint32_t z, int bits)
+{
+    // J. Skilling, "Programming the Hilbert curve" (2004): axes -> transposed index, then interleave
+    uint32_t X[3] = {x, y, z};
+    const uint32_t M = 1u << (bits - 1);
+    for (uint32_t Q = M; Q > 1; Q >>= 1) {
+        const uint32_t P = Q - 1;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            if (X[i] & Q) X[0] ^= P;
+            else { const uint32_t t = (X[0] ^ X[i]) & P; X[0] ^= t; X[i] ^= t; }
+        }
+    }
+    X[1] ^= X[0]; X[2] ^= X[1];
+    uint32_t t = 0;
+    for (uint32_t Q = M; Q > 1; Q >>= 1)
+        if (X[2] & Q) t ^= Q - 1;
+    X[0] ^= t; X[1] ^= t; X[2] ^= t;
+    uint64_t h = 0;
+    for (int b = bits - 1; b >= 0; --b)
+        h = (h << 3) | (uint64_t)((((X[0] >> b) & 1u) << 2) | (((X[1] >> b) & 1u) << 1) | ((X[2] >> b) & 1u));
+    return h;
+}
+
+__global__ void __launch_bounds__(256) curve_key_kernel(const float4* __restrict__ s_pos, const uint32_t* __restrict__ skey,
+                                                        const uint8_t* __restrict__ s_role, int64_t n, GridDesc g, int sub, int shift, int bits,
+                                                        uint64_t* __restrict__ keys, int32_t* __restrict__ pos, unsigned long long* __restrict__ d_nq)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    bool query = false;
+    if (i < n) {
+        query = !s_role || (s_role[i] & 1);
+        uint64_t key = 1ull << (3 * bits);          // no scoring role: behind every query
+        if (query) {
+            const uint32_t k = __ldg(skey + i);
+            const uint32_t t = k / (uint32_t)g.dim[0];
+            int cc[3];
+            cc[0] = (int)(k - t * (uint32_t)g.dim[0]);
+            cc[2] = (int)(t / (uint32_t)g.dim[1]);
+            cc[1] = (int)(t - (uint32_t)cc[2] * (uint32_t)g.dim[1]);
+            double org[3] = {g.org[0], g.org[1], g.org[2]};
+            int zoff = 0;
+            if (g.views) {
+                const int v = __ldg(g.layer_view + cc[2]);
+                if (v >= 0) { const ViewDesc* V = g.views + v; org[0] = V->org[0]; org[1] = V->org[1]; org[2] = V->org[2]; zoff = V->zoff; }
+            }
+            const float4 p = __ldg(s_pos + i);
+            const float v3[3] = {p.x, p.y, p.z};
+            uint32_t f[3];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                // position inside the cell in [0, 1): only the ORDER of the queries depends on it, never a result
+                const double fr = ((double)v3[a] - org[a]) / g.cell - (double)(cc[a] + g.off[a] - (a == 2 ? zoff : 0));
+                const int sc = min(max((int)(fr * (double)(1 << sub)), 0), (1 << sub) - 1);
+                f[a] = (((uint32_t)cc[a] << sub) | (uint32_t)sc) >> shift;
+            }
+            key = hilbert3(f[0], f[1], f[2], bits);
+        }
+        keys[i] = key;
+        pos[i] = (int32_t)i;
+    }
+    const unsigned m = __ballot_sync(0xFFFFFFFFu, query);
+    if (m && (threadIdx.x & 31) == 0) atomicAdd(d_nq, (unsigned long long)__popc(m));
+}
+
+// Cost estimate of warp w of the query order = candidate points in the box the kernel will stage for it.
+__global__ void __launch_bounds__(128) warp_cost_kernel(const int32_t* __restrict__ qorder, const unsigned long long* __restrict__ d_nq, int nwarps,
+                                                        const uint32_t* __restrict__ skey, const int32_t* __restrict__ cell_start,
+                                                        int dimx, int dimy, int dimz, int reach, float cellf, float rcull2,
+                                                        uint32_t* __restrict__ cost, uint32_t* __restrict__ order)
 {
     const int w = blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= nwarps) return;
-    const int2 item = __ldg(work + w);
-    const uint32_t k0 = __ldg(skey + item.x), k1 = __ldg(skey + item.x + item.y - 1);
-    const uint32_t t = k0 / (uint32_t)dimx;
-    const int minx = (int)(k0 - t * (uint32_t)dimx), maxx = (int)(k1 - (k1 / (uint32_t)dimx) * (uint32_t)dimx);
-    const int gz0 = (int)(t / (uint32_t)dimy), gy0 = (int)(t - (uint32_t)gz0 * (uint32_t)dimy);
+    const int nq = (int)*d_nq;
+    int lo[3] = {0x7FFFFFFF, 0x7FFFFFFF, 0x7FFFFFFF}, hi[3] = {-1, -1, -1};
+    for (int l = w * 32; l < min(w * 32 + 32, nq); ++l) {
+        const uint32_t k = __ldg(skey + __ldg(qorder + l));
+        const uint32_t t = k / (uint32_t)dimx;
+        const int cz = (int)(t / (uint32_t)dimy);
+        const int cc[3] = {(int)(k - t * (uint32_t)dimx), (int)(t - (uint32_t)cz * (uint32_t)dimy), cz};
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { lo[a] = min(lo[a], cc[a]); hi[a] = max(hi[a], cc[a]); }
+    }
     unsigned c = 0;
-    for (int zz = max(gz0 - reach, 0); zz <= min(gz0 + reach, dimz - 1); ++zz)
-        for (int yy = max(gy0 - reach, 0); yy <= min(gy0 + reach, dimy - 1); ++yy) {
-            const int gy = max(abs(yy - gy0) - 1, 0), gz = max(abs(zz - gz0) - 1, 0);
-            const float gap2 = (float)(gy * gy + gz * gz) * cellf * cellf;
-            if (!(gap2 < rcull2)) continue;
-            const int rx = min((int)(sqrtf(rcull2 - gap2) / cellf) + 1, reach);
-            const int64_t base = ((int64_t)zz * dimy + yy) * dimx;
-            c += (unsigned)(__ldg(cell_start + base + min(maxx + rx, dimx - 1) + 1) - __ldg(cell_start + base + max(minx - rx, 0)));
-        }
+    if (hi[0] >= 0)
+        for (int zz = max(lo[2] - reach, 0); zz <= min(hi[2] + reach, dimz - 1); ++zz)
+            for (int yy = max(lo[1] - reach, 0); yy <= min(hi[1] + reach, dimy - 1); ++yy) {
+                const int gy = max(max(lo[1] - yy, yy - hi[1]) - 1, 0), gz = max(max(lo[2] - zz, zz - hi[2]) - 1, 0);
+                const float gap2 = (float)(gy * gy + gz * gz) * cellf * cellf;
+                if (!(gap2 < rcull2)) continue;
+                const int rx = min((int)(sqrtf(rcull2 - gap2) / cellf) + 1, reach);
+                const int64_t base = ((int64_t)zz * dimy + yy) * dimx;
+                c += (unsigned)(__ldg(cell_start + base + min(hi[0] + rx, dimx - 1) + 1) - __ldg(cell_start + base + max(lo[0] - rx, 0)));
+            }
     cost[w] = c;
     order[w] = (uint32_t)w;
 }
-__global__ void __launch_bounds__(256) permute_work_kernel(const int2* __restrict__ work, const uint32_t* __restrict__ order, int nwarps,
-                                                           int2* __restrict__ out)
+
+// Leaves the query order in c->qorder (sorted positions), the number of queries in c->counters[11] (device; n when
+// no roles are given) and, when longest_first, the launch order of the warps in c->warp_order.
+// Longest first: one warp of the feature kernel runs for milliseconds (32 queries x thousands of neighbours), so a
+// launch of only a few waves -- one slab of an 8-GPU job is ~9 -- idles ~half a warp-time per SM slot at its end.
+// Launching the expensive warps first (LPT scheduling) leaves the cheap ones for the tail.  Blocks retire
+// independently, so the order of the launch never changes a result.
+cudaError_t build_query_order(kpl_ctx* c, int64_t n, bool use_role, bool longest_first)
 {
-    const int w = blockIdx.x * blockDim.x + threadIdx.x;
-    if (w < nwarps) out[w] = work[order[w]];
-}
-// Reorders c->work (nwarps entries) by descending cost estimate.
-cudaError_t sort_work_longest_first(kpl_ctx* c, int nwarps, float radius)
-{
-    if (nwarps < 2) return cudaSuccess;
     const GridDesc& g = c->grid;
     cudaError_t e;
-    if ((e = ensure(c->scratch_i, 4 * (size_t)nwarps + 16)) || (e = ensure(c->work_tmp, (size_t)nwarps + 1))) return e;
-    uint32_t* cost_a = (uint32_t*)c->scratch_i.p;
-    uint32_t* cost_b = cost_a + nwarps;
-    uint32_t* ord_a = cost_b + nwarps;
-    uint32_t* ord_b = ord_a + nwarps;
+    c->have_warp_order = false;
+    if (n <= 0) return cudaSuccess;
+    if ((e = ensure(c->ckey_a, (size_t)n)) || (e = ensure(c->ckey_b, (size_t)n)) || (e = ensure(c->qorder_a, (size_t)n)) ||
+        (e = ensure(c->qorder, (size_t)n)))
+        return e;
+    // lattice: 2^sub sub-cells per cell and axis while the largest axis fits 21 bits (3 x 21 = 63-bit curve index);
+    // grids beyond 2^21 cells along one axis drop low bits instead
+    const int maxdim = std::max(g.dim[0], std::max(g.dim[1], g.dim[2]));
+    int sub = 2, shift = 0;
+    while (sub > 0 && ((int64_t)maxdim << sub) > (1ll << 21)) --sub;
+    while ((((int64_t)maxdim << sub) >> shift) > (1ll << 21)) ++shift;
+    int bits = 1;
+    while ((1ll << bits) < (((int64_t)maxdim << sub) >> shift) + 1) ++bits;
+    unsigned long long* d_nq = c->counters.p + 11;
+    if ((e = cudaMemsetAsync(d_nq, 0, sizeof(unsigned long long), c->stream))) return e;
     size_t bytes = 0;
-    cub::DeviceRadixSort::SortPairsDescending(nullptr, bytes, cost_a, cost_b, ord_a, ord_b, nwarps, 0, 32, c->stream);
+    cub::DeviceRadixSort::SortPairs(nullptr, bytes, c->ckey_a.p, c->ckey_b.p, c->qorder_a.p, c->qorder.p, (int)n, 0, 64, c->stream);
     if ((e = ensure(c->cub_tmp, bytes))) return e;
-    const double r = (double)radius;
-    warp_cost_kernel<<<(nwarps + 127) / 128, 128, 0, c->stream>>>(c->work.p, nwarps, c->key_b.p, c->cell_start.p, g.dim[0], g.dim[1], g.dim[2],
-                                                                   g.reach_feat, (float)g.cell, (float)(r * r * (1.0 + 1e-5)), cost_a, ord_a);
+    curve_key_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->s_pos.p, c->key_b.p, use_role ? c->s_role.p : nullptr, n, g, sub, shift, bits,
+                                                                        c->ckey_a.p, c->qorder_a.p, d_nq);
     bytes = c->cub_tmp.cap;
-    if ((e = cub::DeviceRadixSort::SortPairsDescending(c->cub_tmp.p, bytes, cost_a, cost_b, ord_a, ord_b, nwarps, 0, 32, c->stream))) return e;
-    permute_work_kernel<<<(nwarps + 255) / 256, 256, 0, c->stream>>>(c->work.p, ord_b, nwarps, c->work_tmp.p);
-    std::swap(c->work, c->work_tmp);
-    c->launches += 2 + 5;
+    const int end_bit = 3 * bits + (use_role ? 1 : 0);      // points without a scoring role carry the bit above the curve index
+    if ((e = cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, bytes, c->ckey_a.p, c->ckey_b.p, c->qorder_a.p, c->qorder.p, (int)n, 0, end_bit, c->stream)))
+        return e;
+    c->launches += 2 + (end_bit + 7) / 8;
+    if (longest_first) {
+        const int nwarps = (int)((n + 31) / 32);
+        if ((e = ensure(c->scratch_i, 3 * (size_t)nwarps + 16)) || (e = ensure(c->warp_order, (size_t)nwarps + 1))) return e;
+        uint32_t* cost_a = (uint32_t*)c->scratch_i.p;
+        uint32_t* cost_b = cost_a + nwarps;
+        uint32_t* ord_a = cost_b + nwarps;
+        bytes = 0;
+        cub::DeviceRadixSort::SortPairsDescending(nullptr, bytes, cost_a, cost_b, ord_a, c->warp_order.p, nwarps, 0, 32, c->stream);
+        if ((e = ensure(c->cub_tmp, bytes))) return e;
+        const double r = (double)c->params.radius_features;
+        warp_cost_kernel<<<(nwarps + 127) / 128, 128, 0, c->stream>>>(c->qorder.p, d_nq, nwarps, c->key_b.p, c->cell_start.p, g.dim[0], g.dim[1], g.dim[2],
+                                                                       g.reach_feat, (float)g.cell, (float)(r * r * (1.0 + 1e-5)), cost_a, ord_a);
+        bytes = c->cub_tmp.cap;
+        if ((e = cub::DeviceRadixSort::SortPairsDescending(c->cub_tmp.p, bytes, cost_a, cost_b, ord_a, c->warp_order.p, nwarps, 0, 32, c->stream))) return e;
+        c->have_warp_order = true;
+        c->launches += 1 + 5;
+    }
     return cudaGetLastError();
 }
 
