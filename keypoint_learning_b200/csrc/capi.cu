@@ -117,7 +117,7 @@ void kpl_destroy(kpl_ctx* ctx)
     release(ctx->key_a); release(ctx->key_b); release(ctx->idx_a); release(ctx->idx_b); release(ctx->cub_tmp);
     release(ctx->row_warps_n); release(ctx->row_offset_n); release(ctx->fragile); release(ctx->views); release(ctx->layer_view);
     release(ctx->view_offsets); release(ctx->qlist);
-    release(ctx->cell_start); release(ctx->work_n); release(ctx->ckey_a); release(ctx->ckey_b); release(ctx->qorder_a); release(ctx->qorder);
+    release(ctx->cell_start); release(ctx->work_n); release(ctx->ckey_a); release(ctx->ckey_b); release(ctx->qorder_a); release(ctx->qorder); release(ctx->warp_starts);
     release(ctx->warp_order); release(ctx->s_pos); release(ctx->s_nrm); release(ctx->feat);
     release(ctx->s_score); release(ctx->score); release(ctx->flag); release(ctx->s_state); release(ctx->kp_idx);
     release(ctx->scratch_f); release(ctx->scratch_i); release(ctx->counters);
@@ -359,16 +359,12 @@ static int prepare_lists(kpl_ctx* ctx, bool normals_given, bool want_features, b
         if (P.normals_mode == KPL_NORMALS_KNN) span_n = normals_knn_uses_work_list(P) ? 1 : -1;
         else if (P.normals_mode == KPL_NORMALS_RADIUS) span_n = P.cells_per_radius;
     }
-    ctx->nwarps_norm = 0;
-    if (span_n >= 0) KPL_CUDA(build_work_list(ctx, span_n));
-    if (want_features) {
-        // A launch of few waves (a slab of a multi-GPU job, a single view) ends with a long idle tail unless the expensive
-        // warps start first; a cloud whose sorted arrays exceed the L2 keeps the spatial order of its queries instead, so
-        // that concurrently running warps keep sharing candidate rows (there the tail is a percent of the launch anyway).
-        const int64_t slots = 148 * 28, warps = (ctx->last_n + 31) / 32;
-        const bool longest_first = warps > slots && warps < 24 * slots && ctx->last_n * 32 < (int64_t)120e6;
-        KPL_CUDA(build_query_order(ctx, ctx->last_n, use_role, longest_first));
-    }
+    // A launch of few waves (a slab of a multi-GPU job, a single view) ends with a long idle tail unless the expensive
+    // warps start first; a cloud whose sorted arrays exceed the L2 keeps the spatial order of its queries instead, so
+    // that concurrently running warps keep sharing candidate rows (there the tail is a percent of the launch anyway).
+    const int64_t slots = 148 * 28;
+    const int64_t longest_first_below = ctx->last_n * 32 < (int64_t)120e6 ? 24 * slots : 0;
+    KPL_CUDA(build_lists(ctx, ctx->last_n, span_n, want_features, use_role, longest_first_below));
     return KPL_OK;
 }
 

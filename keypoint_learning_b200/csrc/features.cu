@@ -323,8 +323,8 @@ template <bool FAST, bool FRAGILE>
 __global__ void __launch_bounds__(FEAT_WARPS * 32)
 feature_kernel(const float4* __restrict__ s_pos, const float4* __restrict__ s_nrm, const uint32_t* __restrict__ skey,
                const int32_t* __restrict__ cell_start,
-               const int32_t* __restrict__ qlist, const unsigned long long* __restrict__ d_nq, int nlist, const uint32_t* __restrict__ warp_order,
-               int rows_by_list, int dimx, int dimy, int dimz, FeatParams P, FusedForest FF, float* __restrict__ feat,
+               const int32_t* __restrict__ qlist, const int32_t* __restrict__ warp_starts, int nwarps, int nlist,
+               const uint32_t* __restrict__ warp_order, int rows_by_list, int dimx, int dimy, int dimz, FeatParams P, FusedForest FF, float* __restrict__ feat,
                unsigned long long* __restrict__ counters)
 {
     extern __shared__ __align__(16) float smem[];
@@ -334,15 +334,15 @@ feature_kernel(const float4* __restrict__ s_pos, const float4* __restrict__ s_nr
     float* sx = hist + P.F * 32;                                  // SoA candidate tile: x, y, z, nx, ny, nz
     float* sy = sx + 32; float* sz = sy + 32; float* snx = sz + 32; float* sny = snx + 32; float* snz = sny + 32;
 
-    // Warp w takes entries [32 w, 32 w + 32) of the query list (sorted positions): the Hilbert order of every point with
-    // a scoring role (kpl_detect*, kpl_features of a whole cloud: the count is on the device) or the ascending list of an
-    // index subset (computePointsForTrainingFeatures, hpp:299-318: rows_by_list, output row = list entry).
+    // Warp w takes entries [warp_starts[w], warp_starts[w + 1]) -- at most 32 -- of the query list (sorted positions): the
+    // Hilbert order of every point with a scoring role (kpl_detect*, kpl_features of a whole cloud; grid.cu: build_lists),
+    // or 32 consecutive entries of the ascending list of an index subset (computePointsForTrainingFeatures, hpp:299-318:
+    // no warp_starts, rows_by_list: output row = list entry).
     int w = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (w >= nwarps) return;
     if (warp_order) w = (int)__ldg(warp_order + w);
-    const int nq = d_nq ? (int)*d_nq : nlist;
-    const int q0 = w * 32;
-    if (q0 >= nq) return;
-    const int nvalid = min(32, nq - q0);
+    const int q0 = warp_starts ? __ldg(warp_starts + w) : w * 32;
+    const int nvalid = warp_starts ? __ldg(warp_starts + w + 1) - q0 : min(32, nlist - q0);
     const bool valid = lane < nvalid;
     const int q = valid ? __ldg(qlist + q0 + lane) : 0;
     bool active = valid;
@@ -366,20 +366,22 @@ feature_kernel(const float4* __restrict__ s_pos, const float4* __restrict__ s_nr
     const uint64_t QY = pack2(qp.y, qp.y), QZ = pack2(qp.z, qp.z);
     const uint64_t QNX = pack2(qn.x, qn.x), QNY = pack2(qn.y, qn.y), QNZ = pack2(qn.z, qn.z);
 
-    // The 32 queries are neighbours on the curve, almost always within a cell or two of each other.  They are processed
-    // in groups of lanes that lie within one cell of the first remaining lane in every axis, so the candidate region of a
-    // pass is a tight box around the group (at most 3 cells wider than the search reach); the rare lanes outside the group
-    // (a jump of the curve, the end of a surface, another view of a batch) idle for that pass (their px is NaN).
+    // The queries of a warp are neighbours on the curve, almost always within a cell or two of each other.  They are
+    // processed in groups: the lanes within two cells of the first remaining lane whose cells span at most three per
+    // axis, so the candidate region of a pass is a tight box around the group; the rare lanes outside it (a chain of
+    // queries drifting over several cells, far-apart entries of an index subset) idle for that pass (their px is NaN).
     unsigned remaining = __ballot_sync(0xFFFFFFFFu, active);
     while (remaining) {
         const int leader = __ffs(remaining) - 1;
         const int lx = __shfl_sync(0xFFFFFFFFu, cx, leader), ly = __shfl_sync(0xFFFFFFFFu, cy, leader), lz = __shfl_sync(0xFFFFFFFFu, cz, leader);
-        const bool member = active && ((remaining >> lane) & 1u) && (unsigned)(cx - lx + 1) <= 2u && (unsigned)(cy - ly + 1) <= 2u &&
-                            (unsigned)(cz - lz + 1) <= 2u;
+        const bool near = active && ((remaining >> lane) & 1u) && (unsigned)(cx - lx + 2) <= 4u && (unsigned)(cy - ly + 2) <= 4u &&
+                          (unsigned)(cz - lz + 2) <= 4u;
+        const int minx = __reduce_min_sync(0xFFFFFFFFu, near ? cx : lx), gy0 = __reduce_min_sync(0xFFFFFFFFu, near ? cy : ly);
+        const int gz0 = __reduce_min_sync(0xFFFFFFFFu, near ? cz : lz);
+        const bool member = near && cx - minx <= 2 && cy - gy0 <= 2 && cz - gz0 <= 2;        // (the leader is one: it is near itself)
         remaining &= ~__ballot_sync(0xFFFFFFFFu, member);
-        const int minx = __reduce_min_sync(0xFFFFFFFFu, member ? cx : lx), maxx = __reduce_max_sync(0xFFFFFFFFu, member ? cx : lx);
-        const int gy0 = __reduce_min_sync(0xFFFFFFFFu, member ? cy : ly), gy1 = __reduce_max_sync(0xFFFFFFFFu, member ? cy : ly);
-        const int gz0 = __reduce_min_sync(0xFFFFFFFFu, member ? cz : lz), gz1 = __reduce_max_sync(0xFFFFFFFFu, member ? cz : lz);
+        const int maxx = __reduce_max_sync(0xFFFFFFFFu, member ? cx : lx);
+        const int gy1 = __reduce_max_sync(0xFFFFFFFFu, member ? cy : ly), gz1 = __reduce_max_sync(0xFFFFFFFFu, member ? cz : lz);
         const float px = member ? qp.x : CUDART_NAN_F;
         const uint64_t QX = pack2(px, px);
 
@@ -696,13 +698,12 @@ cudaError_t launch_features(kpl_ctx* c, int64_t n, bool use_role, bool fuse_fore
                      : (frag ? feature_kernel<false, true> : feature_kernel<false, false>);
     // per device and per process state of the runtime: set it on every launch that needs it (a host-side call)
     if (smem > 48 * 1024 && (e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return e;
-    // the query order was built by the caller (build_query_order); an index subset brings its own list
-    const int64_t nq_max = d_qlist ? m_list : n;
-    const int warps = (int)((nq_max + 31) / 32);
+    // the query order and its warp list were built by the caller (build_lists); an index subset brings its own list
+    const int warps = d_qlist ? (int)((m_list + 31) / 32) : c->nwarps_feat;
     if (warps == 0) return cudaSuccess;
     int blocks = (warps + wpb - 1) / wpb;
     kern<<<blocks, wpb * 32, smem, c->stream>>>(c->s_pos.p, c->s_nrm.p, c->key_b.p, c->cell_start.p,
-                                                d_qlist ? d_qlist : c->qorder.p, d_qlist ? nullptr : c->counters.p + 11, (int)m_list,
+                                                d_qlist ? d_qlist : c->qorder.p, d_qlist ? nullptr : c->warp_starts.p, warps, (int)m_list,
                                                 (!d_qlist && c->have_warp_order) ? c->warp_order.p : nullptr, d_qlist ? 1 : 0,
                                                 c->grid.dim[0], c->grid.dim[1], c->grid.dim[2], P, FF,
                                                 store_rows ? c->feat.p : nullptr, c->counters.p);

@@ -264,44 +264,18 @@ __global__ void __launch_bounds__(128) run_list_kernel(const int32_t* __restrict
     if (!FILL) row_warps[row] = warps;
 }
 
-// Builds the work list of the normal kernels for the grid in place (one host synchronisation: its size).
-cudaError_t build_work_list(kpl_ctx* c, int span)
-{
-    const GridDesc& g = c->grid;
-    const int64_t nrows = (int64_t)g.dim[1] * g.dim[2];
-    const unsigned blocks = (unsigned)((nrows + 127) / 128);
-    cudaError_t e;
-    size_t bytes = 0;
-    cub::DeviceScan::ExclusiveSum(nullptr, bytes, (int32_t*)nullptr, (int32_t*)nullptr, (int)nrows + 1, c->stream);
-    if ((e = ensure(c->cub_tmp, bytes))) return e;
-    int32_t total = 0;
-    c->nwarps_norm = 0;
-    if ((e = ensure(c->row_warps_n, (size_t)nrows + 1)) || (e = ensure(c->row_offset_n, (size_t)nrows + 1))) return e;
-    run_list_kernel<false><<<blocks, 128, 0, c->stream>>>(c->cell_start.p, g.dim[0], nrows, span, c->row_warps_n.p, nullptr, nullptr);
-    if ((e = cudaMemsetAsync(c->row_warps_n.p + nrows, 0, sizeof(int32_t), c->stream))) return e;
-    size_t tmp = c->cub_tmp.cap;
-    if ((e = cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, tmp, c->row_warps_n.p, c->row_offset_n.p, (int)nrows + 1, c->stream))) return e;
-    if ((e = cudaMemcpyAsync(&total, c->row_offset_n.p + nrows, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream))) return e;
-    c->launches += 3;
-    if ((e = cudaStreamSynchronize(c->stream))) return e;
-    c->syncs++;
-    if (total == 0) return cudaGetLastError();
-    if ((e = ensure(c->work_n, (size_t)total + 1))) return e;
-    run_list_kernel<true><<<blocks, 128, 0, c->stream>>>(c->cell_start.p, g.dim[0], nrows, span, nullptr, c->row_offset_n.p, c->work_n.p);
-    c->nwarps_norm = total;
-    c->launches++;
-    return cudaGetLastError();
-}
-
 // ---- query order of the feature kernel -----------------------------------------------------------------------
 // A warp of the feature kernel takes 32 queries and walks the union of their neighbourhoods; every lane idles while
 // the others vote for candidates it does not take.  The tighter the 32 queries sit together, the more alike their
 // neighbour sets are -- and ANY assignment of queries to warps gives the same results, because each query accumulates
 // its own votes in canonical candidate order.  So the queries are ordered along a Hilbert curve over a lattice of
 // cell / 2^sub sub-cells (sub = 2: 4 x 4 x 4 per grid cell) and every warp takes 32 CONSECUTIVE queries of that order:
-// all warps but the last are full (runs of a cell row filled 0.90 of the lanes), and the 32 queries of a warp are a
+// nearly all warps are full (runs of a cell row filled 0.90 of the lanes), and the 32 queries of a warp are a
 // compact patch of the surface (model on the 10 M-point scene, tools/sim_query_order.py: 0.69 -> 0.78 of the vote
-// slots used).  Points without a scoring role are left out of the list.
+// slots used).  Where the curve jumps -- two consecutive queries more than one cell apart: it left the surface and
+// came back elsewhere -- the list is cut, so that a warp never holds two far-apart clusters (it would walk both
+// neighbourhoods one after the other with most lanes idle, and such long-running warps set the duration of a
+// single-wave launch).  Points without a scoring role are left out of the list.
 __device__ __forceinline__ uint64_t hilbert3(uint32_t x, uint32_t y, uint32_t z, int bits)
 {
     // J. Skilling, "Programming the Hilbert curve" (2004): axes -> transposed index, then interleave
@@ -367,17 +341,49 @@ __global__ void __launch_bounds__(256) curve_key_kernel(const float4* __restrict
     if (m && (threadIdx.x & 31) == 0) atomicAdd(d_nq, (unsigned long long)__popc(m));
 }
 
+// head[i] = i when entry i of the query order starts a segment (first entry, or more than one cell from its predecessor in
+// some axis), else 0: an inclusive max-scan turns it into the segment start of every entry
+__global__ void __launch_bounds__(256) segment_head_kernel(const int32_t* __restrict__ qorder, const unsigned long long* __restrict__ d_nq, int64_t n,
+                                                           const uint32_t* __restrict__ skey, int dimx, int dimy, int32_t* __restrict__ head)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int h = 0;
+    if (i > 0 && i < (int64_t)*d_nq) {
+        const uint32_t ka = __ldg(skey + __ldg(qorder + i - 1)), kb = __ldg(skey + __ldg(qorder + i));
+        const uint32_t ta = ka / (uint32_t)dimx, tb = kb / (uint32_t)dimx;
+        const int dx = (int)(ka - ta * (uint32_t)dimx) - (int)(kb - tb * (uint32_t)dimx);
+        const int za = (int)(ta / (uint32_t)dimy), zb = (int)(tb / (uint32_t)dimy);
+        const int dy = (int)(ta - (uint32_t)za * (uint32_t)dimy) - (int)(tb - (uint32_t)zb * (uint32_t)dimy);
+        if (abs(dx) > 1 || abs(dy) > 1 || abs(za - zb) > 1) h = (int)i;
+    }
+    head[i] = h;
+}
+// flag[i] = 1 where a warp starts: every 32nd entry of a segment
+__global__ void __launch_bounds__(256) warp_start_kernel(const int32_t* __restrict__ segstart, const unsigned long long* __restrict__ d_nq, int64_t n,
+                                                         uint8_t* __restrict__ flag)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) flag[i] = (i < (int64_t)*d_nq && (((int)i - segstart[i]) & 31) == 0) ? 1 : 0;
+}
+__global__ void terminate_starts_kernel(int32_t* __restrict__ starts, const int32_t* __restrict__ d_nwarps, const unsigned long long* __restrict__ d_nq)
+{
+    starts[*d_nwarps] = (int32_t)*d_nq;
+}
+struct MaxOp {
+    __host__ __device__ __forceinline__ int32_t operator()(int32_t a, int32_t b) const { return a > b ? a : b; }
+};
+
 // Cost estimate of warp w of the query order = candidate points in the box the kernel will stage for it.
-__global__ void __launch_bounds__(128) warp_cost_kernel(const int32_t* __restrict__ qorder, const unsigned long long* __restrict__ d_nq, int nwarps,
+__global__ void __launch_bounds__(128) warp_cost_kernel(const int32_t* __restrict__ qorder, const int32_t* __restrict__ starts, int nwarps,
                                                         const uint32_t* __restrict__ skey, const int32_t* __restrict__ cell_start,
                                                         int dimx, int dimy, int dimz, int reach, float cellf, float rcull2,
                                                         uint32_t* __restrict__ cost, uint32_t* __restrict__ order)
 {
     const int w = blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= nwarps) return;
-    const int nq = (int)*d_nq;
     int lo[3] = {0x7FFFFFFF, 0x7FFFFFFF, 0x7FFFFFFF}, hi[3] = {-1, -1, -1};
-    for (int l = w * 32; l < min(w * 32 + 32, nq); ++l) {
+    for (int l = __ldg(starts + w); l < __ldg(starts + w + 1); ++l) {
         const uint32_t k = __ldg(skey + __ldg(qorder + l));
         const uint32_t t = k / (uint32_t)dimx;
         const int cz = (int)(t / (uint32_t)dimy);
@@ -400,43 +406,95 @@ __global__ void __launch_bounds__(128) warp_cost_kernel(const int32_t* __restric
     order[w] = (uint32_t)w;
 }
 
-// Leaves the query order in c->qorder (sorted positions), the number of queries in c->counters[11] (device; n when
-// no roles are given) and, when longest_first, the launch order of the warps in c->warp_order.
-// Longest first: one warp of the feature kernel runs for milliseconds (32 queries x thousands of neighbours), so a
-// launch of only a few waves -- one slab of an 8-GPU job is ~9 -- idles ~half a warp-time per SM slot at its end.
-// Launching the expensive warps first (LPT scheduling) leaves the cheap ones for the tail.  Blocks retire
-// independently, so the order of the launch never changes a result.
-cudaError_t build_query_order(kpl_ctx* c, int64_t n, bool use_role, bool longest_first)
+// Builds, for the grid in place, the work list of the normal kernels (span_n >= 0: c->work_n, c->nwarps_norm) and the
+// query order + warp list of the feature kernel (want_features: c->qorder, c->warp_starts with c->nwarps_feat + 1
+// entries) with ONE host synchronisation for the two list sizes.  With longest_first the feature warps additionally get a
+// launch order (c->warp_order), most expensive first: one warp of the feature kernel runs for milliseconds (32 queries x
+// thousands of neighbours), so a launch of only a few waves -- one slab of an 8-GPU job is ~9 -- idles ~half a warp-time
+// per SM slot at its end unless the cheap warps are the ones left for the tail.  Blocks retire independently, so the order
+// of the launch never changes a result.
+cudaError_t build_lists(kpl_ctx* c, int64_t n, int span_n, bool want_features, bool use_role, int64_t longest_first_below)
 {
     const GridDesc& g = c->grid;
+    const int64_t nrows = (int64_t)g.dim[1] * g.dim[2];
+    const unsigned rblocks = (unsigned)((nrows + 127) / 128);
+    const unsigned pblocks = (unsigned)((n + 255) / 256);
     cudaError_t e;
+    c->nwarps_norm = c->nwarps_feat = 0;
     c->have_warp_order = false;
     if (n <= 0) return cudaSuccess;
-    if ((e = ensure(c->ckey_a, (size_t)n)) || (e = ensure(c->ckey_b, (size_t)n)) || (e = ensure(c->qorder_a, (size_t)n)) ||
-        (e = ensure(c->qorder, (size_t)n)))
-        return e;
-    // lattice: 2^sub sub-cells per cell and axis while the largest axis fits 21 bits (3 x 21 = 63-bit curve index);
-    // grids beyond 2^21 cells along one axis drop low bits instead
-    const int maxdim = std::max(g.dim[0], std::max(g.dim[1], g.dim[2]));
-    int sub = 2, shift = 0;
-    while (sub > 0 && ((int64_t)maxdim << sub) > (1ll << 21)) --sub;
-    while ((((int64_t)maxdim << sub) >> shift) > (1ll << 21)) ++shift;
-    int bits = 1;
-    while ((1ll << bits) < (((int64_t)maxdim << sub) >> shift) + 1) ++bits;
+    int32_t total_n = 0, total_f = 0;
+    size_t bytes = 0, need = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, bytes, (int32_t*)nullptr, (int32_t*)nullptr, (int)nrows + 1, c->stream);
+    need = bytes;
+    if (want_features) {
+        cub::DeviceRadixSort::SortPairs(nullptr, bytes, (uint64_t*)nullptr, (uint64_t*)nullptr, (int32_t*)nullptr, (int32_t*)nullptr, (int)n, 0, 64, c->stream);
+        need = std::max(need, bytes);
+        cub::DeviceScan::InclusiveScan(nullptr, bytes, (int32_t*)nullptr, (int32_t*)nullptr, MaxOp(), (int)n, c->stream);
+        need = std::max(need, bytes);
+        cub::DeviceSelect::Flagged(nullptr, bytes, thrust::counting_iterator<int32_t>(0), (uint8_t*)nullptr, (int32_t*)nullptr, (int32_t*)nullptr, (int)n, c->stream);
+        need = std::max(need, bytes);
+    }
+    if ((e = ensure(c->cub_tmp, need))) return e;
+    // ---- sizes of both lists
+    if (span_n >= 0) {
+        if ((e = ensure(c->row_warps_n, (size_t)nrows + 1)) || (e = ensure(c->row_offset_n, (size_t)nrows + 1))) return e;
+        run_list_kernel<false><<<rblocks, 128, 0, c->stream>>>(c->cell_start.p, g.dim[0], nrows, span_n, c->row_warps_n.p, nullptr, nullptr);
+        if ((e = cudaMemsetAsync(c->row_warps_n.p + nrows, 0, sizeof(int32_t), c->stream))) return e;
+        size_t tmp = c->cub_tmp.cap;
+        if ((e = cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, tmp, c->row_warps_n.p, c->row_offset_n.p, (int)nrows + 1, c->stream))) return e;
+        if ((e = cudaMemcpyAsync(&total_n, c->row_offset_n.p + nrows, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream))) return e;
+        c->launches += 3;
+    }
     unsigned long long* d_nq = c->counters.p + 11;
-    if ((e = cudaMemsetAsync(d_nq, 0, sizeof(unsigned long long), c->stream))) return e;
-    size_t bytes = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, bytes, c->ckey_a.p, c->ckey_b.p, c->qorder_a.p, c->qorder.p, (int)n, 0, 64, c->stream);
-    if ((e = ensure(c->cub_tmp, bytes))) return e;
-    curve_key_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->s_pos.p, c->key_b.p, use_role ? c->s_role.p : nullptr, n, g, sub, shift, bits,
-                                                                        c->ckey_a.p, c->qorder_a.p, d_nq);
-    bytes = c->cub_tmp.cap;
-    const int end_bit = 3 * bits + (use_role ? 1 : 0);      // points without a scoring role carry the bit above the curve index
-    if ((e = cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, bytes, c->ckey_a.p, c->ckey_b.p, c->qorder_a.p, c->qorder.p, (int)n, 0, end_bit, c->stream)))
-        return e;
-    c->launches += 2 + (end_bit + 7) / 8;
-    if (longest_first) {
-        const int nwarps = (int)((n + 31) / 32);
+    int32_t* d_nwarps = reinterpret_cast<int32_t*>(c->counters.p + 12);
+    if (want_features) {
+        if ((e = ensure(c->ckey_a, (size_t)n)) || (e = ensure(c->ckey_b, (size_t)n)) || (e = ensure(c->qorder_a, (size_t)n)) ||
+            (e = ensure(c->qorder, (size_t)n)) || (e = ensure(c->warp_starts, (size_t)n + 2)))
+            return e;
+        // lattice: 2^sub sub-cells per cell and axis while the largest axis fits 21 bits (3 x 21 = 63-bit curve index);
+        // grids beyond 2^21 cells along one axis drop low bits instead
+        const int maxdim = std::max(g.dim[0], std::max(g.dim[1], g.dim[2]));
+        int sub = 2, shift = 0;
+        while (sub > 0 && ((int64_t)maxdim << sub) > (1ll << 21)) --sub;
+        while ((((int64_t)maxdim << sub) >> shift) > (1ll << 21)) ++shift;
+        int bits = 1;
+        while ((1ll << bits) < (((int64_t)maxdim << sub) >> shift) + 1) ++bits;
+        if ((e = cudaMemsetAsync(d_nq, 0, 2 * sizeof(unsigned long long), c->stream))) return e;
+        curve_key_kernel<<<pblocks, 256, 0, c->stream>>>(c->s_pos.p, c->key_b.p, use_role ? c->s_role.p : nullptr, n, g, sub, shift, bits,
+                                                         c->ckey_a.p, c->qorder_a.p, d_nq);
+        const int end_bit = 3 * bits + (use_role ? 1 : 0);      // points without a scoring role carry the bit above the curve index
+        size_t tmp = c->cub_tmp.cap;
+        if ((e = cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tmp, c->ckey_a.p, c->ckey_b.p, c->qorder_a.p, c->qorder.p, (int)n, 0, end_bit, c->stream)))
+            return e;
+        // warp list: cut at the jumps of the curve, 32 entries per warp inside a segment (the sort buffers are free now)
+        int32_t* seg = c->qorder_a.p;
+        uint8_t* flag = reinterpret_cast<uint8_t*>(c->ckey_a.p);
+        segment_head_kernel<<<pblocks, 256, 0, c->stream>>>(c->qorder.p, d_nq, n, c->key_b.p, g.dim[0], g.dim[1], seg);
+        tmp = c->cub_tmp.cap;
+        if ((e = cub::DeviceScan::InclusiveScan(c->cub_tmp.p, tmp, seg, seg, MaxOp(), (int)n, c->stream))) return e;
+        warp_start_kernel<<<pblocks, 256, 0, c->stream>>>(seg, d_nq, n, flag);
+        tmp = c->cub_tmp.cap;
+        if ((e = cub::DeviceSelect::Flagged(c->cub_tmp.p, tmp, thrust::counting_iterator<int32_t>(0), flag, c->warp_starts.p, d_nwarps, (int)n, c->stream)))
+            return e;
+        terminate_starts_kernel<<<1, 1, 0, c->stream>>>(c->warp_starts.p, d_nwarps, d_nq);
+        if ((e = cudaMemcpyAsync(&total_f, d_nwarps, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream))) return e;
+        c->launches += 7 + (end_bit + 7) / 8;
+    }
+    if (span_n >= 0 || want_features) {
+        if ((e = cudaStreamSynchronize(c->stream))) return e;
+        c->syncs++;
+    }
+    // ---- the lists themselves
+    if (span_n >= 0 && total_n > 0) {
+        if ((e = ensure(c->work_n, (size_t)total_n + 1))) return e;
+        run_list_kernel<true><<<rblocks, 128, 0, c->stream>>>(c->cell_start.p, g.dim[0], nrows, span_n, nullptr, c->row_offset_n.p, c->work_n.p);
+        c->nwarps_norm = total_n;
+        c->launches++;
+    }
+    c->nwarps_feat = total_f;
+    if (want_features && total_f > 1 && total_f < longest_first_below) {
+        const int nwarps = total_f;
         if ((e = ensure(c->scratch_i, 3 * (size_t)nwarps + 16)) || (e = ensure(c->warp_order, (size_t)nwarps + 1))) return e;
         uint32_t* cost_a = (uint32_t*)c->scratch_i.p;
         uint32_t* cost_b = cost_a + nwarps;
@@ -445,8 +503,8 @@ cudaError_t build_query_order(kpl_ctx* c, int64_t n, bool use_role, bool longest
         cub::DeviceRadixSort::SortPairsDescending(nullptr, bytes, cost_a, cost_b, ord_a, c->warp_order.p, nwarps, 0, 32, c->stream);
         if ((e = ensure(c->cub_tmp, bytes))) return e;
         const double r = (double)c->params.radius_features;
-        warp_cost_kernel<<<(nwarps + 127) / 128, 128, 0, c->stream>>>(c->qorder.p, d_nq, nwarps, c->key_b.p, c->cell_start.p, g.dim[0], g.dim[1], g.dim[2],
-                                                                       g.reach_feat, (float)g.cell, (float)(r * r * (1.0 + 1e-5)), cost_a, ord_a);
+        warp_cost_kernel<<<(nwarps + 127) / 128, 128, 0, c->stream>>>(c->qorder.p, c->warp_starts.p, nwarps, c->key_b.p, c->cell_start.p, g.dim[0], g.dim[1],
+                                                                       g.dim[2], g.reach_feat, (float)g.cell, (float)(r * r * (1.0 + 1e-5)), cost_a, ord_a);
         bytes = c->cub_tmp.cap;
         if ((e = cub::DeviceRadixSort::SortPairsDescending(c->cub_tmp.p, bytes, cost_a, cost_b, ord_a, c->warp_order.p, nwarps, 0, 32, c->stream))) return e;
         c->have_warp_order = true;
