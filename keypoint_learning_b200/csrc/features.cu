@@ -44,6 +44,7 @@ static constexpr int FEAT_WARPS = 1;
 struct FeatParams {
     int n, A, B, F, reach;
     int unbias;            // 1 - bits(2^23): see soft_bin_x2
+    int group_extent;      // cells a group of queries may span beyond its first, per axis
     int recip_normalize;   // row.normalize() as Eigen 3.2.x: multiply by 1/norm instead of dividing (kpl_params.eigen32_normalize)
     float r2, support, adim, ahalf, ainv, bdim, bhalf, binv, cellf, rcull2, mhalf;
     uint64_t one2;   // (1.0f, 1.0f), opaque to the compiler: see dist2_x2
@@ -367,18 +368,19 @@ feature_kernel(const float4* __restrict__ s_pos, const float4* __restrict__ s_nr
     const uint64_t QNX = pack2(qn.x, qn.x), QNY = pack2(qn.y, qn.y), QNZ = pack2(qn.z, qn.z);
 
     // The queries of a warp are neighbours on the curve, almost always within a cell or two of each other.  They are
-    // processed in groups: the lanes within two cells of the first remaining lane whose cells span at most three per
-    // axis, so the candidate region of a pass is a tight box around the group; the rare lanes outside it (a chain of
+    // processed in groups: the lanes within P.group_extent cells of the first remaining lane whose cells span at most
+    // P.group_extent + 1 per axis, so the candidate region of a pass is a tight box around the group; the rare lanes outside it (a chain of
     // queries drifting over several cells, far-apart entries of an index subset) idle for that pass (their px is NaN).
+    const int GE = P.group_extent;
     unsigned remaining = __ballot_sync(0xFFFFFFFFu, active);
     while (remaining) {
         const int leader = __ffs(remaining) - 1;
         const int lx = __shfl_sync(0xFFFFFFFFu, cx, leader), ly = __shfl_sync(0xFFFFFFFFu, cy, leader), lz = __shfl_sync(0xFFFFFFFFu, cz, leader);
-        const bool near = active && ((remaining >> lane) & 1u) && (unsigned)(cx - lx + 2) <= 4u && (unsigned)(cy - ly + 2) <= 4u &&
-                          (unsigned)(cz - lz + 2) <= 4u;
+        const bool near = active && ((remaining >> lane) & 1u) && (unsigned)(cx - lx + GE) <= 2u * GE && (unsigned)(cy - ly + GE) <= 2u * GE &&
+                          (unsigned)(cz - lz + GE) <= 2u * GE;
         const int minx = __reduce_min_sync(0xFFFFFFFFu, near ? cx : lx), gy0 = __reduce_min_sync(0xFFFFFFFFu, near ? cy : ly);
         const int gz0 = __reduce_min_sync(0xFFFFFFFFu, near ? cz : lz);
-        const bool member = near && cx - minx <= 2 && cy - gy0 <= 2 && cz - gz0 <= 2;        // (the leader is one: it is near itself)
+        const bool member = near && cx - minx <= GE && cy - gy0 <= GE && cz - gz0 <= GE;        // (the leader is one: it is near itself)
         remaining &= ~__ballot_sync(0xFFFFFFFFu, member);
         const int maxx = __reduce_max_sync(0xFFFFFFFFu, member ? cx : lx);
         const int gy1 = __reduce_max_sync(0xFFFFFFFFu, member ? cy : ly), gz1 = __reduce_max_sync(0xFFFFFFFFu, member ? cz : lz);
@@ -662,6 +664,10 @@ cudaError_t launch_features(kpl_ctx* c, int64_t n, bool use_role, bool fuse_fore
     P.one2 = 0x3F8000003F800000ull;
     P.mhalf = -0.5f;
     P.unbias = 1 - (int)FLOOR_MAGIC_BITS;
+    P.group_extent = 3;      // 2 / 3 cells measured 151.8 / 151.1 ms on the 10 M scene, 1.77 / 1.28 ms on the 64 k-point bundled view
+#ifdef KPL_EXPERIMENTS
+    if (const char* ev = getenv("KPL_GROUP_E")) P.group_extent = atoi(ev);
+#endif
     auto dup = [](float v) { uint32_t b; memcpy(&b, &v, 4); return ((uint64_t)b << 32) | b; };
     P.adim2 = dup(P.adim); P.nadim2 = dup(-P.adim); P.ainv2 = dup(P.ainv); P.ahalf2 = dup(P.ahalf);
     // the packed loop bins the HALF cosine: bin width, half width and reciprocal scaled by exact powers of two

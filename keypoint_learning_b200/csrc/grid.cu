@@ -18,6 +18,7 @@
 #include <thrust/iterator/reverse_iterator.h>
 #include <thrust/iterator/counting_iterator.h>
 #include <cmath>
+#include <cstdlib>
 #include "kpl_internal.h"
 
 namespace kpl {
@@ -344,7 +345,7 @@ __global__ void __launch_bounds__(256) curve_key_kernel(const float4* __restrict
 // head[i] = i when entry i of the query order starts a segment (first entry, or more than one cell from its predecessor in
 // some axis), else 0: an inclusive max-scan turns it into the segment start of every entry
 __global__ void __launch_bounds__(256) segment_head_kernel(const int32_t* __restrict__ qorder, const unsigned long long* __restrict__ d_nq, int64_t n,
-                                                           const uint32_t* __restrict__ skey, int dimx, int dimy, int32_t* __restrict__ head)
+                                                           const uint32_t* __restrict__ skey, int dimx, int dimy, int jump, int32_t* __restrict__ head)
 {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -355,7 +356,7 @@ __global__ void __launch_bounds__(256) segment_head_kernel(const int32_t* __rest
         const int dx = (int)(ka - ta * (uint32_t)dimx) - (int)(kb - tb * (uint32_t)dimx);
         const int za = (int)(ta / (uint32_t)dimy), zb = (int)(tb / (uint32_t)dimy);
         const int dy = (int)(ta - (uint32_t)za * (uint32_t)dimy) - (int)(tb - (uint32_t)zb * (uint32_t)dimy);
-        if (abs(dx) > 1 || abs(dy) > 1 || abs(za - zb) > 1) h = (int)i;
+        if (abs(dx) > jump || abs(dy) > jump || abs(za - zb) > jump) h = (int)i;
     }
     head[i] = h;
 }
@@ -455,7 +456,11 @@ cudaError_t build_lists(kpl_ctx* c, int64_t n, int span_n, bool want_features, b
         // lattice: 2^sub sub-cells per cell and axis while the largest axis fits 21 bits (3 x 21 = 63-bit curve index);
         // grids beyond 2^21 cells along one axis drop low bits instead
         const int maxdim = std::max(g.dim[0], std::max(g.dim[1], g.dim[2]));
-        int sub = 2, shift = 0;
+        int sub = 2, shift = 0, jump = 1;
+#ifdef KPL_EXPERIMENTS
+        if (const char* ev = getenv("KPL_SUB")) sub = atoi(ev);
+        if (const char* ev = getenv("KPL_JUMP")) jump = atoi(ev);
+#endif
         while (sub > 0 && ((int64_t)maxdim << sub) > (1ll << 21)) --sub;
         while ((((int64_t)maxdim << sub) >> shift) > (1ll << 21)) ++shift;
         int bits = 1;
@@ -470,7 +475,7 @@ cudaError_t build_lists(kpl_ctx* c, int64_t n, int span_n, bool want_features, b
         // warp list: cut at the jumps of the curve, 32 entries per warp inside a segment (the sort buffers are free now)
         int32_t* seg = c->qorder_a.p;
         uint8_t* flag = reinterpret_cast<uint8_t*>(c->ckey_a.p);
-        segment_head_kernel<<<pblocks, 256, 0, c->stream>>>(c->qorder.p, d_nq, n, c->key_b.p, g.dim[0], g.dim[1], seg);
+        segment_head_kernel<<<pblocks, 256, 0, c->stream>>>(c->qorder.p, d_nq, n, c->key_b.p, g.dim[0], g.dim[1], jump, seg);
         tmp = c->cub_tmp.cap;
         if ((e = cub::DeviceScan::InclusiveScan(c->cub_tmp.p, tmp, seg, seg, MaxOp(), (int)n, c->stream))) return e;
         warp_start_kernel<<<pblocks, 256, 0, c->stream>>>(seg, d_nq, n, flag);
