@@ -74,13 +74,20 @@ __device__ __forceinline__ void key_to_cell_f(uint32_t key, int dimx, int dimy, 
 }
 
 // ---- verified-fast arithmetic --------------------------------------------------------------------
-static constexpr float FAST_SQRT_LO = 9.094947017729282e-13f;   // 2^-40
+// The FMA-corrected rsqrt square root is bit-identical to the IEEE one on [2^-100, 2^40) (selftest_kernel checks every
+// float of that range on the device; below 2^-102 the correction term turns denormal and the last bit goes wrong,
+// tools/probe_fast_sqrt.cu).  Smaller d2 -- duplicate points (0), denormal-range distances -- need no branch: with the
+// rsqrt argument clamped to 2^-100 the sequence returns 0 for 0 and something below 2^-50 otherwise, like the true root,
+// and both vanish in the only two places the distance is used (floor(dist / adim) = 0; dist - adim / 2 rounds to
+// -adim / 2) as long as adim >= 2^-20, which launch_features requires of the FAST variant.
+static constexpr float FAST_SQRT_LO = 7.888609052210118e-31f;   // 2^-100
 static constexpr float FAST_SQRT_HI = 1.099511627776e12f;       // 2^40
+static constexpr float FAST_ADIM_MIN = 9.5367431640625e-07f;    // 2^-20
 
 __device__ __forceinline__ float fast_sqrt_core(float x)
 {
     float y;
-    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(fmaxf(x, FAST_SQRT_LO)));
     const float s = __fmul_rn(x, y), h = __fmul_rn(y, 0.5f);
     const float e = __fmaf_rn(-s, s, x);
     return __fmaf_rn(e, h, s);
@@ -89,10 +96,7 @@ __device__ __forceinline__ float fast_sqrt_core(float x)
 template <bool FAST>
 __device__ __forceinline__ float ksqrt(float x)
 {
-    if (!FAST) return __fsqrt_rn(x);
-    float r = fast_sqrt_core(x);
-    if (!(x >= FAST_SQRT_LO)) r = __fsqrt_rn(x);   // zero (duplicate points) and denormal-range d2: rare
-    return r;
+    return FAST ? fast_sqrt_core(x) : __fsqrt_rn(x);
 }
 __device__ __forceinline__ float fast_div_core(float x, float c, float cinv)
 {
@@ -133,8 +137,8 @@ __device__ __forceinline__ uint64_t fast_div_x2(uint64_t x, uint64_t nc, uint64_
 __device__ __forceinline__ uint64_t fast_sqrt_x2(uint64_t x, float x0, float x1)
 {
     float y0, y1;
-    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y0) : "f"(x0));
-    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y1) : "f"(x1));
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y0) : "f"(fmaxf(x0, FAST_SQRT_LO)));
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y1) : "f"(fmaxf(x1, FAST_SQRT_LO)));
     const uint64_t y = pack2(y0, y1);
     const uint64_t s = mul2(x, y), h = mul2(y, 0x3F0000003F000000ull);
     const uint64_t e = fma2(neg2(s), s, x);
@@ -192,7 +196,7 @@ __device__ __forceinline__ float half_cosine(float dot, float minus_half)
     return h;
 }
 
-// One thread per (binade, mantissa): result[0] counts sqrt mismatches over [2^-40, 2^40), result[1]
+// One thread per (binade, mantissa): result[0] counts sqrt mismatches over [2^-100, 2^40), result[1]
 // / result[2] division mismatches for the annulus / bin width over every mantissa of [1, 2) and [-2,-1)
 // (exact power-of-two scaling extends the proof to every binade without under/overflow), result[3]
 // mismatches of the packed squared distance against the scalar dist2() on values built from the mantissa.
@@ -201,7 +205,7 @@ __global__ void __launch_bounds__(256) selftest_kernel(float adim, float ainv, f
     const uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;   // 2^23 mantissas
     if (m >= (1u << 23)) return;
     unsigned bad_s = 0, bad_a = 0, bad_b = 0, bad_p = 0;
-    for (int ex = 127 - 40; ex < 127 + 40; ++ex) {
+    for (int ex = 127 - 100; ex < 127 + 40; ++ex) {
         const float x = __uint_as_float(((uint32_t)ex << 23) | m);
         bad_s += (__float_as_uint(fast_sqrt_core(x)) != __float_as_uint(__fsqrt_rn(x)));
     }
@@ -483,7 +487,7 @@ feature_kernel(const float4* __restrict__ s_pos, const float4* __restrict__ s_nr
                 // hi_first: the candidate in the HIGH half of the packed operands is the earlier one (64-bit loads of the
                 // reversed tile); both halves vote then
                 auto vote_pair = [&](const uint64_t X, const uint64_t Y, const uint64_t Z, const uint64_t NX, const uint64_t NY,
-                                     const uint64_t NZ, const bool two, const bool lane_counts, auto hi_first) {
+                                     const uint64_t NZ, const bool two, auto hi_first) {
                     const uint64_t D = dist2_x2(QX, QY, QZ, X, Y, Z, P.one2);
                     // 1 - (n0*m0 + (n1*m1 + n2*m2)), hpp:341-342 with Eigen's reduction order, clamped to [0, 2]
                     // (src/KeypointLearning.cpp:70-73) -- carried as its exact half
@@ -491,8 +495,7 @@ feature_kernel(const float4* __restrict__ s_pos, const float4* __restrict__ s_nr
                     float t0, t1, d0, d1;
                     unpack2(dot, t0, t1);
                     unpack2(D, d0, d1);
-                    uint64_t DIST = fast_sqrt_x2(D, d0, d1);                                           // hpp:345 sqrt(distances[..])
-                    if (lane_counts && !(fminf(d0, d1) >= FAST_SQRT_LO)) DIST = pack2(__fsqrt_rn(d0), __fsqrt_rn(d1));   // zero / denormal-range d2: rare
+                    const uint64_t DIST = fast_sqrt_x2(D, d0, d1);                                     // hpp:345 sqrt(distances[..])
                     const uint64_t HCOS = pack2(half_cosine(t0, P.mhalf), half_cosine(t1, P.mhalf));
                     int a0, a1, ap0, ap1, b0, b1, bp0, bp1;
                     uint64_t WA, UA, WB, UB;
@@ -520,8 +523,7 @@ feature_kernel(const float4* __restrict__ s_pos, const float4* __restrict__ s_nr
                     for (int sl = 30; sl >= 0; sl -= 2)            // candidates 31 - sl - 1 (high half) and 31 - sl (low half)
                         vote_pair(*reinterpret_cast<const uint64_t*>(sx + sl), *reinterpret_cast<const uint64_t*>(sy + sl),
                                   *reinterpret_cast<const uint64_t*>(sz + sl), *reinterpret_cast<const uint64_t*>(snx + sl),
-                                  *reinterpret_cast<const uint64_t*>(sny + sl), *reinterpret_cast<const uint64_t*>(snz + sl), true, valid,
-                                  std::true_type());
+                                  *reinterpret_cast<const uint64_t*>(sny + sl), *reinterpret_cast<const uint64_t*>(snz + sl), true, std::true_type());
                     mask = 0;
                 }
                 while (mask) {
@@ -533,8 +535,7 @@ feature_kernel(const float4* __restrict__ s_pos, const float4* __restrict__ s_nr
                     const unsigned t0 = tile0 + 4u * m0, t1 = tile0 + 4u * m1;
                     vote_pair(pack2(lds_tile<0>(t0), lds_tile<0>(t1)), pack2(lds_tile<128>(t0), lds_tile<128>(t1)),
                               pack2(lds_tile<256>(t0), lds_tile<256>(t1)), pack2(lds_tile<384>(t0), lds_tile<384>(t1)),
-                              pack2(lds_tile<512>(t0), lds_tile<512>(t1)), pack2(lds_tile<640>(t0), lds_tile<640>(t1)), two, true,
-                              std::false_type());
+                              pack2(lds_tile<512>(t0), lds_tile<512>(t1)), pack2(lds_tile<640>(t0), lds_tile<640>(t1)), two, std::false_type());
                 }
             } else {
                 while (mask) {
@@ -623,7 +624,7 @@ static cudaError_t fast_math_verdict(kpl_ctx* c, const FeatParams& P, bool& fast
     {
         std::lock_guard<std::mutex> lock(cache_mutex);
         for (const Verdict& v : cache)
-            if (v.adim == P.adim && v.bdim == P.bdim && v.device == c->device) { fast = v.fast && P.r2 <= FAST_SQRT_HI; return cudaSuccess; }
+            if (v.adim == P.adim && v.bdim == P.bdim && v.device == c->device) { fast = v.fast && P.r2 <= FAST_SQRT_HI && P.adim >= FAST_ADIM_MIN; return cudaSuccess; }
     }
     unsigned* d_res = reinterpret_cast<unsigned*>(c->counters.p + 6);   // counters[6..7] are scratch
     cudaError_t e;
@@ -639,7 +640,7 @@ static cudaError_t fast_math_verdict(kpl_ctx* c, const FeatParams& P, bool& fast
         std::lock_guard<std::mutex> lock(cache_mutex);
         cache.push_back({P.adim, P.bdim, c->device, fast});
     }
-    fast = fast && P.r2 <= FAST_SQRT_HI;         // the fast sqrt is only proven below 2^40
+    fast = fast && P.r2 <= FAST_SQRT_HI && P.adim >= FAST_ADIM_MIN;   // range of the fast square root (see FAST_SQRT_LO)
     c->launches++;
     return cudaGetLastError();
 }
