@@ -313,15 +313,22 @@ __device__ __forceinline__ float lds_tile(unsigned a)
 // in shared-memory latency at 28 resident warps: 211 ms vs 204 ms on the 10 M-point scene).
 // ja / jb = primary annulus / bin index + 1 (hbm = this lane's column one annulus row BELOW the histogram), ap / bp = pair
 // indices; the votes carry the signs of the soft-binning quotients, |v| is the weight.
-__device__ __forceinline__ void vote4(unsigned hbm, unsigned hb, unsigned row_bytes, int ja, int ap, int jb, int bp, float v00, float v01, float v10, float v11)
+__device__ __forceinline__ void vote4(unsigned hbm, unsigned hb, unsigned row_bytes, int ja, int ap, int jb, int bp, float v00, float v01, float v10,
+                                      float v11, bool on = true)
 {
     const unsigned ra = hbm + (unsigned)ja * row_bytes, rp = hb + (unsigned)ap * row_bytes;
     const unsigned c00 = ra + ((unsigned)jb << 7), c01 = ra + ((unsigned)bp << 7);      // c00 / c10 lie one bin too high: OFF = -128
     const unsigned c10 = rp + ((unsigned)jb << 7), c11 = rp + ((unsigned)bp << 7);
-    sts_f32<-128>(c00, __fadd_rn(lds_f32<-128>(c00), fabsf(v00)));
-    sts_f32<0>(c01, __fadd_rn(lds_f32<0>(c01), fabsf(v01)));
-    sts_f32<-128>(c10, __fadd_rn(lds_f32<-128>(c10), fabsf(v10)));
-    sts_f32<0>(c11, __fadd_rn(lds_f32<0>(c11), fabsf(v11)));
+    // `on` = false (the odd last vote of a lane, paired with itself): everything but the stores runs -- predicated stores
+    // instead of a divergent branch around the four updates
+    const float h00 = __fadd_rn(lds_f32<-128>(c00), fabsf(v00));
+    if (on) sts_f32<-128>(c00, h00);
+    const float h01 = __fadd_rn(lds_f32<0>(c01), fabsf(v01));
+    if (on) sts_f32<0>(c01, h01);
+    const float h10 = __fadd_rn(lds_f32<-128>(c10), fabsf(v10));
+    if (on) sts_f32<-128>(c10, h10);
+    const float h11 = __fadd_rn(lds_f32<0>(c11), fabsf(v11));
+    if (on) sts_f32<0>(c11, h11);
 }
 
 template <bool FAST, bool FRAGILE>
@@ -511,7 +518,7 @@ feature_kernel(const float4* __restrict__ s_pos, const float4* __restrict__ s_nr
                         vote4(hbm, hb, row_bytes, a0, ap0, b0, bp0, v00a, v01a, v10a, v11a);
                     } else {
                         vote4(hbm, hb, row_bytes, a0, ap0, b0, bp0, v00a, v01a, v10a, v11a);
-                        if (two) vote4(hbm, hb, row_bytes, a1, ap1, b1, bp1, v00b, v01b, v10b, v11b);
+                        vote4(hbm, hb, row_bytes, a1, ap1, b1, bp1, v00b, v01b, v10b, v11b, two);
                     }
                 };
                 // Interior tiles -- every query of the warp takes every one of the 32 candidates, about a third of
