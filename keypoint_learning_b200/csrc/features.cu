@@ -40,11 +40,15 @@ namespace kpl {
 // gives ptxas its best allocation: 64 registers without spills (bounds of 128 threads: 64 with spills, 180.0 ms;
 // (32, 28): 71 registers, 181.9 ms; (32): 178.0 ms).
 static constexpr int FEAT_WARPS = 1;
+// Largest mask of a tile from which the in-order loop (16 iterations of ~120 instructions) beats the bit walk
+// (ceil(max / 2) iterations of ~137)
+static constexpr int DENSE_TILE = 29;
 
 struct FeatParams {
     int n, A, B, F, reach;
     int unbias;            // 1 - bits(2^23): see soft_bin_x2
     int group_extent;      // cells a group of queries may span beyond its first, per axis
+    int dense_tile;        // DENSE_TILE
     int recip_normalize;   // row.normalize() as Eigen 3.2.x: multiply by 1/norm instead of dividing (kpl_params.eigen32_normalize)
     float r2, support, adim, ahalf, ainv, bdim, bhalf, binv, cellf, rcull2, mhalf;
     uint64_t one2;   // (1.0f, 1.0f), opaque to the compiler: see dist2_x2
@@ -492,9 +496,9 @@ feature_kernel(const float4* __restrict__ s_pos, const float4* __restrict__ s_nr
                 // pair while the current eight read-modify-writes drain -- was measured slower: 80 registers,
                 // 211 ms vs 204 ms on the 10 M-point scene; capped at 72 registers 215 ms.)
                 // hi_first: the candidate in the HIGH half of the packed operands is the earlier one (64-bit loads of the
-                // reversed tile); both halves vote then
+                // reversed tile).  on_lo / on_hi: whether that half's four updates are stored (predicated stores).
                 auto vote_pair = [&](const uint64_t X, const uint64_t Y, const uint64_t Z, const uint64_t NX, const uint64_t NY,
-                                     const uint64_t NZ, const bool two, auto hi_first) {
+                                     const uint64_t NZ, const bool on_lo, const bool on_hi, auto hi_first) {
                     const uint64_t D = dist2_x2(QX, QY, QZ, X, Y, Z, P.one2);
                     // 1 - (n0*m0 + (n1*m1 + n2*m2)), hpp:341-342 with Eigen's reduction order, clamped to [0, 2]
                     // (src/KeypointLearning.cpp:70-73) -- carried as its exact half
@@ -514,23 +518,26 @@ feature_kernel(const float4* __restrict__ s_pos, const float4* __restrict__ s_nr
                     unpack2(mul2(UB, WA), v10a, v10b);
                     unpack2(mul2(WB, WA), v11a, v11b);
                     if constexpr (decltype(hi_first)::value) {
-                        vote4(hbm, hb, row_bytes, a1, ap1, b1, bp1, v00b, v01b, v10b, v11b);
-                        vote4(hbm, hb, row_bytes, a0, ap0, b0, bp0, v00a, v01a, v10a, v11a);
+                        vote4(hbm, hb, row_bytes, a1, ap1, b1, bp1, v00b, v01b, v10b, v11b, on_hi);
+                        vote4(hbm, hb, row_bytes, a0, ap0, b0, bp0, v00a, v01a, v10a, v11a, on_lo);
                     } else {
-                        vote4(hbm, hb, row_bytes, a0, ap0, b0, bp0, v00a, v01a, v10a, v11a);
-                        vote4(hbm, hb, row_bytes, a1, ap1, b1, bp1, v00b, v01b, v10b, v11b, two);
+                        vote4(hbm, hb, row_bytes, a0, ap0, b0, bp0, v00a, v01a, v10a, v11a, on_lo);
+                        vote4(hbm, hb, row_bytes, a1, ap1, b1, bp1, v00b, v01b, v10b, v11b, on_hi);
                     }
                 };
-                // Interior tiles -- every query of the warp takes every one of the 32 candidates, about a third of
-                // all vote iterations -- need no bit walking: the warp steps through the tile in order and the
-                // candidate pairs come straight out of 64-bit broadcast loads.  Lanes beyond the run's last point
-                // (lane >= nvalid) tag along on NaN queries; their histogram columns are never read.
-                if (__all_sync(0xFFFFFFFFu, valid ? (mask == 0xFFFFFFFFu) : true)) {
+                // Dense tiles -- some query takes (nearly) all 32 candidates, so the bit walk below would run 15 or 16
+                // iterations anyway; half of all vote iterations, a third of them in tiles EVERY query takes whole -- are
+                // stepped through in order instead: no bit walking, the candidate pairs come straight out of 64-bit
+                // broadcast loads, and a lane stores only the votes of its own mask bits.
+                if (__reduce_max_sync(0xFFFFFFFFu, (unsigned)__popc(mask)) >= (unsigned)P.dense_tile) {
 #pragma unroll 2
-                    for (int sl = 30; sl >= 0; sl -= 2)            // candidates 31 - sl - 1 (high half) and 31 - sl (low half)
+                    for (int sl = 30; sl >= 0; sl -= 2) {          // candidates 31 - sl - 1 (high half) and 31 - sl (low half)
+                        const unsigned two_bits = mask >> sl;
                         vote_pair(*reinterpret_cast<const uint64_t*>(sx + sl), *reinterpret_cast<const uint64_t*>(sy + sl),
                                   *reinterpret_cast<const uint64_t*>(sz + sl), *reinterpret_cast<const uint64_t*>(snx + sl),
-                                  *reinterpret_cast<const uint64_t*>(sny + sl), *reinterpret_cast<const uint64_t*>(snz + sl), true, std::true_type());
+                                  *reinterpret_cast<const uint64_t*>(sny + sl), *reinterpret_cast<const uint64_t*>(snz + sl),
+                                  (two_bits & 1u) != 0, (two_bits & 2u) != 0, std::true_type());
+                    }
                     mask = 0;
                 }
                 while (mask) {
@@ -542,7 +549,7 @@ feature_kernel(const float4* __restrict__ s_pos, const float4* __restrict__ s_nr
                     const unsigned t0 = tile0 + 4u * m0, t1 = tile0 + 4u * m1;
                     vote_pair(pack2(lds_tile<0>(t0), lds_tile<0>(t1)), pack2(lds_tile<128>(t0), lds_tile<128>(t1)),
                               pack2(lds_tile<256>(t0), lds_tile<256>(t1)), pack2(lds_tile<384>(t0), lds_tile<384>(t1)),
-                              pack2(lds_tile<512>(t0), lds_tile<512>(t1)), pack2(lds_tile<640>(t0), lds_tile<640>(t1)), two, std::false_type());
+                              pack2(lds_tile<512>(t0), lds_tile<512>(t1)), pack2(lds_tile<640>(t0), lds_tile<640>(t1)), true, two, std::false_type());
                 }
             } else {
                 while (mask) {
@@ -673,8 +680,10 @@ cudaError_t launch_features(kpl_ctx* c, int64_t n, bool use_role, bool fuse_fore
     P.mhalf = -0.5f;
     P.unbias = 1 - (int)FLOOR_MAGIC_BITS;
     P.group_extent = 3;      // 2 / 3 cells measured 151.8 / 151.1 ms on the 10 M scene, 1.77 / 1.28 ms on the 64 k-point bundled view
+    P.dense_tile = DENSE_TILE;
 #ifdef KPL_EXPERIMENTS
     if (const char* ev = getenv("KPL_GROUP_E")) P.group_extent = atoi(ev);
+    if (const char* ev = getenv("KPL_DENSE_TILE")) P.dense_tile = atoi(ev);
 #endif
     auto dup = [](float v) { uint32_t b; memcpy(&b, &v, 4); return ((uint64_t)b << 32) | b; };
     P.adim2 = dup(P.adim); P.nadim2 = dup(-P.adim); P.ainv2 = dup(P.ainv); P.ahalf2 = dup(P.ahalf);
