@@ -82,8 +82,8 @@ typedef struct kpl_params {
     int32_t slab_guard_cells; /*    to look beyond such a face fails with KPL_E_HALO, except for points in the    */
                               /*    outermost slab_guard_cells columns at that face (nothing kept depends on them) */
     int32_t slab_owned_lo;    /* forced grid only: the local columns [lo, hi) hold every point with a scoring role    */
-    int32_t slab_owned_hi;    /*    (hi > lo; 0,0 = not stated).  Warps of the feature kernel are then never shared      */
-                              /*    between scored and unscored columns, and unscored columns get no warps at all         */
+    int32_t slab_owned_hi;    /*    (hi > lo; 0,0 = not stated).  A hint kept for ABI stability: the feature kernel's    */
+                              /*    query list is built from the roles themselves, unscored points get no lanes at all   */
     int32_t uniform_sampling_centre; /* kpl_uniform_sample: 0 = PCL 1.8.0's literal rule (closest to the voxel INDEX vector taken as
                                         a point), 1 = closest to the voxel centre                                        */
     int32_t eigen32_normalize;/* per-annulus row.normalize() (hpp:360-365): 0 = divide by the norm (Eigen >= 3.3, default),   */
