@@ -464,6 +464,45 @@ def test_duplicate_points(kpl, oracle, main_forest):
     d.close()
 
 
+def test_scattered_clusters_and_isolated_points(kpl, oracle, main_forest):
+    """The feature kernel's query list (Hilbert order, cut where the curve jumps; grid.cu: build_lists) on a cloud that is
+    nothing but jumps: small clusters far apart, isolated points (warps of one query), and a cluster whose points are
+    2e-21 apart (d2 in the denormal range: the branch-free square root must give what the IEEE one gives, features.cu)."""
+    rng = np.random.default_rng(99)
+    base = np.load(os.path.join(os.path.dirname(__file__), "golden", "views", "cheff000.npz"))["xyz"]
+    parts = []
+    for c in range(40):                                                    # 40 patches of 5..120 points, 300 apart
+        m = int(rng.integers(5, 121))
+        s = int(rng.integers(0, len(base) - 4000))
+        blob = base[s:s + 4000]
+        blob = blob[np.argsort(np.linalg.norm(blob - blob[0], axis=1))[:m]]
+        parts.append(blob - blob[0] + np.array([300.0 * (c % 7), 300.0 * ((c // 7) % 3), 300.0 * (c // 21)], np.float32))
+    parts.append(rng.uniform(-1000, 1000, (200, 3)).astype(np.float32))    # isolated points
+    tiny = np.zeros((12, 3), np.float32)
+    tiny[:, 0] = np.arange(12, dtype=np.float32) * np.float32(2e-21)       # d2 = 4e-42 .. : denormal squared distances
+    tiny[:, 1] = (np.arange(12) % 3).astype(np.float32) * np.float32(1e-21)
+    parts.append(tiny)                                                     # at the origin, inside the first patch
+    xyz = np.ascontiguousarray(np.concatenate(parts).astype(np.float32))
+    xyz = np.ascontiguousarray(xyz[rng.permutation(len(xyz))])
+    nrm = oracle.normals_knn(xyz, 10)
+    d = make_detector(kpl)
+    d.keepIntermediates(True)
+    d.setInputCloud(xyz)
+    _, idx = d.compute()
+    assert same_bits(d.fetch("normals", len(xyz), 4), nrm)                 # (coincident points: NaN curvature on both sides)
+    feat = oracle.features(xyz, nrm, R_FEAT, 5, 10, order=1)
+    assert same_bits(d.fetch("features", len(xyz), 50), feat)
+    sc = oracle.scores_from_sums(oracle.forest_sum(main_forest, feat), main_forest["ntrees"])
+    sc = np.where(np.isfinite(nrm[:, :3]).all(1), sc, np.nan).astype(np.float32)      # no finite normal: unscored (hpp:277)
+    assert same_bits(d.getResponse(), sc)
+    assert np.array_equal(idx, oracle.nms(xyz, sc, R_NMS, TH))
+    # an index subset that straddles the clusters (its own query list: 32 consecutive entries per warp, several groups)
+    sub = rng.choice(len(xyz), 700, replace=False).astype(np.int32)
+    d.setNormals(nrm)
+    assert same_bits(d.computePointsForTrainingFeatures(sub), feat[sub])
+    d.close()
+
+
 # ---------------------------------------------------------------------------------------------
 # full-size synthetic configuration: size-independent properties
 # ---------------------------------------------------------------------------------------------
