@@ -117,7 +117,7 @@ void kpl_destroy(kpl_ctx* ctx)
     release(ctx->key_a); release(ctx->key_b); release(ctx->idx_a); release(ctx->idx_b); release(ctx->cub_tmp);
     release(ctx->row_warps_n); release(ctx->row_offset_n); release(ctx->fragile); release(ctx->views); release(ctx->layer_view);
     release(ctx->view_offsets); release(ctx->qlist);
-    release(ctx->cell_start); release(ctx->work_n); release(ctx->ckey_a); release(ctx->ckey_b); release(ctx->qorder_a); release(ctx->qorder); release(ctx->warp_starts);
+    release(ctx->cell_start); release(ctx->work_n); release(ctx->ckey_a); release(ctx->ckey_b); release(ctx->qorder_a); release(ctx->qorder_all); release(ctx->warp_starts_n); release(ctx->qorder_role); release(ctx->warp_starts_role);
     release(ctx->warp_order); release(ctx->s_pos); release(ctx->s_nrm); release(ctx->feat);
     release(ctx->s_score); release(ctx->score); release(ctx->flag); release(ctx->s_state); release(ctx->kp_idx);
     release(ctx->scratch_f); release(ctx->scratch_i); release(ctx->counters);
@@ -355,8 +355,9 @@ static int prepare_lists(kpl_ctx* ctx, bool normals_given, bool want_features, b
 {
     const kpl_params& P = ctx->params;
     int span_n = -1;
+    bool curve_normals = false;
     if (!normals_given) {
-        if (P.normals_mode == KPL_NORMALS_KNN) span_n = normals_knn_uses_work_list(P) ? 1 : -1;
+        if (P.normals_mode == KPL_NORMALS_KNN) curve_normals = normals_knn_uses_work_list(P);
         else if (P.normals_mode == KPL_NORMALS_RADIUS) span_n = P.cells_per_radius;
     }
     // A launch of few waves (a slab of a multi-GPU job, a single view) ends with a long idle tail unless the expensive
@@ -364,7 +365,7 @@ static int prepare_lists(kpl_ctx* ctx, bool normals_given, bool want_features, b
     // that concurrently running warps keep sharing candidate rows (there the tail is a percent of the launch anyway).
     const int64_t slots = 148 * 28;
     const int64_t longest_first_below = ctx->last_n * 32 < (int64_t)120e6 ? 24 * slots : 0;
-    KPL_CUDA(build_lists(ctx, ctx->last_n, span_n, want_features, use_role, longest_first_below));
+    KPL_CUDA(build_lists(ctx, ctx->last_n, span_n, curve_normals, want_features, use_role, longest_first_below));
     return KPL_OK;
 }
 

@@ -726,7 +726,7 @@ cudaError_t launch_features(kpl_ctx* c, int64_t n, bool use_role, bool fuse_fore
     if (warps == 0) return cudaSuccess;
     int blocks = (warps + wpb - 1) / wpb;
     kern<<<blocks, wpb * 32, smem, c->stream>>>(c->s_pos.p, c->s_nrm.p, c->key_b.p, c->cell_start.p,
-                                                d_qlist ? d_qlist : c->qorder.p, d_qlist ? nullptr : c->warp_starts.p, warps, (int)m_list,
+                                                d_qlist ? d_qlist : c->qorder_f, d_qlist ? nullptr : c->warp_starts_f, warps, (int)m_list,
                                                 (!d_qlist && c->have_warp_order) ? c->warp_order.p : nullptr, d_qlist ? 1 : 0,
                                                 c->grid.dim[0], c->grid.dim[1], c->grid.dim[2], P, FF,
                                                 store_rows ? c->feat.p : nullptr, c->counters.p);

@@ -276,7 +276,8 @@ __global__ void __launch_bounds__(128) run_list_kernel(const int32_t* __restrict
 // slots used).  Where the curve jumps -- two consecutive queries more than one cell apart: it left the surface and
 // came back elsewhere -- the list is cut, so that a warp never holds two far-apart clusters (it would walk both
 // neighbourhoods one after the other with most lanes idle, and such long-running warps set the duration of a
-// single-wave launch).  Points without a scoring role are left out of the list.
+// single-wave launch).  Points without a scoring role are left out of the feature kernel's list; the cooperative k-NN
+// normal kernel works through the same order over ALL points (normals.cu).
 __device__ __forceinline__ uint64_t hilbert3(uint32_t x, uint32_t y, uint32_t z, int bits)
 {
     // J. Skilling, "Programming the Hilbert curve" (2004): axes -> transposed index, then interleave
@@ -301,46 +302,39 @@ __device__ __forceinline__ uint64_t hilbert3(uint32_t x, uint32_t y, uint32_t z,
     return h;
 }
 
-__global__ void __launch_bounds__(256) curve_key_kernel(const float4* __restrict__ s_pos, const uint32_t* __restrict__ skey,
-                                                        const uint8_t* __restrict__ s_role, int64_t n, GridDesc g, int sub, int shift, int bits,
-                                                        uint64_t* __restrict__ keys, int32_t* __restrict__ pos, unsigned long long* __restrict__ d_nq)
+__global__ void __launch_bounds__(256) curve_key_kernel(const float4* __restrict__ s_pos, const uint32_t* __restrict__ skey, int64_t n, GridDesc g,
+                                                        int sub, int shift, int bits,
+                                                        uint64_t* __restrict__ keys, int32_t* __restrict__ pos, unsigned long long* __restrict__ d_n)
 {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    bool query = false;
-    if (i < n) {
-        query = !s_role || (s_role[i] & 1);
-        uint64_t key = 1ull << (3 * bits);          // no scoring role: behind every query
-        if (query) {
-            const uint32_t k = __ldg(skey + i);
-            const uint32_t t = k / (uint32_t)g.dim[0];
-            int cc[3];
-            cc[0] = (int)(k - t * (uint32_t)g.dim[0]);
-            cc[2] = (int)(t / (uint32_t)g.dim[1]);
-            cc[1] = (int)(t - (uint32_t)cc[2] * (uint32_t)g.dim[1]);
-            double org[3] = {g.org[0], g.org[1], g.org[2]};
-            int zoff = 0;
-            if (g.views) {
-                const int v = __ldg(g.layer_view + cc[2]);
-                if (v >= 0) { const ViewDesc* V = g.views + v; org[0] = V->org[0]; org[1] = V->org[1]; org[2] = V->org[2]; zoff = V->zoff; }
-            }
-            const float4 p = __ldg(s_pos + i);
-            const float v3[3] = {p.x, p.y, p.z};
-            uint32_t f[3];
-#pragma unroll
-            for (int a = 0; a < 3; ++a) {
-                // position inside the cell in [0, 1): only the ORDER of the queries depends on it, never a result
-                const double fr = ((double)v3[a] - org[a]) / g.cell - (double)(cc[a] + g.off[a] - (a == 2 ? zoff : 0));
-                const int sc = min(max((int)(fr * (double)(1 << sub)), 0), (1 << sub) - 1);
-                f[a] = (((uint32_t)cc[a] << sub) | (uint32_t)sc) >> shift;
-            }
-            key = hilbert3(f[0], f[1], f[2], bits);
-        }
-        keys[i] = key;
-        pos[i] = (int32_t)i;
+    if (i == 0) *d_n = (unsigned long long)n;
+    if (i >= n) return;
+    const uint32_t k = __ldg(skey + i);
+    const uint32_t t = k / (uint32_t)g.dim[0];
+    int cc[3];
+    cc[0] = (int)(k - t * (uint32_t)g.dim[0]);
+    cc[2] = (int)(t / (uint32_t)g.dim[1]);
+    cc[1] = (int)(t - (uint32_t)cc[2] * (uint32_t)g.dim[1]);
+    double org[3] = {g.org[0], g.org[1], g.org[2]};
+    int zoff = 0;
+    if (g.views) {
+        const int v = __ldg(g.layer_view + cc[2]);
+        if (v >= 0) { const ViewDesc* V = g.views + v; org[0] = V->org[0]; org[1] = V->org[1]; org[2] = V->org[2]; zoff = V->zoff; }
     }
-    const unsigned m = __ballot_sync(0xFFFFFFFFu, query);
-    if (m && (threadIdx.x & 31) == 0) atomicAdd(d_nq, (unsigned long long)__popc(m));
+    const float4 p = __ldg(s_pos + i);
+    const float v3[3] = {p.x, p.y, p.z};
+    uint32_t f[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        // position inside the cell in [0, 1): only the ORDER of the queries depends on it, never a result
+        const double fr = ((double)v3[a] - org[a]) / g.cell - (double)(cc[a] + g.off[a] - (a == 2 ? zoff : 0));
+        const int sc = min(max((int)(fr * (double)(1 << sub)), 0), (1 << sub) - 1);
+        f[a] = (((uint32_t)cc[a] << sub) | (uint32_t)sc) >> shift;
+    }
+    keys[i] = hilbert3(f[0], f[1], f[2], bits);
+    pos[i] = (int32_t)i;
 }
+__global__ void widen_count_kernel(const int32_t* __restrict__ in, unsigned long long* __restrict__ out) { *out = (unsigned long long)*in; }
 
 // head[i] = i when entry i of the query order starts a segment (first entry, or more than one cell from its predecessor in
 // some axis), else 0: an inclusive max-scan turns it into the segment start of every entry
@@ -407,14 +401,46 @@ __global__ void __launch_bounds__(128) warp_cost_kernel(const int32_t* __restric
     order[w] = (uint32_t)w;
 }
 
-// Builds, for the grid in place, the work list of the normal kernels (span_n >= 0: c->work_n, c->nwarps_norm) and the
-// query order + warp list of the feature kernel (want_features: c->qorder, c->warp_starts with c->nwarps_feat + 1
-// entries) with ONE host synchronisation for the two list sizes.  With longest_first the feature warps additionally get a
-// launch order (c->warp_order), most expensive first: one warp of the feature kernel runs for milliseconds (32 queries x
-// thousands of neighbours), so a launch of only a few waves -- one slab of an 8-GPU job is ~9 -- idles ~half a warp-time
-// per SM slot at its end unless the cheap warps are the ones left for the tail.  Blocks retire independently, so the order
-// of the launch never changes a result.
-cudaError_t build_lists(kpl_ctx* c, int64_t n, int span_n, bool want_features, bool use_role, int64_t longest_first_below)
+// role flag of entry i of a query order
+__global__ void __launch_bounds__(256) role_flag_kernel(const int32_t* __restrict__ qorder, const uint8_t* __restrict__ s_role, int64_t n,
+                                                        uint8_t* __restrict__ flag)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) flag[i] = s_role[qorder[i]] & 1;
+}
+
+// Warp list of a query order of *d_nq entries (n = capacity): segments cut at the jumps of the curve, 32 entries per warp
+// inside a segment.  starts gets *d_nwarps + 1 entries.  seg (n ints) and flag (n bytes) are scratch.
+static cudaError_t make_warp_list(kpl_ctx* c, const int32_t* qorder, const unsigned long long* d_nq, int64_t n, int jump,
+                                  int32_t* seg, uint8_t* flag, int32_t* starts, int32_t* d_nwarps)
+{
+    const GridDesc& g = c->grid;
+    const unsigned pblocks = (unsigned)((n + 255) / 256);
+    cudaError_t e;
+    segment_head_kernel<<<pblocks, 256, 0, c->stream>>>(qorder, d_nq, n, c->key_b.p, g.dim[0], g.dim[1], jump, seg);
+    size_t tmp = c->cub_tmp.cap;
+    if ((e = cub::DeviceScan::InclusiveScan(c->cub_tmp.p, tmp, seg, seg, MaxOp(), (int)n, c->stream))) return e;
+    warp_start_kernel<<<pblocks, 256, 0, c->stream>>>(seg, d_nq, n, flag);
+    tmp = c->cub_tmp.cap;
+    if ((e = cub::DeviceSelect::Flagged(c->cub_tmp.p, tmp, thrust::counting_iterator<int32_t>(0), flag, starts, d_nwarps, (int)n, c->stream))) return e;
+    terminate_starts_kernel<<<1, 1, 0, c->stream>>>(starts, d_nwarps, d_nq);
+    c->launches += 5;
+    return cudaGetLastError();
+}
+
+// Builds, for the grid in place, the lists of the normal kernels and of the feature kernel with ONE host synchronisation
+// for their sizes:
+//   span_n >= 0        run list of the radius-normal kernel (c->work_n, c->nwarps_norm);
+//   curve_normals      Hilbert order of ALL points + warp list for the cooperative k-NN kernel (c->qorder_all,
+//                      c->warp_starts_n, c->nwarps_norm);
+//   want_features      query order + warp list of the feature kernel (c->qorder_f / c->warp_starts_f, c->nwarps_feat): the
+//                      points with a scoring role, in the same Hilbert order (without roles it IS the list of all points).
+// The feature warps additionally get a launch order (c->warp_order), most expensive first, when their number is below
+// longest_first_below: one warp of the feature kernel runs for milliseconds (32 queries x thousands of neighbours), so a
+// launch of only a few waves -- one slab of an 8-GPU job is ~9 -- idles ~half a warp-time per SM slot at its end unless the
+// cheap warps are the ones left for the tail.  Blocks retire independently, so the order of the launch never changes a
+// result.
+cudaError_t build_lists(kpl_ctx* c, int64_t n, int span_n, bool curve_normals, bool want_features, bool use_role, int64_t longest_first_below)
 {
     const GridDesc& g = c->grid;
     const int64_t nrows = (int64_t)g.dim[1] * g.dim[2];
@@ -423,21 +449,25 @@ cudaError_t build_lists(kpl_ctx* c, int64_t n, int span_n, bool want_features, b
     cudaError_t e;
     c->nwarps_norm = c->nwarps_feat = 0;
     c->have_warp_order = false;
+    c->qorder_f = nullptr; c->warp_starts_f = nullptr;
     if (n <= 0) return cudaSuccess;
-    int32_t total_n = 0, total_f = 0;
+    const bool curve = curve_normals || want_features;
+    int32_t total_n = 0, total_f = 0, total_c = 0;
     size_t bytes = 0, need = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, bytes, (int32_t*)nullptr, (int32_t*)nullptr, (int)nrows + 1, c->stream);
     need = bytes;
-    if (want_features) {
+    if (curve) {
         cub::DeviceRadixSort::SortPairs(nullptr, bytes, (uint64_t*)nullptr, (uint64_t*)nullptr, (int32_t*)nullptr, (int32_t*)nullptr, (int)n, 0, 64, c->stream);
         need = std::max(need, bytes);
         cub::DeviceScan::InclusiveScan(nullptr, bytes, (int32_t*)nullptr, (int32_t*)nullptr, MaxOp(), (int)n, c->stream);
         need = std::max(need, bytes);
         cub::DeviceSelect::Flagged(nullptr, bytes, thrust::counting_iterator<int32_t>(0), (uint8_t*)nullptr, (int32_t*)nullptr, (int32_t*)nullptr, (int)n, c->stream);
         need = std::max(need, bytes);
+        cub::DeviceSelect::Flagged(nullptr, bytes, (int32_t*)nullptr, (uint8_t*)nullptr, (int32_t*)nullptr, (int32_t*)nullptr, (int)n, c->stream);
+        need = std::max(need, bytes);
     }
     if ((e = ensure(c->cub_tmp, need))) return e;
-    // ---- sizes of both lists
+    // ---- sizes
     if (span_n >= 0) {
         if ((e = ensure(c->row_warps_n, (size_t)nrows + 1)) || (e = ensure(c->row_offset_n, (size_t)nrows + 1))) return e;
         run_list_kernel<false><<<rblocks, 128, 0, c->stream>>>(c->cell_start.p, g.dim[0], nrows, span_n, c->row_warps_n.p, nullptr, nullptr);
@@ -447,11 +477,14 @@ cudaError_t build_lists(kpl_ctx* c, int64_t n, int span_n, bool want_features, b
         if ((e = cudaMemcpyAsync(&total_n, c->row_offset_n.p + nrows, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream))) return e;
         c->launches += 3;
     }
-    unsigned long long* d_nq = c->counters.p + 11;
-    int32_t* d_nwarps = reinterpret_cast<int32_t*>(c->counters.p + 12);
-    if (want_features) {
+    // counters: [11] all points [12] warps of the all-points list [13] queries with a scoring role [14] their warps
+    unsigned long long* d_nall = c->counters.p + 11;
+    int32_t* d_nwarps_all = reinterpret_cast<int32_t*>(c->counters.p + 12);
+    unsigned long long* d_nq = c->counters.p + 13;
+    int32_t* d_nwarps_q = reinterpret_cast<int32_t*>(c->counters.p + 14);
+    if (curve) {
         if ((e = ensure(c->ckey_a, (size_t)n)) || (e = ensure(c->ckey_b, (size_t)n)) || (e = ensure(c->qorder_a, (size_t)n)) ||
-            (e = ensure(c->qorder, (size_t)n)) || (e = ensure(c->warp_starts, (size_t)n + 2)))
+            (e = ensure(c->qorder_all, (size_t)n)) || (e = ensure(c->warp_starts_n, (size_t)n + 2)))
             return e;
         // lattice: 2^sub sub-cells per cell and axis while the largest axis fits 21 bits (3 x 21 = 63-bit curve index);
         // grids beyond 2^21 cells along one axis drop low bits instead
@@ -465,41 +498,51 @@ cudaError_t build_lists(kpl_ctx* c, int64_t n, int span_n, bool want_features, b
         while ((((int64_t)maxdim << sub) >> shift) > (1ll << 21)) ++shift;
         int bits = 1;
         while ((1ll << bits) < (((int64_t)maxdim << sub) >> shift) + 1) ++bits;
-        if ((e = cudaMemsetAsync(d_nq, 0, 2 * sizeof(unsigned long long), c->stream))) return e;
-        curve_key_kernel<<<pblocks, 256, 0, c->stream>>>(c->s_pos.p, c->key_b.p, use_role ? c->s_role.p : nullptr, n, g, sub, shift, bits,
-                                                         c->ckey_a.p, c->qorder_a.p, d_nq);
-        const int end_bit = 3 * bits + (use_role ? 1 : 0);      // points without a scoring role carry the bit above the curve index
+        if ((e = cudaMemsetAsync(d_nall, 0, 4 * sizeof(unsigned long long), c->stream))) return e;
+        curve_key_kernel<<<pblocks, 256, 0, c->stream>>>(c->s_pos.p, c->key_b.p, n, g, sub, shift, bits, c->ckey_a.p, c->qorder_a.p, d_nall);
+        const int end_bit = 3 * bits;
         size_t tmp = c->cub_tmp.cap;
-        if ((e = cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tmp, c->ckey_a.p, c->ckey_b.p, c->qorder_a.p, c->qorder.p, (int)n, 0, end_bit, c->stream)))
+        if ((e = cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tmp, c->ckey_a.p, c->ckey_b.p, c->qorder_a.p, c->qorder_all.p, (int)n, 0, end_bit, c->stream)))
             return e;
-        // warp list: cut at the jumps of the curve, 32 entries per warp inside a segment (the sort buffers are free now)
+        c->launches += 2 + (end_bit + 7) / 8;
+        // (the sort buffers are free now: scratch of the warp lists)
         int32_t* seg = c->qorder_a.p;
         uint8_t* flag = reinterpret_cast<uint8_t*>(c->ckey_a.p);
-        segment_head_kernel<<<pblocks, 256, 0, c->stream>>>(c->qorder.p, d_nq, n, c->key_b.p, g.dim[0], g.dim[1], jump, seg);
-        tmp = c->cub_tmp.cap;
-        if ((e = cub::DeviceScan::InclusiveScan(c->cub_tmp.p, tmp, seg, seg, MaxOp(), (int)n, c->stream))) return e;
-        warp_start_kernel<<<pblocks, 256, 0, c->stream>>>(seg, d_nq, n, flag);
-        tmp = c->cub_tmp.cap;
-        if ((e = cub::DeviceSelect::Flagged(c->cub_tmp.p, tmp, thrust::counting_iterator<int32_t>(0), flag, c->warp_starts.p, d_nwarps, (int)n, c->stream)))
-            return e;
-        terminate_starts_kernel<<<1, 1, 0, c->stream>>>(c->warp_starts.p, d_nwarps, d_nq);
-        if ((e = cudaMemcpyAsync(&total_f, d_nwarps, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream))) return e;
-        c->launches += 7 + (end_bit + 7) / 8;
+        if (curve_normals || !use_role) {
+            if ((e = make_warp_list(c, c->qorder_all.p, d_nall, n, jump, seg, flag, c->warp_starts_n.p, d_nwarps_all))) return e;
+            if ((e = cudaMemcpyAsync(&total_c, d_nwarps_all, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream))) return e;
+        }
+        if (want_features && use_role) {
+            // the queries with a scoring role, in the same order
+            if ((e = ensure(c->qorder_role, (size_t)n)) || (e = ensure(c->warp_starts_role, (size_t)n + 2))) return e;
+            role_flag_kernel<<<pblocks, 256, 0, c->stream>>>(c->qorder_all.p, c->s_role.p, n, flag);
+            int32_t* d_sel = reinterpret_cast<int32_t*>(c->counters.p + 15);
+            tmp = c->cub_tmp.cap;
+            if ((e = cub::DeviceSelect::Flagged(c->cub_tmp.p, tmp, c->qorder_all.p, flag, c->qorder_role.p, d_sel, (int)n, c->stream))) return e;
+            widen_count_kernel<<<1, 1, 0, c->stream>>>(d_sel, d_nq);
+            c->launches += 3;
+            if ((e = make_warp_list(c, c->qorder_role.p, d_nq, n, jump, seg, flag, c->warp_starts_role.p, d_nwarps_q))) return e;
+            if ((e = cudaMemcpyAsync(&total_f, d_nwarps_q, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream))) return e;
+        }
     }
-    if (span_n >= 0 || want_features) {
+    if (span_n >= 0 || curve) {
         if ((e = cudaStreamSynchronize(c->stream))) return e;
         c->syncs++;
     }
-    // ---- the lists themselves
+    // ---- the run list itself
     if (span_n >= 0 && total_n > 0) {
         if ((e = ensure(c->work_n, (size_t)total_n + 1))) return e;
         run_list_kernel<true><<<rblocks, 128, 0, c->stream>>>(c->cell_start.p, g.dim[0], nrows, span_n, nullptr, c->row_offset_n.p, c->work_n.p);
         c->nwarps_norm = total_n;
         c->launches++;
     }
-    c->nwarps_feat = total_f;
-    if (want_features && total_f > 1 && total_f < longest_first_below) {
-        const int nwarps = total_f;
+    if (curve_normals) c->nwarps_norm = total_c;
+    if (want_features) {
+        if (use_role) { c->qorder_f = c->qorder_role.p; c->warp_starts_f = c->warp_starts_role.p; c->nwarps_feat = total_f; }
+        else { c->qorder_f = c->qorder_all.p; c->warp_starts_f = c->warp_starts_n.p; c->nwarps_feat = total_c; }
+    }
+    if (want_features && c->nwarps_feat > 1 && c->nwarps_feat < longest_first_below) {
+        const int nwarps = c->nwarps_feat;
         if ((e = ensure(c->scratch_i, 3 * (size_t)nwarps + 16)) || (e = ensure(c->warp_order, (size_t)nwarps + 1))) return e;
         uint32_t* cost_a = (uint32_t*)c->scratch_i.p;
         uint32_t* cost_b = cost_a + nwarps;
@@ -508,7 +551,7 @@ cudaError_t build_lists(kpl_ctx* c, int64_t n, int span_n, bool want_features, b
         cub::DeviceRadixSort::SortPairsDescending(nullptr, bytes, cost_a, cost_b, ord_a, c->warp_order.p, nwarps, 0, 32, c->stream);
         if ((e = ensure(c->cub_tmp, bytes))) return e;
         const double r = (double)c->params.radius_features;
-        warp_cost_kernel<<<(nwarps + 127) / 128, 128, 0, c->stream>>>(c->qorder.p, c->warp_starts.p, nwarps, c->key_b.p, c->cell_start.p, g.dim[0], g.dim[1],
+        warp_cost_kernel<<<(nwarps + 127) / 128, 128, 0, c->stream>>>(c->qorder_f, c->warp_starts_f, nwarps, c->key_b.p, c->cell_start.p, g.dim[0], g.dim[1],
                                                                        g.dim[2], g.reach_feat, (float)g.cell, (float)(r * r * (1.0 + 1e-5)), cost_a, ord_a);
         bytes = c->cub_tmp.cap;
         if ((e = cub::DeviceRadixSort::SortPairsDescending(c->cub_tmp.p, bytes, cost_a, cost_b, ord_a, c->warp_order.p, nwarps, 0, 32, c->stream))) return e;

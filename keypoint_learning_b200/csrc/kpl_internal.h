@@ -96,9 +96,12 @@ struct kpl_ctx {
     int nwarps_norm = 0, nwarps_feat = 0;         // sizes of work_n / warp_starts for the grid in place
     kpl::DevBuf<int2> work_n;                     // (first sorted position, count <= 32) per warp of the normal kernels
     // feature kernel: queries (sorted positions) in Hilbert order of a sub-cell lattice, 32 consecutive ones per warp
-    // (grid.cu: build_lists); warp w takes entries [warp_starts[w], warp_starts[w + 1]) of qorder
+    // (grid.cu: build_lists); warp w takes entries [warp_starts[w], warp_starts[w + 1]) of the order.  _all / _n: every
+    // point (cooperative k-NN normals; the feature kernel too when no roles are given), _role: the points with a scoring role
     kpl::DevBuf<uint64_t> ckey_a, ckey_b;
-    kpl::DevBuf<int32_t> qorder_a, qorder, warp_starts;
+    kpl::DevBuf<int32_t> qorder_a, qorder_all, warp_starts_n, qorder_role, warp_starts_role;
+    const int32_t* qorder_f = nullptr;            // the feature kernel's list for the grid in place (one of the above)
+    const int32_t* warp_starts_f = nullptr;
     kpl::DevBuf<uint32_t> warp_order;             // launch order of the warps, most expensive first (few-wave launches)
     bool have_warp_order = false;
     kpl::DevBuf<float4> s_pos, s_nrm;            // cell-sorted positions (w = original index bits) / normals
@@ -115,8 +118,7 @@ struct kpl_ctx {
     kpl::DevBuf<float> scratch_f;                // fetch / reorder scratch
     kpl::DevBuf<int32_t> scratch_i;
     // [0] feature pairs [1] candidate pairs [2] above th [3] n_kp [4] unscored [5] scored [6] scratch [7] near threshold
-    // [8] fragile points [9] clipped k-NN searches (slab edge) [10] scratch [11] queries of the feature kernel [12] its warps
-    // [13..15] scratch
+    // [8] fragile points [9] clipped k-NN searches (slab edge) [10] scratch [11..15] sizes of the query lists (grid.cu: build_lists)
     kpl::DevBuf<unsigned long long> counters;
     static constexpr int NCOUNTERS = 16;
     int syncs = 0;                               // cudaStreamSynchronize calls of the call in flight
@@ -144,7 +146,7 @@ bool normals_knn_uses_work_list(const kpl_params& P);
 cudaError_t launch_bbox_init(kpl_ctx* c);
 cudaError_t launch_gather_keypoints(kpl_ctx* c, const float4* d_xyz, const int32_t* d_kp_idx, int64_t nkp, float4* d_out);
 cudaError_t launch_normals_integral_image(kpl_ctx* c, const float4* d_xyz, int W, int H, float smoothing_size, float4* d_out);
-cudaError_t build_lists(kpl_ctx* c, int64_t n, int span_n, bool want_features, bool use_role, int64_t longest_first_below);
+cudaError_t build_lists(kpl_ctx* c, int64_t n, int span_n, bool curve_normals, bool want_features, bool use_role, int64_t longest_first_below);
 cudaError_t launch_count_occupied_cells(kpl_ctx* c, int64_t n, unsigned long long* d_out);
 cudaError_t build_query_list(kpl_ctx* c, int64_t n, const int32_t* d_indices, int64_t m);
 cudaError_t launch_scatter_rows(kpl_ctx* c, const float* d_rows, int64_t m, int width, float* d_out);

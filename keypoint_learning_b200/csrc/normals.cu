@@ -228,112 +228,159 @@ __device__ __forceinline__ void knn_insert(uint32_t (&hi)[K], uint32_t (&lo)[K],
 
 // Warp-cooperative form of the k = 10 search (the TestDetector setting).  The per-thread kernel above spends
 // most of its issue slots on idle lanes (ncu: 7.75 of 32 threads active per instruction) because every
-// lane walks its own cell ranges.  Here a warp owns 32 consecutive sorted points; lanes that share a cell
-// row and lie within one cell of each other in x form a group whose 3 x 3 candidate rows are staged
-// 32 candidates at a time in shared memory.  A packed-FP32 pass marks the candidates that can still enter
-// a lane's list (d2 <= its current k-th best); only those are inserted, in the exact (d2, index) order.
-// Rows that no member lane can still use are skipped warp-uniformly.  Lanes whose k-th best is not provably
-// inside their 3 x 3 x 3 block (sparse regions) fall back to the growing-ring scan of the per-thread kernel.
+// lane walks its own cell ranges.  Here a warp owns 32 consecutive points of the Hilbert order of all points
+// (grid.cu: build_lists -- a compact patch of the surface, a few millimetres across where the cells are 5 mm);
+// the lanes within a cell of each other form a group whose candidate rows -- the cell rows of the group plus
+// one on every side -- are staged 32 candidates at a time in shared memory.  A packed-FP32 pass marks the
+// candidates that can still enter a lane's list (d2 <= its current k-th best); only those are inserted, in the
+// exact (d2, index) order.  Rows, and the cells at the two ends of a row, that no member lane can still use are
+// skipped warp-uniformly: the k-th best of a lane only shrinks, so what is skipped could never have entered its
+// list.  Lanes whose k-th best is not provably inside their 3 x 3 x 3 block (sparse regions) fall back to the
+// growing-ring scan of the per-thread kernel.
 template <int K>
 __global__ void __launch_bounds__(32) normals_knn_coop_kernel(const float4* __restrict__ s_pos, const uint32_t* __restrict__ skey,
                                                               const int32_t* __restrict__ cell_start, const float4* __restrict__ xyz,
-                                                              GridDesc g, const int2* __restrict__ work, uint64_t one2,
-                                                              float vpx, float vpy, float vpz, float4* __restrict__ s_nrm,
+                                                              GridDesc g, const int32_t* __restrict__ qorder, const int32_t* __restrict__ warp_starts,
+                                                              uint64_t one2, float vpx, float vpy, float vpz, float4* __restrict__ s_nrm,
                                                               unsigned long long* __restrict__ counters)
 {
     __shared__ __align__(16) float tile[128];
     float* sx = tile; float* sy = tile + 32; float* sz = tile + 64;
     uint32_t* si = reinterpret_cast<uint32_t*>(tile + 96);
     const int lane = threadIdx.x;
-    const int2 item = __ldg(work + blockIdx.x);              // up to 32 consecutive sorted points of one run (grid.cu)
-    const int q = item.x + lane;
-    const bool active = lane < item.y;
+    const int q0 = __ldg(warp_starts + blockIdx.x);           // entries [q0, q0 + count) of the order, count <= 32
+    const bool active = lane < __ldg(warp_starts + blockIdx.x + 1) - q0;
+    const int q = active ? __ldg(qorder + q0 + lane) : 0;
     float4 p = make_float4(CUDART_NAN_F, 0.f, 0.f, 0.f);
     int cx = 0, cy = 0, cz = 0;
     if (active) { p = __ldg(s_pos + q); key_to_cell(__ldg(skey + q), g, cx, cy, cz); }
-    // every point of a work item lies in ONE cell row, hence in one view: lane 0 is always valid
-    const LocalGrid LG = local_grid(g, __shfl_sync(0xFFFFFFFFu, cz, 0));
     uint32_t bd2[K];          // bit patterns of the k smallest squared distances, ascending by (d2, index)
     uint32_t bi[K];
-#pragma unroll
-    for (int t = 0; t < K; ++t) { bd2[t] = 0x7F800000u; bi[t] = 0xFFFFFFFFu; }   // +inf, no index
     const uint64_t QY = pack2(p.y, p.y), QZ = pack2(p.z, p.z);
+    // First attempt with a BOUNDED list: most of the kernel's time went into list insertions (ncu: 65 % of the
+    // instructions) because a list that starts at +inf takes the first 32 candidates whole and ~50 more while it
+    // converges.  The lane's own cell tells the local density: with n_c points in a cell the surface crosses, a ball of
+    // r0^2 = 30 cell^2 / (pi n_c) holds ~30 of them.  The list starts full of sentinels (r0^2, no index), so only
+    // candidates inside that ball are ever inserted; if fewer than K turn up, the lane repeats the search unbounded.
+    // Either way the list ends as the K smallest (d2, index) of everything scanned.
+    float r0sq = CUDART_INF_F;
+    if (active) {
+        const int64_t cell = ((int64_t)cz * g.dim[1] + cy) * g.dim[0] + cx;
+        const int nc = __ldg(cell_start + cell + 1) - __ldg(cell_start + cell);
+        const float guess = 9.55f * (float)g.cell * (float)g.cell / (float)max(nc, 1);
+        if (nc >= 8 && guess < 0.9f * (float)g.cell * (float)g.cell) r0sq = guess;     // else: unbounded from the start
+    }
+#pragma unroll
+    for (int t = 0; t < K; ++t) { bd2[t] = __float_as_uint(r0sq); bi[t] = 0xFFFFFFFFu; }   // bound (or +inf), no index
 
-    // squared lower bounds on the distance to the neighbouring cell layer on the low / high side of y and z
+    // lower bounds on the distance to the faces of the lane's own cell on the low / high side of every axis
     // (shrunk by 1e-5: rounding in the cell assignment or in d2 can never hide a candidate)
-    float lo2[3], hi2[3];
+    float lo1[3], hi1[3];
+    const float cellf = (float)g.cell * 0.99999f;
     {
+        // every lane of a warp lies in ONE view of a batch (the list is cut where the curve jumps, and views are layers apart)
+        const LocalGrid LGq = local_grid(g, cz);
         const float v[3] = {p.x, p.y, p.z};
         const int cc[3] = {cx, cy, cz};
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
-            const double f = cell_fraction(g, LG, a, v[a], cc[a]);   // in [0, 1)
-            const float dl = fmaxf((float)(f * g.cell) * 0.99999f - 1e-30f, 0.0f);
-            const float dh = fmaxf((float)((1.0 - f) * g.cell) * 0.99999f - 1e-30f, 0.0f);
-            lo2[a] = active ? dl * dl * 0.99999f : CUDART_INF_F; hi2[a] = active ? dh * dh * 0.99999f : CUDART_INF_F;
+            const double f = cell_fraction(g, LGq, a, v[a], cc[a]);   // in [0, 1)
+            lo1[a] = active ? fmaxf((float)(f * g.cell) * 0.99999f - 1e-30f, 0.0f) : CUDART_INF_F;
+            hi1[a] = active ? fmaxf((float)((1.0 - f) * g.cell) * 0.99999f - 1e-30f, 0.0f) : CUDART_INF_F;
         }
     }
+    // squared lower bound on the distance between this lane's point and the cells at offset d (in cells) along axis a
+    auto gap_sq = [&](int a, int d) -> float {
+        if (d == 0) return 0.0f;
+        const float t = (d < 0 ? lo1[a] : hi1[a]) + (float)(abs(d) - 1) * cellf;
+        return t * t * 0.99999f;
+    };
 
-    unsigned remaining = __ballot_sync(0xFFFFFFFFu, active);
+    bool searching = active;          // lanes taking part in the current attempt
+#pragma unroll 1
+    for (int attempt = 0; attempt < 2; ++attempt) {
+    unsigned remaining = __ballot_sync(0xFFFFFFFFu, searching);
     while (remaining) {
+        // a group: the lanes within one cell of the first remaining lane whose cells span at most two per axis
         const int leader = __ffs(remaining) - 1;
-        const int minx = __shfl_sync(0xFFFFFFFFu, cx, leader);
-        const int gy0 = __shfl_sync(0xFFFFFFFFu, cy, leader), gz0 = __shfl_sync(0xFFFFFFFFu, cz, leader);
-        const bool member = active && ((remaining >> lane) & 1u) && cy == gy0 && cz == gz0 && (unsigned)(cx - minx) <= 1u;
+        const int lx = __shfl_sync(0xFFFFFFFFu, cx, leader), ly = __shfl_sync(0xFFFFFFFFu, cy, leader), lz = __shfl_sync(0xFFFFFFFFu, cz, leader);
+        const bool near = searching && ((remaining >> lane) & 1u) && (unsigned)(cx - lx + 1) <= 2u && (unsigned)(cy - ly + 1) <= 2u &&
+                          (unsigned)(cz - lz + 1) <= 2u;
+        const int gx0 = __reduce_min_sync(0xFFFFFFFFu, near ? cx : lx), gy0 = __reduce_min_sync(0xFFFFFFFFu, near ? cy : ly);
+        const int gz0 = __reduce_min_sync(0xFFFFFFFFu, near ? cz : lz);
+        const bool member = near && cx - gx0 <= 1 && cy - gy0 <= 1 && cz - gz0 <= 1;
         remaining &= ~__ballot_sync(0xFFFFFFFFu, member);
-        const int maxx = __reduce_max_sync(0xFFFFFFFFu, member ? cx : minx);
+        const int gy1 = __reduce_max_sync(0xFFFFFFFFu, member ? cy : ly), gz1 = __reduce_max_sync(0xFFFFFFFFu, member ? cz : lz);
+        const LocalGrid LG = local_grid(g, lz);
         const float px = member ? p.x : CUDART_NAN_F;
         const uint64_t QX = pack2(px, px);
-        const int xa = max(minx - 1, 0), xb = min(maxx + 1, g.dim[0] - 1);
-        // centre row first (it tightens every lane's k-th best), then the eight others
+        const int ny = gy1 - gy0 + 3, nrows = ny * (gz1 - gz0 + 3);
+        // the group's own rows first (they tighten every lane's k-th best), then the rows around them
 #pragma unroll 1
-        for (int r = 0; r < 9; ++r) {
-            const int o = (r == 0) ? 4 : (r <= 4 ? r - 1 : r);       // 4, 0, 1, 2, 3, 5, 6, 7, 8
-            const int dy = o % 3 - 1, dz = o / 3 - 1;
-            const int y = gy0 + dy, z = gz0 + dz;
-            if (y < 0 || y >= g.dim[1] || z < LG.zlo || z > LG.zhi) continue;
-            const float gap2 = (dy < 0 ? lo2[1] : (dy > 0 ? hi2[1] : 0.0f)) + (dz < 0 ? lo2[2] : (dz > 0 ? hi2[2] : 0.0f));
-            if (!__any_sync(0xFFFFFFFFu, member && gap2 <= __uint_as_float(bd2[K - 1]))) continue;     // no member can use this row
-            const int64_t base = ((int64_t)z * g.dim[1] + y) * g.dim[0];
-            const int rs = __ldg(cell_start + base + xa), re = __ldg(cell_start + base + xb + 1);
-            for (int tb = rs; tb < re; tb += 32) {
-                float4 c = make_float4(CUDART_NAN_F, 0.f, 0.f, 0.f);
-                if (tb + lane < re) c = __ldg(s_pos + tb + lane);
-                __syncwarp();
-                sx[lane] = c.x; sy[lane] = c.y; sz[lane] = c.z; si[lane] = __float_as_uint(c.w);
-                __syncwarp();
-                const int cnt = min(32, re - tb);
-                const float worst = __uint_as_float(bd2[K - 1]);
-                uint32_t mask = 0;
+        for (int pass = 0; pass < 2; ++pass) {
+#pragma unroll 1
+            for (int r = 0; r < nrows; ++r) {
+                const int y = gy0 - 1 + r % ny, z = gz0 - 1 + r / ny;
+                const bool own = y >= gy0 && y <= gy1 && z >= gz0 && z <= gz1;
+                if (own != (pass == 0)) continue;
+                if (y < 0 || y >= g.dim[1] || z < LG.zlo || z > LG.zhi) continue;
+                const float worst0 = __uint_as_float(bd2[K - 1]);
+                const float gap2 = gap_sq(1, y - cy) + gap_sq(2, z - cz);
+                const bool use_row = member && gap2 <= worst0;
+                if (!__any_sync(0xFFFFFFFFu, use_row)) continue;                           // no member can use this row
+                // cells of the row some member can still use: its own, and the one on either side if close enough
+                const int xa = max(__reduce_min_sync(0xFFFFFFFFu, use_row ? cx - ((gap2 + gap_sq(0, -1) <= worst0) ? 1 : 0) : 0x7FFFFFFF), 0);
+                const int xb = min(__reduce_max_sync(0xFFFFFFFFu, use_row ? cx + ((gap2 + gap_sq(0, 1) <= worst0) ? 1 : 0) : -1), g.dim[0] - 1);
+                const int64_t base = ((int64_t)z * g.dim[1] + y) * g.dim[0];
+                const int rs = __ldg(cell_start + base + xa), re = __ldg(cell_start + base + xb + 1);
+                for (int tb = rs; tb < re; tb += 32) {
+                    float4 c = make_float4(CUDART_NAN_F, 0.f, 0.f, 0.f);
+                    if (tb + lane < re) c = __ldg(s_pos + tb + lane);
+                    __syncwarp();
+                    sx[lane] = c.x; sy[lane] = c.y; sz[lane] = c.z; si[lane] = __float_as_uint(c.w);
+                    __syncwarp();
+                    const int cnt = min(32, re - tb);
+                    const float worst = __uint_as_float(bd2[K - 1]);
+                    uint32_t mask = 0;
 #pragma unroll
-                for (int k0 = 0; k0 < 32; k0 += 8) {
-                    if (k0 < cnt) {
+                    for (int k0 = 0; k0 < 32; k0 += 8) {
+                        if (k0 < cnt) {
 #pragma unroll
-                        for (int u = 0; u < 8; u += 4) {
-                            const ulonglong2 X = *reinterpret_cast<const ulonglong2*>(sx + k0 + u);
-                            const ulonglong2 Y = *reinterpret_cast<const ulonglong2*>(sy + k0 + u);
-                            const ulonglong2 Z = *reinterpret_cast<const ulonglong2*>(sz + k0 + u);
-                            float d0, d1, d2, d3;
-                            unpack2(dist2_x2(QX, QY, QZ, X.x, Y.x, Z.x, one2), d0, d1);
-                            unpack2(dist2_x2(QX, QY, QZ, X.y, Y.y, Z.y, one2), d2, d3);
-                            if (d0 <= worst) mask |= 0x80000000u >> (k0 + u);
-                            if (d1 <= worst) mask |= 0x80000000u >> (k0 + u + 1);
-                            if (d2 <= worst) mask |= 0x80000000u >> (k0 + u + 2);
-                            if (d3 <= worst) mask |= 0x80000000u >> (k0 + u + 3);
+                            for (int u = 0; u < 8; u += 4) {
+                                const ulonglong2 X = *reinterpret_cast<const ulonglong2*>(sx + k0 + u);
+                                const ulonglong2 Y = *reinterpret_cast<const ulonglong2*>(sy + k0 + u);
+                                const ulonglong2 Z = *reinterpret_cast<const ulonglong2*>(sz + k0 + u);
+                                float d0, d1, d2, d3;
+                                unpack2(dist2_x2(QX, QY, QZ, X.x, Y.x, Z.x, one2), d0, d1);
+                                unpack2(dist2_x2(QX, QY, QZ, X.y, Y.y, Z.y, one2), d2, d3);
+                                if (d0 <= worst) mask |= 0x80000000u >> (k0 + u);
+                                if (d1 <= worst) mask |= 0x80000000u >> (k0 + u + 1);
+                                if (d2 <= worst) mask |= 0x80000000u >> (k0 + u + 2);
+                                if (d3 <= worst) mask |= 0x80000000u >> (k0 + u + 3);
+                            }
                         }
                     }
-                }
-                while (mask) {
-                    const int m = 31 - __clz(mask);
-                    mask ^= 1u << m;
-                    const int k = 31 - m;
-                    const float d2 = dist2(p.x, p.y, p.z, sx[k], sy[k], sz[k]);
-                    knn_insert<K>(bd2, bi, __float_as_uint(d2), si[k]);
+                    while (mask) {
+                        const int m = 31 - __clz(mask);
+                        mask ^= 1u << m;
+                        const int k = 31 - m;
+                        const float d2 = dist2(p.x, p.y, p.z, sx[k], sy[k], sz[k]);
+                        knn_insert<K>(bd2, bi, __float_as_uint(d2), si[k]);
+                    }
                 }
             }
         }
     }
+    // second attempt, unbounded, for the lanes whose ball held fewer than K points
+    searching = active && attempt == 0 && bi[K - 1] == 0xFFFFFFFFu && bd2[K - 1] != 0x7F800000u;
+    if (!__any_sync(0xFFFFFFFFu, searching)) break;
+    if (searching) {
+#pragma unroll
+        for (int t = 0; t < K; ++t) { bd2[t] = 0x7F800000u; bi[t] = 0xFFFFFFFFu; }
+    }
+    }
     if (!active) return;
+    const LocalGrid LG = local_grid(g, cz);
     // exactness guard of the 3 x 3 x 3 block; growing rings (per lane, rescanning) where it does not hold
     {
         const bool all1 = (cz - 1 <= LG.zlo && cy - 1 <= 0 && cx - 1 <= 0 && cz + 1 >= LG.zhi && cy + 1 >= g.dim[1] - 1 && cx + 1 >= g.dim[0] - 1);
@@ -399,8 +446,8 @@ bool normals_knn_uses_work_list(const kpl_params& P)
     return coop;
 }
 
-// The work list of the warp-cooperative kernel (runs of at most two cells: one group per warp) is built by the
-// caller together with the feature kernel's (build_work_lists, one host synchronisation for both).
+// The query order and warp list of the warp-cooperative kernel are built by the caller together with the feature
+// kernel's (grid.cu: build_lists, one host synchronisation for both).
 cudaError_t launch_normals_knn(kpl_ctx* c, int64_t n)
 {
     const kpl_params& P = c->params;
@@ -408,7 +455,8 @@ cudaError_t launch_normals_knn(kpl_ctx* c, int64_t n)
     const float4* xyz = c->cur_xyz;
     if (normals_knn_uses_work_list(P)) {
         if (c->nwarps_norm > 0)
-            normals_knn_coop_kernel<10><<<(unsigned)c->nwarps_norm, 32, 0, c->stream>>>(c->s_pos.p, c->key_b.p, c->cell_start.p, xyz, c->grid, c->work_n.p,
+            normals_knn_coop_kernel<10><<<(unsigned)c->nwarps_norm, 32, 0, c->stream>>>(c->s_pos.p, c->key_b.p, c->cell_start.p, xyz, c->grid,
+                                                                                        c->qorder_all.p, c->warp_starts_n.p,
                                                                                         0x3F8000003F800000ull, P.viewpoint[0], P.viewpoint[1],
                                                                                         P.viewpoint[2], c->s_nrm.p, c->counters.p);
     }
