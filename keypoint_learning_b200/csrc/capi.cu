@@ -518,7 +518,7 @@ static int run_detect(kpl_ctx* ctx, const float4* d_xyz, const float4* d_nrm, co
     return detect_finish(ctx, n, n_kp_out);
 }
 
-// A batch of independent views in ONE pass: one stacked grid, one work list, one launch per stage, per-view
+// A batch of independent views in ONE pass: one stacked grid, one query order, one launch per stage, per-view
 // keypoint ranges -- a 200 k-point view alone is 1.5 waves of the feature kernel and a handful of host round trips.
 static int run_detect_batch(kpl_ctx* ctx, const float4* d_xyz, const float4* d_nrm, int64_t n, const int64_t* h_offsets, int nviews,
                             float* d_scores_out, int32_t* d_kp_out, int64_t* d_kp_offsets_out, int64_t* n_kp_out)
