@@ -3,7 +3,7 @@
 // its helpers findAnnulusPair / findBinPair (src/KeypointLearning.cpp:41-92) and the FLANN radius
 // search behind searchForNeighbors (hpp:334).
 //
-// Mapping: one warp (= one block) owns 32 consecutive queries of the query order (grid.cu: build_query_order, a
+// Mapping: one warp (= one block) owns 32 consecutive queries of the query order (grid.cu: build_lists, a
 // Hilbert curve over sub-cells, so the 32 queries are a compact patch of the surface), one lane per query, and
 // the warp's queries share a tight candidate box.  The warp walks the cell rows that can hold neighbours
 // of any of its queries; each row is ONE contiguous range of the sorted arrays, staged 32 candidates at a
@@ -12,8 +12,9 @@
 //   1. membership: every lane evaluates the exact FLANN predicate d2 < r2 for all 32 candidates --
 //      broadcast 128-bit shared loads, four candidates per step in packed FP32 (FADD2/FMUL2/FFMA2) --
 //      into a 32-bit mask;
-//   2. votes: every lane walks the set bits of ITS mask in ascending order, two neighbours per iteration
-//      with the FP32 arithmetic of both packed, so the expensive vote runs only for real neighbours.
+//   2. votes: every lane walks the set bits of ITS mask in ascending candidate order, two neighbours per iteration
+//      with the FP32 arithmetic of both packed, so the expensive vote runs only for real neighbours (tiles some
+//      lane takes nearly whole are stepped through in order instead, every lane storing only its own votes).
 // Each query therefore sees its neighbours in ascending sorted position = canonical
 // (cell key, index) order and accumulates its votes sequentially in FP32 into a lane-private
 // histogram column hist[cell][lane] (bank == lane: conflict-free, no atomics).  That fixed order
@@ -37,8 +38,9 @@ namespace kpl {
 
 // One warp per block: its shared memory is released the moment it finishes (4 / 2 / 1 warps per block measured
 // 219.5 / -- / 204.0 ms on the 10 M-point scene, profiles/r1e_sweep_warps_per_block.txt).  __launch_bounds__(32) also
-// gives ptxas its best allocation: 64 registers without spills (bounds of 128 threads: 64 with spills, 180.0 ms;
-// (32, 28): 71 registers, 181.9 ms; (32): 178.0 ms).
+// gives ptxas its best allocation (round 1: 64 registers without spills; bounds of 128 threads: 64 with spills,
+// 180.0 ms; (32, 28): 71 registers, 181.9 ms; (32): 178.0 ms.  The round-2 kernel takes 72 registers, which still
+// fits the 28 blocks per SM that shared memory allows).
 static constexpr int FEAT_WARPS = 1;
 // Largest mask of a tile from which the in-order loop (16 iterations of ~120 instructions) beats the bit walk
 // (ceil(max / 2) iterations of ~137)
