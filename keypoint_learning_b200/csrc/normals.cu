@@ -241,7 +241,7 @@ template <int K>
 __global__ void __launch_bounds__(32) normals_knn_coop_kernel(const float4* __restrict__ s_pos, const uint32_t* __restrict__ skey,
                                                               const int32_t* __restrict__ cell_start, const float4* __restrict__ xyz,
                                                               GridDesc g, const int32_t* __restrict__ qorder, const int32_t* __restrict__ warp_starts,
-                                                              uint64_t one2, float vpx, float vpy, float vpz, float4* __restrict__ s_nrm,
+                                                              uint64_t one2, float ball_factor, float vpx, float vpy, float vpz, float4* __restrict__ s_nrm,
                                                               unsigned long long* __restrict__ counters)
 {
     __shared__ __align__(16) float tile[128];
@@ -260,14 +260,14 @@ __global__ void __launch_bounds__(32) normals_knn_coop_kernel(const float4* __re
     // First attempt with a BOUNDED list: most of the kernel's time went into list insertions (ncu: 65 % of the
     // instructions) because a list that starts at +inf takes the first 32 candidates whole and ~50 more while it
     // converges.  The lane's own cell tells the local density: with n_c points in a cell the surface crosses, a ball of
-    // r0^2 = 30 cell^2 / (pi n_c) holds ~30 of them.  The list starts full of sentinels (r0^2, no index), so only
+    // r0^2 = ball_factor cell^2 / n_c (ball_factor = 24 / pi) holds ~24 of them.  The list starts full of sentinels (r0^2, no index), so only
     // candidates inside that ball are ever inserted; if fewer than K turn up, the lane repeats the search unbounded.
     // Either way the list ends as the K smallest (d2, index) of everything scanned.
     float r0sq = CUDART_INF_F;
     if (active) {
         const int64_t cell = ((int64_t)cz * g.dim[1] + cy) * g.dim[0] + cx;
         const int nc = __ldg(cell_start + cell + 1) - __ldg(cell_start + cell);
-        const float guess = 9.55f * (float)g.cell * (float)g.cell / (float)max(nc, 1);
+        const float guess = ball_factor * (float)g.cell * (float)g.cell / (float)max(nc, 1);
         if (nc >= 8 && guess < 0.9f * (float)g.cell * (float)g.cell) r0sq = guess;     // else: unbounded from the start
     }
 #pragma unroll
@@ -454,10 +454,15 @@ cudaError_t launch_normals_knn(kpl_ctx* c, int64_t n)
     int blocks = (int)((n + 127) / 128);
     const float4* xyz = c->cur_xyz;
     if (normals_knn_uses_work_list(P)) {
+        float ball_factor = 7.6f;           // 24 / pi: ~24 expected points in the first attempt's ball (normals_knn_coop_kernel;
+                                            // 5.1 / 6.4 / 7.6 / 9.55 measured 8.23 / 6.91 / 6.72 / 6.93 ms on the 10 M scene)
+#ifdef KPL_EXPERIMENTS
+        if (const char* ev = getenv("KPL_KNN_BALL")) ball_factor = (float)atof(ev);
+#endif
         if (c->nwarps_norm > 0)
             normals_knn_coop_kernel<10><<<(unsigned)c->nwarps_norm, 32, 0, c->stream>>>(c->s_pos.p, c->key_b.p, c->cell_start.p, xyz, c->grid,
                                                                                         c->qorder_all.p, c->warp_starts_n.p,
-                                                                                        0x3F8000003F800000ull, P.viewpoint[0], P.viewpoint[1],
+                                                                                        0x3F8000003F800000ull, ball_factor, P.viewpoint[0], P.viewpoint[1],
                                                                                         P.viewpoint[2], c->s_nrm.p, c->counters.p);
     }
     else if (P.k_normals == 10)
